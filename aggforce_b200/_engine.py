@@ -1,0 +1,473 @@
+"""Frame-parallel statistics engine: device plumbing between the Python API and the kernels.
+
+PyTorch is used for device memory, streams and (optionally) ``torch.distributed``; all
+arithmetic on trajectory data happens in ``libagf_b200.so``.  Nothing here computes on the CPU
+beyond index bookkeeping (CSR lists of constraint groups, the set of unique matrix columns).
+
+Data model
+----------
+A trajectory array ``(n_frames, n_sites, 3)`` is wrapped in :class:`Frames`:
+  * numpy (host) input  -> uploaded in pieces on a side stream; kernels for piece *i* run while
+    piece *i+1* is in flight; the device copy is kept for later passes when it fits in HBM;
+  * torch CUDA input    -> used in place, results stay on the device.
+Frames are independent and every fitted quantity is a sum over frames, so under
+``frame_sharding`` each rank passes its own frame slice and the accumulators are combined with
+one NCCL all-reduce.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes as C
+import warnings
+from typing import Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import F32, F64, AgfError
+
+_PIECE_BYTES = 256 << 20  # host->device upload granularity
+_RESIDENT_FRACTION = 0.45  # keep a host array resident on the device if it fits in this share of free HBM
+
+
+# --------------------------------------------------------------------------------------
+# device / stream helpers
+# --------------------------------------------------------------------------------------
+def device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise AgfError("aggforce_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.float64:
+        return F64
+    raise AgfError(f"unsupported dtype {t.dtype}")
+
+
+_COPY_STREAMS: dict = {}
+
+
+def _copy_stream() -> torch.cuda.Stream:
+    dev = torch.cuda.current_device()
+    if dev not in _COPY_STREAMS:
+        _COPY_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    return _COPY_STREAMS[dev]
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    """Device -> pinned host copy, returned as a numpy array."""
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    host.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return host.numpy()
+
+
+def dev_i32(values: Sequence[int]) -> torch.Tensor:
+    return torch.as_tensor(np.asarray(values, dtype=np.int32), device=device())
+
+
+def dev_f64(values) -> torch.Tensor:
+    return torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64), device=device())
+
+
+# --------------------------------------------------------------------------------------
+# frame sharding across ranks
+# --------------------------------------------------------------------------------------
+class _Sharding:
+    enabled = False
+    group = None
+
+
+def _dist():
+    import torch.distributed as dist
+
+    return dist
+
+
+@contextlib.contextmanager
+def frame_sharding(enabled: bool = True, group=None):
+    """Within this context every fit treats its input as ONE RANK'S SLICE of the frames.
+
+    Partial Grams / pair moments / residual sums are all-reduced over ``group`` (default
+    process group) so every rank fits the same map, then applies it to its own frames.
+    """
+    prev = (_Sharding.enabled, _Sharding.group)
+    _Sharding.enabled, _Sharding.group = enabled, group
+    try:
+        yield
+    finally:
+        _Sharding.enabled, _Sharding.group = prev
+
+
+def sharded() -> bool:
+    if not _Sharding.enabled:
+        return False
+    dist = _dist()
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size(_Sharding.group) > 1
+
+
+def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
+    if sharded():
+        _dist().all_reduce(t, group=_Sharding.group)
+    return t
+
+
+def allreduce_min_(t: torch.Tensor) -> torch.Tensor:
+    if sharded():
+        dist = _dist()
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=_Sharding.group)
+    return t
+
+
+def allgather_host(arr: np.ndarray) -> List[np.ndarray]:
+    """Gather one small float64 array per rank (same shape everywhere)."""
+    if not sharded():
+        return [arr]
+    dist = _dist()
+    on_cuda = dist.get_backend(_Sharding.group) == "nccl"
+    t = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float64))
+    if on_cuda:
+        t = t.to(device())
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size(_Sharding.group))]
+    dist.all_gather(outs, t, group=_Sharding.group)
+    return [o.cpu().numpy() for o in outs]
+
+
+def global_count(local: int) -> int:
+    if not sharded():
+        return int(local)
+    dist = _dist()
+    on_cuda = dist.get_backend(_Sharding.group) == "nccl"
+    t = torch.tensor([int(local)], dtype=torch.int64, device=device() if on_cuda else "cpu")
+    dist.all_reduce(t, group=_Sharding.group)
+    return int(t.item())
+
+
+# --------------------------------------------------------------------------------------
+# trajectory arrays
+# --------------------------------------------------------------------------------------
+class Frames:
+    """A ``(n_frames, n_sites, 3)`` array as the kernels see it (see module docstring)."""
+
+    def __init__(self, array) -> None:
+        inner = getattr(array, "frames", None)
+        if isinstance(inner, Frames):  # agg._Shared: reuse the upload made by project_forces
+            array = inner
+        if isinstance(array, Frames):
+            self.__dict__ = array.__dict__  # share state (and the cached device copy)
+            return
+        self._dev: Optional[torch.Tensor] = None
+        self._host: Optional[np.ndarray] = None
+        if isinstance(array, torch.Tensor) and array.is_cuda:
+            if array.dtype not in (torch.float32, torch.float64):
+                array = array.to(torch.float64)
+            self._dev = array.contiguous()
+            shape = tuple(self._dev.shape)
+        else:
+            if isinstance(array, torch.Tensor):
+                array = array.numpy()
+            host = np.asarray(array)
+            if host.dtype not in (np.float32, np.float64):
+                host = host.astype(np.float64)
+            self._host = np.ascontiguousarray(host)
+            shape = self._host.shape
+        if len(shape) != 3 or shape[2] != 3:
+            raise ValueError(f"expected an array of shape (n_frames, n_sites, 3); got {shape}")
+        self.n_frames, self.n_sites = int(shape[0]), int(shape[1])
+
+    @property
+    def on_host(self) -> bool:
+        return self._host is not None
+
+    @property
+    def np_dtype(self):
+        if self._host is not None:
+            return self._host.dtype
+        return np.float32 if self._dev.dtype == torch.float32 else np.float64
+
+    @property
+    def torch_dtype(self):
+        return torch.float32 if self.np_dtype == np.float32 else torch.float64
+
+    def nbytes(self) -> int:
+        return self.n_frames * self.n_sites * 3 * np.dtype(self.np_dtype).itemsize
+
+    def _fits(self) -> bool:
+        free, _ = torch.cuda.mem_get_info()
+        return self.nbytes() <= _RESIDENT_FRACTION * free
+
+    def pieces(self, start: int = 0, stop: Optional[int] = None) -> Iterator[Tuple[int, torch.Tensor]]:
+        """Yield ``(first_frame, device_tensor)`` pieces covering frames [start, stop).
+
+        Every yielded tensor is safe to use on the current stream.  Host arrays are uploaded
+        on a side stream one piece ahead of the consumer.
+        """
+        stop = self.n_frames if stop is None else min(stop, self.n_frames)
+        if start >= stop:
+            return
+        if self._dev is not None:
+            yield start, self._dev[start:stop]
+            return
+        device()
+        frame_bytes = max(1, self.n_sites * 3 * np.dtype(self.np_dtype).itemsize)
+        per = max(4, (_PIECE_BYTES // frame_bytes) // 4 * 4)
+        whole = start == 0 and stop == self.n_frames and self._fits()
+        cs, cur = _copy_stream(), torch.cuda.current_stream()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            src = torch.from_numpy(self._host)
+        if whole:
+            full = torch.empty((self.n_frames, self.n_sites, 3), dtype=self.torch_dtype, device=device())
+        bounds = list(range(start, stop, per)) + [stop]
+        events = []
+        views = []
+
+        def launch(i: int) -> None:
+            a, b = bounds[i], bounds[i + 1]
+            dst = full[a:b] if whole else torch.empty((b - a, self.n_sites, 3), dtype=self.torch_dtype,
+                                                      device=device())
+            with torch.cuda.stream(cs):
+                dst.copy_(src[a:b], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(cs)
+            dst.record_stream(cs)
+            events.append(ev)
+            views.append(dst)
+
+        cs.wait_stream(cur)
+        n_pieces = len(bounds) - 1
+        launch(0)
+        for i in range(n_pieces):
+            if i + 1 < n_pieces:
+                launch(i + 1)
+            cur.wait_event(events[i])
+            yield bounds[i], views[i]
+            views[i] = None  # type: ignore[call-overload]
+        if whole:
+            self._dev = full
+
+    def resident(self) -> torch.Tensor:
+        """The whole array on the device (uploaded once and cached)."""
+        if self._dev is None:
+            if not self._fits():
+                raise AgfError("trajectory array does not fit in device memory; use pieces()")
+            for _ in self.pieces():
+                pass
+        return self._dev  # type: ignore[return-value]
+
+    def prefix(self, n: int) -> torch.Tensor:
+        """First ``n`` frames on the device."""
+        n = min(n, self.n_frames)
+        if self._dev is not None:
+            return self._dev[:n]
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return torch.from_numpy(self._host[:n]).to(device())
+
+
+# --------------------------------------------------------------------------------------
+# index structures
+# --------------------------------------------------------------------------------------
+def csr_from_labels(labels: np.ndarray, n_groups: int) -> Tuple[np.ndarray, np.ndarray]:
+    """CSR (ptr, members) listing, for every group g, the sites with ``labels == g`` in
+    increasing site order; negative labels are skipped."""
+    labels = np.asarray(labels, dtype=np.int64)
+    keep = np.nonzero(labels >= 0)[0]
+    order = keep[np.argsort(labels[keep], kind="stable")]
+    counts = np.bincount(labels[keep], minlength=n_groups)
+    ptr_ = np.zeros(n_groups + 1, dtype=np.int32)
+    np.cumsum(counts, out=ptr_[1:])
+    return ptr_, order.astype(np.int32)
+
+
+# --------------------------------------------------------------------------------------
+# kernel wrappers
+# --------------------------------------------------------------------------------------
+def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Tensor:
+    """Kernel (a): all-reduced, symmetrised second-moment matrix (device f64 [n_red, n_red])."""
+    ptr_, sites = csr_from_labels(col_of_site, n_red)
+    d_ptr, d_sites = dev_i32(ptr_), dev_i32(sites)
+    gram = torch.zeros((n_red, n_red), dtype=torch.float64, device=device())
+    for _, piece in frames.pieces():
+        _lib.call("agf_gram_linear", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites, ptr(d_ptr),
+                  ptr(d_sites), n_red, ptr(gram), stream_ptr())
+    allreduce_sum_(gram)
+    _lib.call("agf_symmetrize", ptr(gram), n_red, stream_ptr())
+    return gram
+
+
+class CompiledMap:
+    """Device-side form of a (n_cg, n_fg) matrix for kernel (d)."""
+
+    def __init__(self, matrix: np.ndarray, keep_zero_columns: bool) -> None:
+        m = np.asarray(matrix)
+        self.n_cg, self.n_fg = m.shape
+        self.out_f32 = m.dtype == np.float32
+        m64 = np.ascontiguousarray(m, dtype=np.float64)
+        nz_per_row = (m64 != 0).sum(axis=1)
+        nnz = int(nz_per_row.sum())
+        self.sparse = (not keep_zero_columns) and nnz <= 8 * self.n_cg and np.isfinite(m64).all()
+        if self.sparse:
+            rows, cols = np.nonzero(m64)
+            ptr_ = np.zeros(self.n_cg + 1, dtype=np.int32)
+            np.cumsum(np.bincount(rows, minlength=self.n_cg), out=ptr_[1:])
+            if nnz == 0:  # degenerate all-zero map: one explicit zero weight keeps the kernel simple
+                ptr_[1:] = 1
+                cols = np.zeros(1, dtype=np.int64)
+                weights = np.zeros(1)
+            else:
+                weights = m64[rows, cols]
+            self.row_ptr, self.row_sites, self.row_w = dev_i32(ptr_), dev_i32(cols), dev_f64(weights)
+            return
+        uniq, inverse = np.unique(m64.T, axis=0, return_inverse=True)
+        inverse = np.asarray(inverse).reshape(-1)
+        if not keep_zero_columns:
+            zero = np.nonzero(~uniq.any(axis=1))[0]
+            if zero.size and uniq.shape[0] > 1:
+                z = int(zero[0])
+                relabel = np.arange(uniq.shape[0])
+                relabel[z] = -1
+                relabel[z + 1 :] -= 1
+                inverse = relabel[inverse]
+                uniq = np.delete(uniq, z, axis=0)
+        ptr_, sites = csr_from_labels(inverse, uniq.shape[0])
+        self.n_ucol, self.nnz = int(uniq.shape[0]), int(sites.size)
+        self.ucol_ptr, self.ucol_sites = dev_i32(ptr_), dev_i32(sites)
+        self.umat_t = dev_f64(uniq)  # [n_ucol, n_cg]
+
+
+def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float, want_sumsq: bool = False,
+              start: int = 0, stop: Optional[int] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+    """Kernel (d).  Returns ``(out [T, n_cg, 3] device, sumsq device f64[1] | None, nan_flags int32[2])``."""
+    if frames.n_sites != cmap.n_fg:
+        raise ValueError(
+            f"map expects {cmap.n_fg} fine-grained sites but the array has {frames.n_sites}"
+        )
+    stop = frames.n_frames if stop is None else stop
+    out_dtype = torch.float32 if (cmap.out_f32 and frames.np_dtype == np.float32) else torch.float64
+    out = torch.empty((stop - start, cmap.n_cg, 3), dtype=out_dtype, device=device())
+    sumsq = torch.zeros(1, dtype=torch.float64, device=device()) if want_sumsq else None
+    flags = torch.zeros(2, dtype=torch.int32, device=device())
+    for t0, piece in frames.pieces(start, stop):
+        o = out[t0 - start : t0 - start + piece.shape[0]]
+        if cmap.sparse:
+            _lib.call("agf_map_apply_sparse", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites,
+                      ptr(cmap.row_ptr), ptr(cmap.row_sites), ptr(cmap.row_w), cmap.n_cg, ptr(o), dtype_code(o),
+                      ptr(sumsq), nan_mode, float(nan_atol), ptr(flags), stream_ptr())
+        else:
+            _lib.call("agf_map_apply", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites,
+                      ptr(cmap.ucol_ptr), ptr(cmap.ucol_sites), cmap.n_ucol, cmap.nnz, ptr(cmap.umat_t), cmap.n_cg,
+                      ptr(o), dtype_code(o), ptr(sumsq), nan_mode, float(nan_atol), ptr(flags), stream_ptr())
+    return out, sumsq, flags
+
+
+_SCREEN_FRAMES = 32
+_RESCREEN_FRAMES = 4096
+
+
+def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
+    """Kernel (c) with exact progressive pruning.  Returns ``(pairs int64 [P, 2], sd float64 [P])``
+    for every pair that survived pruning (the caller applies ``sd < threshold``)."""
+    if other is not None and other.n_frames != frames.n_frames:
+        raise ValueError("xyz and cross_xyz must have the same number of frames")
+    n, n_o = frames.n_sites, (frames.n_sites if other is None else other.n_sites)
+    t_local = frames.n_frames
+    t_total = global_count(t_local)
+    empty = (np.zeros((0, 2), dtype=np.int64), np.zeros(0))
+    if t_total == 0 or t_local == 0 and not sharded():
+        return empty
+    # a pair can only be a constraint if  M2_total <= thr^2 * T  (var = M2 / T < thr^2); partial
+    # M2 never exceeds the total, so anything above the (slightly widened) bound is pruned for good.
+    bound = float(threshold) ** 2 * t_total * (1.0 + 1e-6) + 1e-300
+    dev = device()
+
+    def other_piece(piece_t0: int, count: int) -> Optional[torch.Tensor]:
+        if other is None:
+            return None
+        return other.resident()[piece_t0 : piece_t0 + count]
+
+    # ---- stage 0: literal all-pairs pass over a short prefix
+    n0 = min(t_local, _SCREEN_FRAMES)
+    m2 = torch.full((n_o, n), float("inf"), dtype=torch.float64, device=dev)
+    if n0 > 0:
+        x0 = frames.prefix(n0)
+        o0 = None if other is None else other.prefix(n0)
+        if o0 is not None and o0.dtype != x0.dtype:
+            o0 = o0.to(x0.dtype)
+        _lib.call("agf_pair_screen", ptr(x0), ptr(o0), dtype_code(x0), n0, n, n_o, ptr(m2), stream_ptr())
+        alive = (m2 <= bound).to(torch.uint8)
+    else:
+        alive = torch.ones((n_o, n), dtype=torch.uint8, device=dev)
+        if other is None:
+            alive = torch.triu(alive, diagonal=1)
+    allreduce_min_(alive)
+    pairs = torch.nonzero(alive).to(torch.int32).contiguous()  # [P, 2] = (i over other, j over xyz)
+    del m2, alive
+    n_pairs = int(pairs.shape[0])
+    if n_pairs == 0:
+        return empty
+
+    # ---- stage 1..: stream all frames for the survivors
+    shift = torch.zeros(n_pairs, dtype=torch.float64, device=dev)
+    if t_local > 0:
+        x0 = frames.prefix(1)
+        o0 = None if other is None else other.prefix(1).to(x0.dtype)
+        _lib.call("agf_pair_first", ptr(x0), ptr(o0), dtype_code(x0), n, n_o, ptr(pairs), n_pairs, ptr(shift),
+                  stream_ptr())
+    acc = torch.zeros((n_pairs, 2), dtype=torch.float64, device=dev)
+
+    def run(a: int, b: int) -> None:
+        for t0, piece in frames.pieces(a, b):
+            o = other_piece(t0, piece.shape[0])
+            if o is not None and o.dtype != piece.dtype:
+                o = o.to(piece.dtype)
+            _lib.call("agf_pair_moments", ptr(piece), ptr(o), dtype_code(piece), piece.shape[0], n, n_o,
+                      ptr(pairs), int(pairs.shape[0]), ptr(shift), ptr(acc), stream_ptr())
+
+    done = 0
+    if t_local > 4 * _RESCREEN_FRAMES and n_pairs > 4 * max(n, n_o) and not sharded():
+        run(0, _RESCREEN_FRAMES)
+        done = _RESCREEN_FRAMES
+        m2p = acc[:, 1] - acc[:, 0] ** 2 / done
+        keep = torch.nonzero(m2p <= bound).reshape(-1)
+        pairs, shift, acc = pairs[keep].contiguous(), shift[keep].contiguous(), acc[keep].contiguous()
+        n_pairs = int(pairs.shape[0])
+        if n_pairs == 0:
+            return empty
+    run(done, t_local)
+
+    # ---- combine (Chan) across ranks in float64 on the host; P is O(n)
+    host = to_host(torch.cat([acc, shift[:, None]], dim=1))
+    s1, s2, c = host[:, 0], host[:, 1], host[:, 2]
+    if t_local > 0:
+        mean = c + s1 / t_local
+        m2_local = s2 - s1 * s1 / t_local
+    else:
+        mean, m2_local = np.zeros(n_pairs), np.zeros(n_pairs)
+    parts = allgather_host(np.concatenate([[float(t_local)], mean, m2_local]))
+    cnt, mu, m2t = 0.0, np.zeros(n_pairs), np.zeros(n_pairs)
+    for part in parts:
+        tb, mb, m2b = part[0], part[1 : 1 + n_pairs], part[1 + n_pairs :]
+        if tb == 0:
+            continue
+        delta = mb - mu
+        tot = cnt + tb
+        m2t = m2t + m2b + delta * delta * cnt * tb / tot
+        mu = mu + delta * tb / tot
+        cnt = tot
+    with np.errstate(invalid="ignore"):
+        sd = np.sqrt(np.maximum(m2t, 0.0) / cnt)
+    sd[np.isnan(m2t)] = np.nan
+    return to_host(pairs).astype(np.int64), sd

@@ -1,0 +1,211 @@
+"""Array maps: ``LinearMap`` (kernel (d)) and ``CLAMap``.
+
+API of the reference's ``src/aggforce/map/core.py`` (LinearMap :46-317, CLAMap :320-430).
+``LinearMap.__call__`` is one fused kernel launch: matrix product, NaN probe, NaN protocol.
+Host (numpy) input returns numpy, CUDA tensors return CUDA tensors.
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Callable, Dict, Final, List, Literal, Optional, Tuple, Union
+
+import numpy as np
+import torch
+
+from .. import _engine
+from ..util import trjdot
+
+
+class _Taggable:
+    """Holds a free-form ``tags`` dictionary (fit logs such as feature coefficients)."""
+
+    def __init__(self, tags: Union[None, Dict[str, str]]) -> None:
+        self.tags = {} if tags is None else tags
+
+
+class LinearMap:
+    """Linear fine-grained -> coarse-grained map defined by its ``standard_matrix``.
+
+    ``mapping`` is either a 2-D array ``(n_cg, n_fg)`` of coefficients, or a list of lists of
+    fine-grained indices (each bead the unweighted mean of its sites; needs ``n_fg_sites``).
+
+    ``handle_nans`` (True | False | "safe"): with NaN handling on, NaN entries of the input are
+    ignored wherever the map gives them zero weight and a ``ValueError`` is raised if the
+    result would depend on them (tolerance ``nan_check_threshold``).  Unlike the reference the
+    caller's array is never modified, i.e. True behaves like "safe".
+    """
+
+    n_dim: Final = 3
+
+    def __init__(
+        self,
+        mapping: Union[List[List[int]], np.ndarray],
+        n_fg_sites: Union[int, None] = None,
+        handle_nans: Union[bool, Literal["safe"]] = True,
+        nan_check_threshold: float = 1e-6,
+    ) -> None:
+        if isinstance(mapping, torch.Tensor):
+            mapping = mapping.detach().cpu().numpy()
+        if isinstance(mapping, np.ndarray) and mapping.ndim == 2:
+            if n_fg_sites is not None:
+                raise ValueError("Cannot specify n_fg_sites when mapping is ArrayLike. Let it be inferred.")
+            matrix = mapping
+        elif hasattr(mapping, "__iter__"):
+            if n_fg_sites is None:
+                raise ValueError("n_fg_sites is required when mapping is a list of index lists.")
+            groups = [list(g) for g in mapping]
+            matrix = np.zeros((len(groups), n_fg_sites))
+            for bead, members in enumerate(groups):
+                row = np.zeros(n_fg_sites)
+                row[members] = 1 / len(members)
+                matrix[bead, :] = row
+        else:
+            raise ValueError(f"Cannot understand mapping {mapping}.")
+        self._standard_matrix = matrix
+        self.handle_nans = handle_nans
+        if self.handle_nans and not np.all(np.isfinite(matrix)):
+            raise ValueError("NaN checking can only be performed if standard_matrix is itself finite.")
+        self.nan_check_threshold = nan_check_threshold
+        self._compiled: Optional[Tuple[bytes, _engine.CompiledMap]] = None
+
+    # ------------------------------------------------------------------ descriptors
+    @property
+    def standard_matrix(self) -> np.ndarray:
+        return self._standard_matrix
+
+    @property
+    def n_cg_sites(self) -> int:
+        return self._standard_matrix.shape[0]
+
+    @property
+    def n_fg_sites(self) -> int:
+        return self._standard_matrix.shape[1]
+
+    @property
+    def participating_fg(self) -> List[List[int]]:
+        """For every bead, the fine-grained sites with a positive coefficient."""
+        table: List[List[int]] = [[] for _ in range(self.n_cg_sites)]
+        for cg, fg in zip(*np.nonzero(self._standard_matrix > 0)):
+            table[cg].append(fg)
+        return table
+
+    def close_to_identity(self, threshold: float = 1e-8) -> bool:
+        m = self._standard_matrix
+        if m.shape[0] != m.shape[1]:
+            return False
+        return bool(np.sqrt(((np.identity(m.shape[0], dtype=m.dtype) - m) ** 2).sum()) <= threshold)
+
+    # ------------------------------------------------------------------ application
+    def _compile(self) -> _engine.CompiledMap:
+        digest = hashlib.blake2b(np.ascontiguousarray(self._standard_matrix).tobytes(), digest_size=16).digest()
+        digest += str(self._standard_matrix.dtype).encode() + bytes([bool(self.handle_nans)])
+        if self._compiled is None or self._compiled[0] != digest:
+            # plain mode keeps all-zero columns so that 0 * NaN = NaN exactly as numpy computes it
+            self._compiled = (digest, _engine.CompiledMap(self._standard_matrix,
+                                                          keep_zero_columns=not self.handle_nans))
+        return self._compiled[1]
+
+    def _apply(self, points, want_sumsq: bool = False):
+        frames = _engine.Frames(points)
+        out, sumsq, flags = _engine.map_apply(
+            frames, self._compile(), nan_mode=1 if self.handle_nans else 0,
+            nan_atol=self.nan_check_threshold, want_sumsq=want_sumsq,
+        )
+        if self.handle_nans and int(flags[1].item()) != 0:
+            raise ValueError(
+                "NaN handling is on and results seem to depend on NaN "
+                "positions in input array. Check input and standard_matrix."
+            )
+        result = _engine.to_host(out) if frames.on_host else out
+        return result, sumsq
+
+    def __call__(self, points):
+        """Map ``(n_steps, n_fg_sites, 3)`` points to ``(n_steps, n_cg_sites, 3)``."""
+        return self._apply(points)[0]
+
+    def apply_with_sumsq(self, points):
+        """``(mapped, sum(mapped**2))`` from one kernel launch (the residual of agg.py:291-297)."""
+        mapped, sumsq = self._apply(points, want_sumsq=True)
+        return mapped, float(sumsq.item())
+
+    def flat_call(self, flattened):
+        """Apply to ``(n_frames, n_fg_sites*3)`` input, returning ``(n_frames, n_cg_sites*3)``."""
+        shape = tuple(flattened.shape)
+        if len(shape) == 3:
+            raise ValueError(f"Expected array of rank 2; got array with shape {shape}.")
+        if shape[1] % self.n_dim != 0:
+            raise ValueError(f"Array of shape {shape} can't be reshaped with dim of {self.n_dim}.")
+        mapped = self(flattened.reshape((shape[0], shape[1] // self.n_dim, self.n_dim)))
+        return mapped.reshape((mapped.shape[0], mapped.shape[1] * mapped.shape[2]))
+
+    # ------------------------------------------------------------------ algebra
+    def _like(self, matrix: np.ndarray) -> "LinearMap":
+        return self.__class__(mapping=matrix, handle_nans=self.handle_nans,
+                              nan_check_threshold=self.nan_check_threshold)
+
+    @property
+    def T(self) -> "LinearMap":
+        return LinearMap(mapping=self._standard_matrix.T, handle_nans=self.handle_nans,
+                         nan_check_threshold=self.nan_check_threshold)
+
+    def __matmul__(self, lm: "LinearMap", /) -> "LinearMap":
+        return LinearMap(mapping=self._standard_matrix @ lm.standard_matrix, handle_nans=self.handle_nans,
+                         nan_check_threshold=self.nan_check_threshold)
+
+    def __rmul__(self, c: float, /) -> "LinearMap":
+        return LinearMap(mapping=c * self._standard_matrix, handle_nans=self.handle_nans,
+                         nan_check_threshold=self.nan_check_threshold)
+
+    def __add__(self, lm: "LinearMap", /) -> "LinearMap":
+        return LinearMap(mapping=self._standard_matrix + lm.standard_matrix, handle_nans=self.handle_nans,
+                         nan_check_threshold=self.nan_check_threshold)
+
+    def astype(self, *args, **kwargs) -> "LinearMap":
+        """Instance whose matrix is cast with ``numpy.astype(*args, **kwargs)``."""
+        return self._like(self._standard_matrix.astype(*args, **kwargs))
+
+
+class CLAMap(_Taggable):
+    """Co-local affine map ``x_t -> A(y_t) x_t + b(y_t)`` (output of featurised fits).
+
+    ``scale(copoints) -> (n_steps, n_cg, n_fg)`` and ``trans(copoints) -> (n_steps, n_cg, 3)``
+    are callables; with ``zeroes_check`` they are probed once on a zero frame to validate /
+    infer ``n_cg_sites`` (reference core.py:381-394).
+    """
+
+    n_dim: Final = 3
+
+    def __init__(
+        self,
+        scale: Callable,
+        trans: Callable,
+        n_fg_sites: int,
+        n_cg_sites: Optional[int] = None,
+        zeroes_check: bool = True,
+        tags: Optional[Dict[str, str]] = None,
+    ) -> None:
+        super().__init__(tags=tags)
+        if zeroes_check:
+            probe = np.zeros((1, n_fg_sites, self.n_dim))
+            mapped = trjdot(probe, scale(probe)) + trans(probe)
+            if n_cg_sites is None:
+                n_cg_sites = mapped.shape[1]
+            elif n_cg_sites != mapped.shape[1]:
+                raise ValueError("n_cg_sites did not match results from zero test")
+        elif n_cg_sites is None:
+            raise ValueError("If n_cg_sites is not set, zeroes_check must be truthy.")
+        self._n_cg_sites: Final = n_cg_sites
+        self._n_fg_sites: Final = n_fg_sites
+        self.scale: Final = scale
+        self.trans: Final = trans
+
+    @property
+    def n_cg_sites(self) -> int:
+        return self._n_cg_sites
+
+    @property
+    def n_fg_sites(self) -> int:
+        return self._n_fg_sites
+
+    def __call__(self, points, copoints):
+        return trjdot(points, self.scale(copoints)) + self.trans(copoints)

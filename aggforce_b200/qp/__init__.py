@@ -1,0 +1,4 @@
+"""Quadratic-programming based force-map optimisation."""
+from .qplinear import qp_linear_map, qp_form, make_bond_constraint_matrix  # noqa: F401
+from .basicagg import constraint_aware_uni_map  # noqa: F401
+from .solver import DEFAULT_SOLVER_OPTIONS, solve_equality_qp  # noqa: F401

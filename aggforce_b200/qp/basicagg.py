@@ -1,0 +1,32 @@
+"""Uniform (0/1) force map that respects constraints; pure index logic on the host.
+
+Drop-in for the reference's ``src/aggforce/qp/basicagg.py:11-62``.
+"""
+from __future__ import annotations
+
+from typing import Union
+
+import numpy as np
+
+from ..constraints import Constraints, reduce_constraint_sets
+from ..map import LinearMap, SeperableTMap
+from ..trajectory import ForcesTrajectory
+
+
+def constraint_aware_uni_map(
+    traj: ForcesTrajectory,  # noqa: ARG001
+    coord_map: LinearMap,
+    constraints: Union[None, Constraints] = None,
+) -> SeperableTMap:
+    """Each bead sums, unweighted, the forces of its own sites and of every site constrained
+    (transitively) to one of them.  ``traj`` is ignored."""
+    matrix = np.asarray(coord_map.standard_matrix)
+    groups = [sorted(g) for g in reduce_constraint_sets(set() if constraints is None else constraints)]
+    out = np.zeros_like(matrix)
+    for bead, row in enumerate(matrix):
+        members = set(np.nonzero(row)[0].tolist())
+        for g in groups:
+            if members.intersection(g):
+                members.update(g)
+        out[bead, sorted(members)] = 1.0
+    return SeperableTMap(coord_map=coord_map, force_map=LinearMap(out))

@@ -1,0 +1,102 @@
+"""Optimal static linear force map -- kernel (a) plus the host QP.
+
+Drop-in for the reference's ``src/aggforce/qp/qplinear.py``.
+"""
+from __future__ import annotations
+
+from typing import Union
+
+import numpy as np
+
+from .. import _engine
+from ..constraints import Constraints, constraint_lookup_dict, reduce_constraint_sets
+from ..map import LinearMap, SeperableTMap
+from ..trajectory import ForcesTrajectory
+from .solver import DEFAULT_SOLVER_OPTIONS, SolverOptions, solve
+
+
+def reduced_columns(n_sites: int, constraints: Constraints) -> np.ndarray:
+    """Reduced-coefficient column of every site (``int64[n_sites]``).
+
+    Sites constrained together share one coefficient.  Column order follows the reference
+    (``qplinear.py:157-163``): walking the sites in increasing order, every site that is not a
+    dependent member of a merged constraint group opens the next column; dependents reuse
+    their anchor's (the smallest index of their group).
+    """
+    anchor_of = constraint_lookup_dict(reduce_constraint_sets(constraints))
+    cols = np.full(n_sites, -1, dtype=np.int64)
+    free = [s for s in range(n_sites) if s not in anchor_of]
+    cols[free] = np.arange(len(free))
+    for site, anchor in anchor_of.items():
+        cols[site] = cols[anchor]
+    return cols
+
+
+def make_bond_constraint_matrix(n_sites: int, constraints: Constraints) -> np.ndarray:
+    """One-hot ``(n_sites, n_reduced)`` matrix expanding reduced coefficients to all sites."""
+    cols = reduced_columns(n_sites, constraints)
+    mat = np.zeros((n_sites, int(cols.max()) + 1 if n_sites else 0))
+    mat[np.arange(n_sites), cols] = 1
+    return mat
+
+
+def qp_form(target: np.ndarray) -> np.ndarray:
+    """``(n_steps, n_sites, 3) -> (n_steps*3, n_sites)`` with rows ordered (step, dim)."""
+    mixed = np.swapaxes(target, 1, 2)
+    return np.reshape(mixed, (mixed.shape[0] * mixed.shape[1], -1))
+
+
+def force_gram(forces, n_sites: int, constraints: Constraints):
+    """``(gram (n_red, n_red) float64 on the host, columns)`` -- the QP objective of
+    ``qplinear.py:66-71``, accumulated on the GPU and all-reduced across frame shards."""
+    cols = reduced_columns(n_sites, constraints)
+    n_red = int(cols.max()) + 1
+    gram = _engine.gram_linear(_engine.Frames(forces), cols, n_red)
+    return _engine.to_host(gram), cols
+
+
+def qp_linear_map(
+    traj: ForcesTrajectory,
+    coord_map: LinearMap,
+    constraints: Union[None, Constraints] = None,
+    l2_regularization: float = 0.0,
+    solver_args: SolverOptions = DEFAULT_SOLVER_OPTIONS,
+) -> SeperableTMap:
+    """Linear force map minimising the mean squared mapped force.
+
+    Same contract as the reference: constrained sites share coefficients, the map satisfies
+    ``coord_map @ W.T = I`` on the reduced coefficients, ``l2_regularization`` penalises the
+    expanded coefficient vector and is relative to the *unnormalised* frame sum.
+    """
+    if constraints is None:
+        constraints = set()
+    n_fg = coord_map.n_fg_sites
+    if traj.forces.shape[1] != n_fg:
+        raise ValueError("coord_map and forces disagree on the number of fine-grained sites.")
+    qp_mat, cols = force_gram(traj.forces, n_fg, constraints)
+    n_red = qp_mat.shape[0]
+    group_size = np.bincount(cols, minlength=n_red).astype(np.float64)
+    if l2_regularization > 0.0:
+        qp_mat[np.diag_indices(n_red)] += l2_regularization * group_size  # l2 * C'C
+    # A = coord_map @ C : sum the coordinate-map columns of every group
+    cmat = np.asarray(coord_map.standard_matrix, dtype=np.float64)
+    a_mat = np.zeros((coord_map.n_cg_sites, n_red))
+    np.add.at(a_mat.T, cols, cmat.T)
+    backend = dict(solver_args or {}).get("backend", "exact")
+    if backend == "exact":
+        sol = solve(qp_mat, a_mat, np.eye(coord_map.n_cg_sites), solver_args)
+        if sol is None:
+            raise ValueError("Map optimization failed.")
+        reduced = sol.T
+    else:
+        rows = []
+        for bead in range(coord_map.n_cg_sites):
+            target = np.zeros(coord_map.n_cg_sites)
+            target[bead] = 1
+            x = solve(qp_mat, a_mat, target, solver_args)
+            if x is None:
+                raise ValueError("Map optimization failed.")
+            rows.append(x)
+        reduced = np.stack(rows)
+    force_map = LinearMap(reduced[:, cols])
+    return SeperableTMap(coord_map=coord_map, force_map=force_map)

@@ -1,0 +1,71 @@
+"""Host-side equality-constrained QP:  min 1/2 x'Px  s.t.  Ax = b.
+
+The reference hands this problem to ``qpsolvers.solve_qp(..., solver="osqp")`` once per bead
+(``qplinear.py:83-85``, ``featlinearmap.py:375-381``).  It has no inequality constraints and no
+linear term, so the minimiser is available in closed form; solving it exactly (one Cholesky
+factorisation shared by all beads / right-hand sides) is what the parity tolerance "weights
+within 1e-6" is defined against.  ``qpsolvers`` is used instead when the caller
+asks for it with ``solver_args={"backend": "qpsolvers", ...}`` and the package is importable.
+"""
+from __future__ import annotations
+
+from typing import Any, Mapping, Optional
+
+import numpy as np
+import scipy.linalg as sl
+import scipy.sparse as ss
+
+DEFAULT_SOLVER_OPTIONS = {
+    "solver": "osqp",
+    "eps_abs": 1e-7,
+    "max_iter": int(1e3),
+    "polish": True,
+    "polish_refine_iter": 10,
+}
+SolverOptions = Mapping[str, Any]
+
+
+def _dense(m) -> np.ndarray:
+    return m.toarray() if ss.issparse(m) else np.asarray(m, dtype=np.float64)
+
+
+def solve_equality_qp(P, A, b) -> Optional[np.ndarray]:
+    """Exact minimiser; ``b`` may be a vector or a matrix with one column per problem.
+
+    ``x = P^-1 A' (A P^-1 A')^+ b`` when ``P`` is positive definite, otherwise a null-space
+    solve (``x = x0 + Z w`` with ``Z`` spanning ``ker A``).  Returns ``None`` if the problem is
+    infeasible or non-finite, mirroring ``solve_qp``'s failure value.
+    """
+    P, A, b = _dense(P), _dense(A), np.asarray(b, dtype=np.float64)
+    if not (np.isfinite(P).all() and np.isfinite(A).all() and np.isfinite(b).all()):
+        return None
+    try:
+        cf = sl.cho_factor(P, lower=True, check_finite=False)
+        pia = sl.cho_solve(cf, A.T, check_finite=False)
+        s = A @ pia
+        lam = np.linalg.lstsq(s, b, rcond=None)[0]
+        x = pia @ lam
+    except (sl.LinAlgError, np.linalg.LinAlgError):
+        _, sv, vt = np.linalg.svd(A, full_matrices=True)
+        rank = int((sv > sv.max() * 1e-12).sum()) if sv.size else 0
+        x0 = np.linalg.lstsq(A, b, rcond=None)[0]
+        z = vt[rank:].T
+        if z.shape[1] == 0:
+            x = x0
+        else:
+            w = np.linalg.lstsq(z.T @ P @ z, -(z.T @ (P @ x0)), rcond=None)[0]
+            x = x0 + z @ w
+    resid = A @ x - b
+    if not np.isfinite(x).all() or np.abs(resid).max(initial=0.0) > 1e-6 * max(1.0, np.abs(b).max(initial=0.0)):
+        return None
+    return x
+
+
+def solve(P, A, b, solver_args: Optional[SolverOptions] = None) -> Optional[np.ndarray]:
+    """Dispatch: exact solve by default, ``qpsolvers`` on request (vector ``b`` only)."""
+    opts = dict(solver_args or {})
+    if opts.pop("backend", "exact") == "qpsolvers":
+        from qpsolvers import solve_qp  # type: ignore[import-not-found]
+
+        return solve_qp(P=P, q=np.zeros(P.shape[0]), A=A, b=b, **opts)
+    return solve_equality_qp(P, A, b)

@@ -1,0 +1,153 @@
+/*
+ * agf_b200.h -- C ABI of libagf_b200.so: the sm_100a kernels behind aggforce's
+ * frame-parallel statistics path.
+ *
+ * The reference (noegroup/aggforce) is pure Python and has no FFI; the interface each
+ * entry point replaces is therefore a handful of numpy lines, cited per function as
+ * <file>:<lines> relative to the reference root.  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add at each of those sites.
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types in any signature;
+ *   - every pointer documented "device" is a CUDA device pointer owned by the caller,
+ *     "host" is ordinary (ideally pinned) host memory; the library never frees or
+ *     retains caller memory;
+ *   - sizes are int64_t / int32_t, streams are passed as void* (a cudaStream_t);
+ *   - functions are stream-ordered and re-entrant per (device, stream); the only global
+ *     state is a thread-local error string;
+ *   - return value: 0 = OK, negative = error (see AGF_E_*), message via agf_last_error();
+ *   - accumulating outputs are documented "(+=)": the caller zeroes them once and may
+ *     call repeatedly over frame chunks / keep partial sums per rank and all-reduce them.
+ *   - dtype codes: AGF_F32 = 0, AGF_F64 = 1.
+ */
+#ifndef AGF_B200_H
+#define AGF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGF_VERSION 100
+
+#define AGF_F32 0
+#define AGF_F64 1
+
+#define AGF_OK 0
+#define AGF_E_INVALID (-1)   /* bad argument (shape, dtype, null pointer, alignment) */
+#define AGF_E_CUDA (-2)      /* a CUDA runtime call or kernel launch failed */
+#define AGF_E_UNSUPPORTED (-3)
+#define AGF_E_NAN (-4)       /* NaN protocol violated (result depends on NaN positions) */
+
+int agf_version(void);
+const char* agf_last_error(void);
+/* Number of SMs of the current device (grid sizing / reporting). */
+int agf_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * (a) linear second-moment Gram.
+ * Replaces  src/aggforce/qp/qplinear.py:66-71
+ *     reg_mat = matmul(qp_form(forces), con_mat);  qp_mat = matmul(reg_mat.T, reg_mat)
+ * with the one-hot con_mat given as a CSR list of the sites of every reduced column
+ * (src/aggforce/qp/qplinear.py:147-163).
+ *
+ *   forces     device, [n_frames, n_sites, 3] contiguous, dtype f32 or f64
+ *   col_ptr    device int32 [n_red + 1], col_sites device int32 [col_ptr[n_red]]
+ *   gram       device f64 [n_red, n_red] row-major, UPPER BLOCK-TRIANGLE (+=).  Call
+ *              agf_symmetrize() once after the last chunk (and after any all-reduce).
+ * FP64 tensor-core (DMMA) SYRK; inputs staged in shared memory with 1-D TMA bulk copies.
+ */
+int agf_gram_linear(const void* forces, int dtype, int64_t n_frames, int32_t n_sites,
+                    const int32_t* col_ptr, const int32_t* col_sites, int32_t n_red,
+                    double* gram, void* stream);
+
+/* gram[j, i] = gram[i, j] for i < j (device f64 [n, n]). */
+int agf_symmetrize(double* gram, int32_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (d) map application, fused with the NaN probe and the residual reduction.
+ * Replaces  src/aggforce/util.py:119-124  (einsum "tfd,cf->tcd")
+ *           src/aggforce/map/core.py:13-16,219-240 (NaN probe + NaN protocol)
+ *           src/aggforce/agg.py:291-297 (mean(x**2), returned as a running sum)
+ *
+ * Dense form: the (n_cg, n_fg) matrix is passed column-compressed -- sites whose matrix
+ * columns are identical share one "unique column" u (for an optimised force map these are
+ * exactly the constraint groups); all-zero columns may be dropped when nan_mode == 1.
+ *   points     device [n_frames, n_sites, 3], dtype in_dtype
+ *   ucol_ptr   device int32 [n_ucol + 1], ucol_sites device int32 [nnz]: sites of column u
+ *   umat_t     device f64 [n_ucol, n_cg] row-major: TRANSPOSE of the matrix restricted to
+ *              the unique columns
+ *   out        device [n_frames, n_cg, 3], dtype out_dtype
+ *   sumsq      device f64 [1] (+=) sum of out**2 (values as stored), or NULL
+ *   nan_mode   0: plain arithmetic (NaN propagates, 0*NaN = NaN as in numpy)
+ *              1: reference NaN protocol -- NaN inputs count as 0; nan_flags[0] is set to 1
+ *                 when any NaN was seen and nan_flags[1] to 1 when a result would change
+ *                 beyond  atol + 1e-5*|result|  if the NaNs were -1 instead (core.py:230).
+ *   nan_flags  device int32 [2] (|=), required when nan_mode == 1
+ */
+int agf_map_apply(const void* points, int in_dtype, int64_t n_frames, int32_t n_sites,
+                  const int32_t* ucol_ptr, const int32_t* ucol_sites, int32_t n_ucol, int32_t nnz,
+                  const double* umat_t, int32_t n_cg, void* out, int out_dtype, double* sumsq,
+                  int nan_mode, double nan_atol, int32_t* nan_flags, void* stream);
+
+/* Sparse-row form for slice / uniform maps (a few non-zeros per bead): CSR rows
+ *   row_ptr device int32 [n_cg + 1], row_sites device int32 [nnz], row_weights device f64 [nnz].
+ * Only the referenced sites are read.  Same outputs / NaN semantics as agf_map_apply with
+ * nan_mode 1 restricted to the referenced sites.
+ */
+int agf_map_apply_sparse(const void* points, int in_dtype, int64_t n_frames, int32_t n_sites,
+                         const int32_t* row_ptr, const int32_t* row_sites, const double* row_weights,
+                         int32_t n_cg, void* out, int out_dtype, double* sumsq, int nan_mode,
+                         double nan_atol, int32_t* nan_flags, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * (c) pair-distance moments for constraint detection.
+ * Replaces  src/aggforce/util.py:64-70 (all-pairs displacement + norm) and
+ *           src/aggforce/constraints/constfinder.py:47 (variance over frames).
+ *
+ * For each listed pair p = (i over `other`, j over `xyz`):  d_t = |xyz[t, j] - other[t, i]|
+ * in float64;  acc[2p] += sum_t (d_t - shift[p]),  acc[2p+1] += sum_t (d_t - shift[p])^2.
+ *   xyz        device [n_frames, n_sites, 3]; other: device [n_frames, n_other, 3] or NULL
+ *              (NULL = same array, the reference's cross_xyz=None)
+ *   pairs      device int32 [n_pairs, 2] (i, j)
+ *   shift      device f64 [n_pairs] (any value near the mean distance; see agf_pair_first)
+ *   acc        device f64 [n_pairs, 2] (+=)
+ */
+int agf_pair_moments(const void* xyz, const void* other, int dtype, int64_t n_frames,
+                     int32_t n_sites, int32_t n_other, const int32_t* pairs, int64_t n_pairs,
+                     const double* shift, double* acc, void* stream);
+
+/* shift[p] = distance of pair p in frame 0 of the given arrays. */
+int agf_pair_first(const void* xyz, const void* other, int dtype, int32_t n_sites,
+                   int32_t n_other, const int32_t* pairs, int64_t n_pairs, double* shift,
+                   void* stream);
+
+/* All-pairs screening pass: for every (i, j) -- i < j when other == NULL, all n_other x
+ * n_sites otherwise -- the sum of squared deviations of d_t from its mean over the given
+ * frames, m2[i * n_sites + j] (device f64, overwritten; entries not visited hold +inf).
+ * Used for exact progressive pruning: M2 over a subset of frames never exceeds M2 over
+ * all frames, so a pair whose partial M2 already exceeds threshold^2 * T_total cannot be
+ * a constraint.
+ */
+int agf_pair_screen(const void* xyz, const void* other, int dtype, int64_t n_frames,
+                    int32_t n_sites, int32_t n_other, double* m2, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Synthetic trajectory generator for benchmarks and tests (counter-based, so any
+ * frame range of any sharding reproduces the same data):  frame0 = global index of the
+ * first generated frame.  See aggforce_b200/synth.py for the model.
+ *   ref_pos    device f32 [n_sites, 3]; parent device int32 [n_sites] (-1 for heavy atoms)
+ *   bond_len   device f32 [n_sites]
+ *   coords/forces  device f32 [n_frames, n_sites, 3] (overwritten); either may be NULL
+ */
+int agf_synth_frames(const float* ref_pos, const int32_t* parent, const float* bond_len,
+                     int32_t n_sites, int64_t frame0, int64_t n_frames, uint64_t seed,
+                     float pos_sigma, float force_sigma, float h_coupling, float* coords,
+                     float* forces, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGF_B200_H */
