@@ -71,9 +71,8 @@ def project_forces(
         else:
             raise ValueError(f"If constrained_inds is {PROJECT_FORCES_CNSTR_AUTO}, coords cannot be None.")
     # one device upload per array, shared by the fit and the application passes
-    coords_in = _engine.Frames(coords) if isinstance(coords, np.ndarray) else coords
-    forces_in = _engine.Frames(forces) if isinstance(forces, np.ndarray) else forces
     t = Trajectory(coords=coords, forces=forces)
+    coords_in, forces_in = _engine.Frames(coords), _engine.Frames(forces)
     traj_map: TMap = method(
         traj=Trajectory(coords=_Shared(coords, coords_in), forces=_Shared(forces, forces_in)),
         coord_map=coord_map,
