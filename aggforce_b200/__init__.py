@@ -10,4 +10,4 @@ from .agg import project_forces  # noqa: F401
 from .constraints import guess_pairwise_constraints  # noqa: F401
 from .qp import qp_linear_map, constraint_aware_uni_map  # noqa: F401
 from .map import LinearMap  # noqa: F401
-from ._engine import frame_sharding  # noqa: F401
+from ._engine import frame_sharding, Frames  # noqa: F401

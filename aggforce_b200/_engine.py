@@ -192,6 +192,13 @@ class Frames:
         return self._host is not None
 
     @property
+    def shape(self) -> Tuple[int, int, int]:
+        return (self.n_frames, self.n_sites, 3)
+
+    def __len__(self) -> int:
+        return self.n_frames
+
+    @property
     def np_dtype(self):
         if self._host is not None:
             return self._host.dtype

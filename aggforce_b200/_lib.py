@@ -69,5 +69,34 @@ def check(status: int, what: str) -> None:
         raise AgfError(f"{what} failed with status {status}: {msg}")
 
 
+# --- launch accounting / per-kernel timing (used by bench.py; off by default)
+LAUNCHES = {"count": 0}
+_TIMING = {"on": False, "records": []}
+
+
+def timing(enabled: bool) -> None:
+    """Record a CUDA-event pair around every entry point (on the launching stream)."""
+    _TIMING["on"] = enabled
+    _TIMING["records"] = []
+
+
+def timing_records():
+    """[(entry point, milliseconds)] for the calls since ``timing(True)`` (synchronises)."""
+    import torch
+
+    torch.cuda.synchronize()
+    return [(name, e0.elapsed_time(e1)) for name, e0, e1 in _TIMING["records"]]
+
+
 def call(name: str, *args) -> None:
+    LAUNCHES["count"] += 1
+    if _TIMING["on"]:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(getattr(lib(), name)(*args), name)
+        e1.record()
+        _TIMING["records"].append((name, e0, e1))
+        return
     check(getattr(lib(), name)(*args), name)

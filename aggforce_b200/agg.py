@@ -65,14 +65,14 @@ def project_forces(
     Returns a dict with keys ``mapped_coords``, ``mapped_forces``, ``tmap``, ``residual``
     (mean squared mapped force, not held out) and ``constraints``.
     """
-    if isinstance(constrained_inds, str) and constrained_inds == PROJECT_FORCES_CNSTR_AUTO:
-        if isinstance(coords, (np.ndarray, torch.Tensor)):
-            constrained_inds = guess_pairwise_constraints(coords)
-        else:
-            raise ValueError(f"If constrained_inds is {PROJECT_FORCES_CNSTR_AUTO}, coords cannot be None.")
-    # one device upload per array, shared by the fit and the application passes
+    auto = isinstance(constrained_inds, str) and constrained_inds == PROJECT_FORCES_CNSTR_AUTO
+    if auto and coords is None:
+        raise ValueError(f"If constrained_inds is {PROJECT_FORCES_CNSTR_AUTO}, coords cannot be None.")
     t = Trajectory(coords=coords, forces=forces)
+    # one device upload per array, shared by constraint detection, the fit and the application
     coords_in, forces_in = _engine.Frames(coords), _engine.Frames(forces)
+    if auto:
+        constrained_inds = guess_pairwise_constraints(coords_in)
     traj_map: TMap = method(
         traj=Trajectory(coords=_Shared(coords, coords_in), forces=_Shared(forces, forces_in)),
         coord_map=coord_map,

@@ -15,6 +15,7 @@ import numpy as np
 __all__ = [
     "pair_distance_sd",
     "guess_pairwise_constraints",
+    "guess_pairwise_constraints_literal",
     "merge_constraint_groups",
     "group_columns",
     "bond_constraint_matrix",
@@ -86,6 +87,18 @@ def guess_pairwise_constraints(
         return {frozenset((int(i), int(j))) for i, j in zip(ii, jj)}
     ii, jj = np.nonzero(sds < threshold)
     return {(int(i), int(j)) for i, j in zip(ii, jj)}
+
+
+def guess_pairwise_constraints_literal(xyz: np.ndarray, threshold: float = 1e-3) -> set:
+    """The reference's formula AT THE REFERENCE'S COST: one materialised (T, n, n, 3)
+    displacement array in the INPUT dtype, its norm, ``np.var`` over frames
+    (util.py:65,70; constfinder.py:46-53).  Used only as the timed CPU baseline; small T."""
+    x = np.asarray(xyz)
+    dists = np.linalg.norm(x[:, None, :, :] - x[:, :, None, :], axis=-1)
+    sds = np.sqrt(np.var(dists, axis=0))
+    np.fill_diagonal(sds, threshold * 2)
+    ii, jj = np.nonzero(sds < threshold)
+    return {frozenset((int(i), int(j))) for i, j in zip(ii, jj)}
 
 
 # --------------------------------------------------------------------------------------
@@ -250,9 +263,10 @@ def apply_map(points: np.ndarray, matrix: np.ndarray) -> np.ndarray:
     """
     x = np.asarray(points, dtype=np.float64)
     m = np.asarray(matrix, dtype=np.float64)
+    path = ["einsum_path", (0, 1)]  # the contraction order the reference requests (util.py:121)
     if m.ndim == 2:
-        return np.einsum("tfd,cf->tcd", x, m)
-    return np.einsum("tfd,tcf->tcd", x, m)
+        return np.einsum("tfd,cf->tcd", x, m, optimize=path)
+    return np.einsum("tfd,tcf->tcd", x, m, optimize=path)
 
 
 def apply_map_nan_protocol(points: np.ndarray, matrix: np.ndarray, atol: float = 1e-6) -> np.ndarray:
