@@ -86,6 +86,14 @@ __global__ void __launch_bounds__(256) apply_sparse_kernel(const TI* __restrict_
 }
 
 // ------------------------------------------------------------------------------------ dense small
+// Work item = 8 consecutive frames ("octet").  A producer warp streams octets through a ring
+// of shared-memory stages with 1-D TMA bulk copies; each of the 8 consumer warps owns whole
+// octets (stage j -> warp j % 8), so there is no block-wide barrier anywhere.  For its octet a
+// warp runs, per 4 unique columns, 3 x NT DMMAs (xyz components x bead tiles): lane (g, q)
+// builds the A element "frame g, unique column x0+q" for all three components straight from
+// the raw stage (constraint-group sum + f64 promotion in registers), B fragments come from the
+// shared-memory copy of the map.  NaNs are detected on the OUTPUT (0 * NaN = NaN poisons the
+// whole row) and only then is the octet redone with the masking protocol.
 struct DenseSmallParams {
   const void* x;
   int64_t n_frames;
@@ -102,147 +110,254 @@ struct DenseSmallParams {
   double nan_atol;
   int32_t* nan_flags;
   ChunkSchedule sch;
-  int32_t ctas;
+  int32_t n_stages;
 };
 
 constexpr int kApplyConsumers = 8;
 constexpr int kApplyThreads = (kApplyConsumers + 1) * 32;
-constexpr int kApplyStages = 3;
+constexpr int kOctet = 8;
+constexpr int kMaxStages = 16;
 
 template <typename TI>
-__device__ __forceinline__ double group_value(const TI* __restrict__ fr, const int32_t* __restrict__ s_ptr,
-                                              const int32_t* __restrict__ s_sites, int x, int n_ucol, bool nan_mode,
-                                              double& nan_count) {
-  double v = 0.0;
-  if (x < n_ucol) {
-    const int b = s_ptr[x], e = s_ptr[x + 1];
-    for (int m = b; m < e; ++m) {
-      double f = to_f64(fr[3 * s_sites[m]]);
-      if (nan_mode && f != f) {
+__device__ __forceinline__ void group_value3(const TI* __restrict__ fr, const int32_t* __restrict__ s_ptr,
+                                             const int32_t* __restrict__ s_sites, int x, int n_ucol, bool mask_nan,
+                                             double (&v)[3], double (&cnt)[3]) {
+  v[0] = v[1] = v[2] = 0.0;
+  cnt[0] = cnt[1] = cnt[2] = 0.0;
+  if (x >= n_ucol) return;
+  for (int m = s_ptr[x]; m < s_ptr[x + 1]; ++m) {
+    const TI* p = fr + 3 * s_sites[m];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      double f = to_f64(p[d]);
+      if (mask_nan && f != f) {
         f = 0.0;
-        nan_count += 1.0;
+        cnt[d] += 1.0;
       }
-      v += f;
+      v[d] += f;
     }
   }
-  return v;
 }
 
-template <typename TI, typename TO, int NT, int KF>
+template <typename TI, typename TO, int NT>
 __global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(const __grid_constant__ DenseSmallParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_cg_pad = NT * 8;
   const int su = panel_stride(n_cg_pad);
   const int xpad = (p.n_ucol + 3) & ~3;
-  // carve-up: U^T panel | CSR | barriers | raw ring
+  // carve-up: U^T panel | member table | CSR | barriers | raw ring
   double* s_u = reinterpret_cast<double*>(smem);
   size_t off = (size_t)xpad * su * sizeof(double);
+  int4* s_tab = reinterpret_cast<int4*>(smem + off);  // up to 4 member offsets (site*3) per unique column, -1 = none
+  off += (size_t)xpad * sizeof(int4);
   int32_t* s_ptr = reinterpret_cast<int32_t*>(smem + off);
   off += (size_t)(p.n_ucol + 1) * 4;
   int32_t* s_sites = reinterpret_cast<int32_t*>(smem + off);
   off += (size_t)p.nnz * 4;
   off = (off + 15) / 16 * 16;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off);
-  off += 2 * kApplyStages * sizeof(uint64_t);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + off);
+  uint64_t* empty = full + kMaxStages;
+  off += 2 * kMaxStages * sizeof(uint64_t);
   off = (off + 127) / 128 * 128;
   TI* raw = reinterpret_cast<TI*>(smem + off);
+  const int64_t frame_elems = (int64_t)p.n_sites * 3;
+  const int64_t stage_elems = ((int64_t)kOctet * frame_elems * (int64_t)sizeof(TI) + 15) / 16 * 16 / (int64_t)sizeof(TI);
+  const int n_stages = p.n_stages;
 
   for (int i = threadIdx.x; i < xpad * su; i += blockDim.x) {
-    int xx = i / su, c = i - xx * su;
+    const int xx = i / su, c = i - xx * su;
     s_u[i] = (xx < p.n_ucol && c < p.n_cg) ? p.umat_t[(int64_t)xx * p.n_cg + c] : 0.0;
   }
   for (int i = threadIdx.x; i <= p.n_ucol; i += blockDim.x) s_ptr[i] = p.ucol_ptr[i];
   for (int i = threadIdx.x; i < p.nnz; i += blockDim.x) s_sites[i] = p.ucol_sites[i];
-
-  FrameRing<TI, kApplyStages> ring;
-  ring.init(raw, bars, reinterpret_cast<const TI*>(p.x), (int64_t)p.n_sites * 3, p.sch, kApplyConsumers);
+  __shared__ int s_generic;  // some unique column has more than 4 member sites -> CSR walk
+  if (threadIdx.x == 0) s_generic = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < xpad; i += blockDim.x) {
+    int m[4] = {-1, -1, -1, -1};
+    if (i < p.n_ucol) {
+      const int b = p.ucol_ptr[i], e = p.ucol_ptr[i + 1];
+      for (int k = 0; k < 4 && b + k < e; ++k) m[k] = 3 * p.ucol_sites[b + k];
+      if (e - b > 4) s_generic = 1;
+    }
+    s_tab[i] = make_int4(m[0], m[1], m[2], m[3]);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    fence_barrier_init();
+  }
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const TI* base = reinterpret_cast<const TI*>(p.x);
   const int64_t first = blockIdx.x, step = gridDim.x;
+  const int64_t n_mine = p.sch.n_chunks > first ? (p.sch.n_chunks - first + step - 1) / step : 0;
+
   if (warp == kApplyConsumers) {
-    ring.produce(first, step);
+    // ---------------- producer warp
+    for (int64_t j = 0; j < n_mine; ++j) {
+      const int64_t c = first + j * step;
+      const int stage = (int)(j % n_stages);
+      const uint32_t parity = (uint32_t)((j / n_stages) & 1);
+      mbar_wait(&empty[stage], parity ^ 1u);
+      const int nf = p.sch.count(c);
+      const int64_t bytes = (int64_t)nf * frame_elems * (int64_t)sizeof(TI);
+      const TI* src = base + p.sch.start(c) * frame_elems;
+      TI* dst = raw + (int64_t)stage * stage_elems;
+      const bool bulk = c != 0 && bytes > 0 && (bytes % 16) == 0 && (reinterpret_cast<uintptr_t>(src) % 16) == 0;
+      if (bulk) {
+        if (lane == 0) {
+          fence_proxy_async();
+          mbar_expect_tx(&full[stage], (uint32_t)bytes);
+          uint32_t done = 0;
+          while (done < (uint32_t)bytes) {
+            const uint32_t piece = (uint32_t)bytes - done < 65536u ? (uint32_t)bytes - done : 65536u;
+            tma_bulk_g2s(reinterpret_cast<char*>(dst) + done, reinterpret_cast<const char*>(src) + done, piece,
+                         &full[stage]);
+            done += piece;
+          }
+        }
+      } else {
+        const int64_t n = (int64_t)nf * frame_elems;
+        for (int64_t i = lane; i < n; i += 32) dst[i] = src[i];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[stage]);
+      }
+      __syncwarp();
+    }
     return;
   }
 
+  // ---------------- consumer warps
   const int g = lane >> 2, q = lane & 3;
   const bool nan_mode = p.nan_mode != 0;
+  const bool generic_groups = s_generic != 0;
   TO* out = reinterpret_cast<TO*>(p.out);
   double sq = 0.0;
   bool saw_nan = false, bad = false;
-  RingCursor<kApplyStages> cur;
-  constexpr int OCT = KF / 8;        // frame octets per chunk
-  constexpr int ITEMS = OCT * 3;     // (octet, xyz component) work items per chunk
-  int64_t item_base = 0;             // running item id keeps warps balanced across chunks
-  for (int64_t c = first; c < p.sch.n_chunks; c += step) {
+  // A waiter can tell the current mbarrier phase from the previous one only, so at most n_stages
+  // warps may consume (then the stage a warp waits for is never two phases ahead of its fill).
+  const int n_cons = n_stages < kApplyConsumers ? n_stages : kApplyConsumers;
+  if (warp >= n_cons) return;
+  for (int64_t j = warp; j < n_mine; j += n_cons) {
+    const int64_t c = first + j * step;
+    const int stage = (int)(j % n_stages);
+    const uint32_t parity = (uint32_t)((j / n_stages) & 1);
+    mbar_wait(&full[stage], parity);
     const int nf = p.sch.count(c);
-    if (nf == 0) continue;
-    const int64_t t0 = p.sch.start(c);
-    mbar_wait(&ring.full[cur.stage], cur.phase);
-    const TI* stage = ring.stage_ptr(cur.stage);
-    for (int it = 0; it < ITEMS; ++it) {
-      if ((int)((item_base + it) % kApplyConsumers) != warp) continue;
-      const int oct = it / 3, d = it - oct * 3;
-      if (oct * 8 >= nf) continue;
-      const int tl = oct * 8 + g;  // this lane's frame (A row g)
-      const bool valid = tl < nf;
-      const TI* fr = stage + (int64_t)(valid ? tl : 0) * p.n_sites * 3 + d;
-      double acc[NT][2];
+    if (nf > 0) {
+      const int64_t t0 = p.sch.start(c);
+      const bool valid = g < nf;
+      const TI* fr = raw + (int64_t)stage * stage_elems + (int64_t)(valid ? g : 0) * frame_elems;
+      double acc[3][NT][2];
 #pragma unroll
-      for (int n = 0; n < NT; ++n) acc[n][0] = acc[n][1] = 0.0;
-      double nan_any = 0.0;
-      for (int x0 = 0; x0 < xpad; x0 += 4) {
-        double nc = 0.0;
-        double a = group_value<TI>(fr, s_ptr, s_sites, x0 + q, p.n_ucol, nan_mode, nc);
-        if (!valid) a = 0.0;
-        nan_any += nc;
-        const double* bp = s_u + (x0 + q) * su + g;
+      for (int d = 0; d < 3; ++d)
 #pragma unroll
-        for (int n = 0; n < NT; ++n) dmma884(acc[n][0], acc[n][1], a, bp[n * 8]);
-      }
-      if (nan_mode && __any_sync(0xffffffffu, nan_any != 0.0)) {
-        // rare path: weight mass sitting on NaN entries, nan_w[t][c] = sum_x U[c][x] * (#NaN in group x)
-        saw_nan = true;
-        double nw[NT][2];
-#pragma unroll
-        for (int n = 0; n < NT; ++n) nw[n][0] = nw[n][1] = 0.0;
+        for (int n = 0; n < NT; ++n) acc[d][n][0] = acc[d][n][1] = 0.0;
+      if (!generic_groups) {
+#pragma unroll 2
         for (int x0 = 0; x0 < xpad; x0 += 4) {
-          double nc = 0.0;
-          (void)group_value<TI>(fr, s_ptr, s_sites, x0 + q, p.n_ucol, true, nc);
-          if (!valid) nc = 0.0;
+          const int4 mem = s_tab[x0 + q];
+          double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+          if (mem.x >= 0) { a0 = to_f64(fr[mem.x]); a1 = to_f64(fr[mem.x + 1]); a2 = to_f64(fr[mem.x + 2]); }
+          if (mem.y >= 0) { a0 += to_f64(fr[mem.y]); a1 += to_f64(fr[mem.y + 1]); a2 += to_f64(fr[mem.y + 2]); }
+          if (mem.z >= 0) { a0 += to_f64(fr[mem.z]); a1 += to_f64(fr[mem.z + 1]); a2 += to_f64(fr[mem.z + 2]); }
+          if (mem.w >= 0) { a0 += to_f64(fr[mem.w]); a1 += to_f64(fr[mem.w + 1]); a2 += to_f64(fr[mem.w + 2]); }
+          if (!valid) a0 = a1 = a2 = 0.0;
           const double* bp = s_u + (x0 + q) * su + g;
 #pragma unroll
-          for (int n = 0; n < NT; ++n) dmma884(nw[n][0], nw[n][1], nc, bp[n * 8]);
+          for (int n = 0; n < NT; ++n) {
+            const double b = bp[n * 8];
+            dmma884(acc[0][n][0], acc[0][n][1], a0, b);
+            dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+            dmma884(acc[2][n][0], acc[2][n][1], a2, b);
+          }
         }
+      } else {
+        for (int x0 = 0; x0 < xpad; x0 += 4) {
+          double v[3], cnt[3];
+          group_value3<TI>(fr, s_ptr, s_sites, x0 + q, p.n_ucol, false, v, cnt);
+          if (!valid) v[0] = v[1] = v[2] = 0.0;
+          const double* bp = s_u + (x0 + q) * su + g;
 #pragma unroll
-        for (int n = 0; n < NT; ++n) {
-          bad |= fabs(nw[n][0]) > p.nan_atol + kNanRtol * fabs(acc[n][0] - nw[n][0]);
-          bad |= fabs(nw[n][1]) > p.nan_atol + kNanRtol * fabs(acc[n][1] - nw[n][1]);
+          for (int n = 0; n < NT; ++n) {
+            const double b = bp[n * 8];
+            dmma884(acc[0][n][0], acc[0][n][1], v[0], b);
+            dmma884(acc[1][n][0], acc[1][n][1], v[1], b);
+            dmma884(acc[2][n][0], acc[2][n][1], v[2], b);
+          }
         }
       }
-      // C[g][2q], C[g][2q+1]: frame t0 + oct*8 + g, beads n*8 + 2q (+1), component d
+      if (nan_mode) {
+        bool has_nan = false;
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+          for (int n = 0; n < NT; ++n) has_nan |= (acc[d][n][0] != acc[d][n][0]) | (acc[d][n][1] != acc[d][n][1]);
+        if (__any_sync(0xffffffffu, has_nan)) {
+          // rare path: redo the octet with NaN -> 0 and accumulate the weight mass on NaN entries
+          double nw[3][NT][2];
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) acc[d][n][0] = acc[d][n][1] = nw[d][n][0] = nw[d][n][1] = 0.0;
+          bool any_cnt = false;
+          for (int x0 = 0; x0 < xpad; x0 += 4) {
+            double v[3], cnt[3];
+            group_value3<TI>(fr, s_ptr, s_sites, x0 + q, p.n_ucol, true, v, cnt);
+            if (!valid) v[0] = v[1] = v[2] = cnt[0] = cnt[1] = cnt[2] = 0.0;
+            any_cnt |= (cnt[0] + cnt[1] + cnt[2]) != 0.0;
+            const double* bp = s_u + (x0 + q) * su + g;
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              const double b = bp[n * 8];
+#pragma unroll
+              for (int d = 0; d < 3; ++d) {
+                dmma884(acc[d][n][0], acc[d][n][1], v[d], b);
+                dmma884(nw[d][n][0], nw[d][n][1], cnt[d], b);
+              }
+            }
+          }
+          saw_nan |= __any_sync(0xffffffffu, any_cnt);
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              bad |= fabs(nw[d][n][0]) > p.nan_atol + kNanRtol * fabs(acc[d][n][0] - nw[d][n][0]);
+              bad |= fabs(nw[d][n][1]) > p.nan_atol + kNanRtol * fabs(acc[d][n][1] - nw[d][n][1]);
+            }
+        }
+      }
+      // C[g][2q], C[g][2q+1] of component d: frame t0+g, beads n*8+2q (+1) -> 6 consecutive outputs
       if (valid) {
-        TO* orow = out + ((t0 + tl) * (int64_t)p.n_cg) * 3 + d;
+        TO* orow = out + (t0 + g) * (int64_t)p.n_cg * 3;
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
           const int cb = n * 8 + 2 * q;
           if (cb < p.n_cg) {
-            store_out(orow + (int64_t)cb * 3, acc[n][0]);
-            double r = (double)static_cast<TO>(acc[n][0]);
-            sq += r * r;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              store_out(orow + (int64_t)cb * 3 + d, acc[d][n][0]);
+              const double r = (double)static_cast<TO>(acc[d][n][0]);
+              sq += r * r;
+            }
           }
           if (cb + 1 < p.n_cg) {
-            store_out(orow + (int64_t)(cb + 1) * 3, acc[n][1]);
-            double r = (double)static_cast<TO>(acc[n][1]);
-            sq += r * r;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+              store_out(orow + (int64_t)(cb + 1) * 3 + d, acc[d][n][1]);
+              const double r = (double)static_cast<TO>(acc[d][n][1]);
+              sq += r * r;
+            }
           }
         }
       }
     }
-    item_base += ITEMS;
     __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.empty[cur.stage]);
-    cur.advance();
+    if (lane == 0) mbar_arrive(&empty[stage]);
   }
   if (p.sumsq) {
     sq = warp_sum(sq);
@@ -347,22 +462,25 @@ __global__ void __launch_bounds__(256) apply_dense_big_kernel(const TI* __restri
 
 template <typename TI, typename TO, int NT>
 static int launch_small(DenseSmallParams& p, cudaStream_t stream) {
-  constexpr int KF = sizeof(TI) == 4 ? 16 : 8;
-  p.sch = make_schedule(p.x, p.n_frames, (int64_t)p.n_sites * 3 * sizeof(TI), KF);
+  p.sch = make_schedule(p.x, p.n_frames, (int64_t)p.n_sites * 3 * sizeof(TI), kOctet);
   const int su = panel_stride(NT * 8);
   const int xpad = (p.n_ucol + 3) & ~3;
-  size_t off = (size_t)xpad * su * sizeof(double) + (size_t)(p.n_ucol + 1) * 4 + (size_t)p.nnz * 4;
-  off = (off + 15) / 16 * 16 + 2 * kApplyStages * sizeof(uint64_t);
+  size_t off = (size_t)xpad * su * sizeof(double) + (size_t)xpad * 16 + (size_t)(p.n_ucol + 1) * 4 + (size_t)p.nnz * 4;
+  off = (off + 15) / 16 * 16 + 2 * kMaxStages * sizeof(uint64_t);
   off = (off + 127) / 128 * 128;
-  size_t stage_bytes = ((size_t)KF * p.n_sites * 3 * sizeof(TI) + 15) / 16 * 16;
-  size_t smem = off + kApplyStages * stage_bytes;
-  if (smem > 220 * 1024) return 1;  // does not fit: caller uses the fallback
-  auto kern = apply_dense_small_kernel<TI, TO, NT, KF>;
+  size_t stage_bytes = ((size_t)kOctet * p.n_sites * 3 * sizeof(TI) + 15) / 16 * 16;
+  const size_t budget = 224 * 1024;
+  if (off + 4 * stage_bytes > budget) return 1;  // does not fit: caller uses the fallback
+  int n_stages = (int)((budget - off) / stage_bytes);
+  if (n_stages > kMaxStages) n_stages = kMaxStages;
+  p.n_stages = n_stages;
+  size_t smem = off + (size_t)n_stages * stage_bytes;
+  auto kern = apply_dense_small_kernel<TI, TO, NT>;
   AGF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t ctas = sm_count();
-  if (ctas > p.sch.n_chunks) ctas = p.sch.n_chunks;
+  int64_t want = (p.sch.n_chunks + kApplyConsumers - 1) / kApplyConsumers;
+  if (ctas > want) ctas = want;
   if (ctas < 1) ctas = 1;
-  p.ctas = (int)ctas;
   kern<<<(int)ctas, kApplyThreads, smem, stream>>>(p);
   AGF_CUDA_TRY(cudaGetLastError());
   return AGF_OK;

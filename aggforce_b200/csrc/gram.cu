@@ -4,14 +4,19 @@
 // transposed copy of the force array).  Here the constraint-group sum, the f32->f64
 // promotion and the SYRK are one kernel:
 //   * frames stream global -> shared memory as 1-D TMA bulk copies (frame_pipe.cuh);
-//   * each chunk is converted to an f64 panel  panel[k=(t,d)][x=reduced column]  with a
-//     bank-conflict-free stride;
-//   * 8 warps run DMMA.8x8x4 on the upper block-triangle, every warp owning a balanced,
-//     table-driven list of 8x8 output tiles whose accumulators stay in registers for the
-//     whole frame range of the CTA (split-K over frames across CTAs);
+//   * each chunk is converted to an f64 panel  panel[k=(t,d)][x=reduced column]  whose row
+//     stride (132 doubles) makes every DMMA fragment load bank-conflict free;
+//   * 8 warps run DMMA.8x8x4.  A-fragment of row tile r and B-fragment of column tile c are
+//     the SAME shared-memory access pattern (lane (g,q) reads panel[k0+q][8*tile+g]), so a
+//     warp loads each needed 8-column fragment once per k-step and reuses it as row and as
+//     column operand;
+//   * which tiles a warp owns is decided at COMPILE time -- template <NT, warp> static plans
+//     over the upper triangle -- so the inner loop is nothing but LDS.64 + DMMA, accumulators
+//     live in registers for the whole frame range of the CTA (split-K over frames);
 //   * accumulators are added to the global Gram with f64 RED atomics at the end.
-// Reduced columns are tiled in blocks of 128; for n_red <= 128 (cln025: 97) a single CTA
-// shape covers the whole matrix, for larger systems CTAs enumerate block pairs (I <= J).
+// n_red <= 128 (cln025: 97): one CTA shape covers the upper triangle (NT = ceil(n_red/8) tile
+// columns).  Larger systems: CTAs enumerate 128x128 block pairs (I <= J) and each warp owns a
+// static 2 x 16 tile rectangle; operands are gathered from global memory (compute bound by 60x).
 #include "frame_pipe.cuh"
 
 namespace agf {
@@ -19,19 +24,8 @@ namespace agf {
 constexpr int kGramThreads = 256;
 constexpr int kGramWarps = 8;
 constexpr int kBlockCols = 128;  // reduced columns per block
-constexpr int kMaxSlots = 32;
+constexpr int kStride = 132;     // panel row stride in doubles (132 % 16 == 4: conflict free)
 
-struct WarpPlan {
-  uint8_t nslots;
-  uint8_t row[kMaxSlots];  // 8-row tile index within the row block
-  uint8_t col[kMaxSlots];  // 8-col tile index within the col block
-};
-
-struct ShapePlan {
-  WarpPlan warp[kGramWarps];
-};
-
-// shape ids: 0 diag(full), 1 off(full x full), 2 off(full x last), 3 diag(last)
 struct GramParams {
   const void* forces;
   int64_t n_frames;
@@ -39,133 +33,197 @@ struct GramParams {
   const int32_t* col_ptr;
   const int32_t* col_sites;
   int32_t n_red;
-  int32_t n_blocks;    // ceil(n_red / 128)
-  int32_t n_pairs;     // n_blocks (n_blocks + 1) / 2
-  int32_t k_splits;    // CTAs per block pair
-  int32_t stride;      // panel row stride in doubles (bank-conflict-free, see panel_stride)
+  int32_t n_blocks;  // ceil(n_red / 128)
+  int32_t n_pairs;   // n_blocks (n_blocks + 1) / 2
+  int32_t k_splits;  // CTAs per block pair
   double* gram;
   ChunkSchedule sch;
-  ShapePlan plan[4];
 };
 
-static void build_plan(ShapePlan& sp, int row_tiles, int col_tiles, bool diag) {
-  // tiles in strip order (row major); diag shapes keep only col >= row
-  int total = 0;
-  for (int r = 0; r < row_tiles; ++r) total += col_tiles - (diag ? r : 0);
-  int base = total / kGramWarps, extra = total % kGramWarps;
-  int w = 0, filled = 0;
-  int quota = base + (w < extra ? 1 : 0);
-  for (int i = 0; i < kGramWarps; ++i) sp.warp[i].nslots = 0;
-  for (int r = 0; r < row_tiles; ++r) {
-    for (int c = (diag ? r : 0); c < col_tiles; ++c) {
-      while (w < kGramWarps - 1 && filled >= quota) {
-        ++w;
-        filled = 0;
-        quota = base + (w < extra ? 1 : 0);
-      }
-      WarpPlan& wp = sp.warp[w];
-      wp.row[wp.nslots] = (uint8_t)r;
-      wp.col[wp.nslots] = (uint8_t)c;
-      ++wp.nslots;
-      ++filled;
+// ------------------------------------------------------------------ static triangular tile plans
+// Tiles of the upper triangle of an NT x NT tile grid in strip (row-major) order; warp w owns
+// the contiguous run [tile_begin(w), tile_begin(w+1)) -- balanced to within one tile.
+__host__ __device__ constexpr int tri_tiles(int nt) { return nt * (nt + 1) / 2; }
+__host__ __device__ constexpr int tile_begin(int nt, int w) {
+  const int total = tri_tiles(nt), base = total / kGramWarps, extra = total % kGramWarps;
+  return w * base + (w < extra ? w : extra);
+}
+__host__ __device__ constexpr int tile_row(int nt, int t) {
+  int r = 0, len = nt;
+  while (t >= len) {
+    t -= len;
+    --len;
+    ++r;
+  }
+  return r;
+}
+__host__ __device__ constexpr int tile_col(int nt, int t) {
+  int r = 0, len = nt;
+  while (t >= len) {
+    t -= len;
+    --len;
+    ++r;
+  }
+  return r + t;
+}
+constexpr int kMaxTriSlots = (tri_tiles(16) + kGramWarps - 1) / kGramWarps;  // 17
+
+template <int NT, int W, int T, int END>
+struct TriTiles {
+  static __device__ __forceinline__ void mma(double (&acc)[kMaxTriSlots][2], const double (&frag)[NT]) {
+    if constexpr (T < END) {
+      constexpr int r = tile_row(NT, T), c = tile_col(NT, T), s = T - tile_begin(NT, W);
+      dmma884(acc[s][0], acc[s][1], frag[r], frag[c]);
+      TriTiles<NT, W, T + 1, END>::mma(acc, frag);
     }
   }
-}
-
-template <typename T>
-__device__ __forceinline__ void fill_panel_staged(const T* __restrict__ raw, int nf, int kf, int n_sites,
-                                                  const int32_t* __restrict__ col_ptr,
-                                                  const int32_t* __restrict__ col_sites, int col0, int n_red,
-                                                  int width_pad, double* __restrict__ panel, int stride) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int t = warp; t < kf; t += kGramWarps) {
-    const T* fr = raw + (int64_t)t * n_sites * 3;
-    for (int x = lane; x < width_pad; x += 32) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-      int col = col0 + x;
-      if (t < nf && col < n_red) {
-        int b = __ldg(col_ptr + col), e = __ldg(col_ptr + col + 1);
-        for (int m = b; m < e; ++m) {
-          const T* p = fr + 3 * __ldg(col_sites + m);
-          s0 += to_f64(p[0]);
-          s1 += to_f64(p[1]);
-          s2 += to_f64(p[2]);
-        }
+  static __device__ __forceinline__ void store(const double (&acc)[kMaxTriSlots][2], double* gram, int n_red, int g,
+                                               int q) {
+    if constexpr (T < END) {
+      constexpr int r = tile_row(NT, T), c = tile_col(NT, T), s = T - tile_begin(NT, W);
+      const int i = r * 8 + g, j = c * 8 + 2 * q;
+      if (i < n_red) {
+        double* row = gram + (int64_t)i * n_red;
+        if (j < n_red) atomicAdd(row + j, acc[s][0]);
+        if (j + 1 < n_red) atomicAdd(row + j + 1, acc[s][1]);
       }
-      double* dst = panel + (t * 3) * stride + x;
-      dst[0] = s0;
-      dst[stride] = s1;
-      dst[2 * stride] = s2;
+      TriTiles<NT, W, T + 1, END>::store(acc, gram, n_red, g, q);
     }
   }
-}
+};
 
-template <typename T>
-__device__ __forceinline__ void fill_panel_global(const T* __restrict__ forces, int64_t t0, int nf, int kf,
-                                                  int n_sites, const int32_t* __restrict__ col_ptr,
-                                                  const int32_t* __restrict__ col_sites, int col0, int n_red,
-                                                  int width_pad, double* __restrict__ panel, int stride) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int t = warp; t < kf; t += kGramWarps) {
-    const T* fr = forces + (t0 + t) * (int64_t)n_sites * 3;
-    for (int x = lane; x < width_pad; x += 32) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-      int col = col0 + x;
-      if (t < nf && col < n_red) {
-        int b = __ldg(col_ptr + col), e = __ldg(col_ptr + col + 1);
-        for (int m = b; m < e; ++m) {
-          const T* p = fr + 3 * __ldg(col_sites + m);
-          s0 += to_f64(__ldg(p));
-          s1 += to_f64(__ldg(p + 1));
-          s2 += to_f64(__ldg(p + 2));
-        }
-      }
-      double* dst = panel + (t * 3) * stride + x;
-      dst[0] = s0;
-      dst[stride] = s1;
-      dst[2 * stride] = s2;
-    }
-  }
-}
-
-// One k-sweep of a chunk: KROWS = 3*KF panel rows.
-template <int SLOTS, int KROWS>
-__device__ __forceinline__ void mma_sweep(const double* __restrict__ pa, const double* __restrict__ pb, int stride,
-                                          const uint32_t (&desc)[SLOTS], int nslots, double (&acc)[SLOTS][2]) {
-  const int lane = threadIdx.x & 31;
-  const int g = lane >> 2, q = lane & 3;
-  const double* a_base = pa + q * stride + g;
-  const double* b_base = pb + q * stride + g;
-#pragma unroll 2
-  for (int kk = 0; kk < KROWS / 4; ++kk) {
-    const double* ak = a_base + kk * 4 * stride;
-    const double* bk = b_base + kk * 4 * stride;
-    double a = 0.0;
+// One chunk: every k-step loads the NT fragments once and feeds this warp's tiles.
+template <int NT, int W, int KSTEPS>
+__device__ __forceinline__ void tri_sweep(const double* __restrict__ lane_panel, double (&acc)[kMaxTriSlots][2]) {
+#pragma unroll 3
+  for (int kk = 0; kk < KSTEPS; ++kk) {
+    const double* pk = lane_panel + kk * 4 * kStride;
+    double frag[NT];
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      if (s < nslots) {
-        uint32_t d = desc[s];
-        if (d & 0x80000000u) a = ak[d & 0xffu];
-        double b = bk[(d >> 8) & 0xffu];
-        dmma884(acc[s][0], acc[s][1], a, b);
+    for (int i = 0; i < NT; ++i) frag[i] = pk[i * 8];  // fragments this warp never uses are dead code
+    TriTiles<NT, W, tile_begin(NT, W), tile_begin(NT, W + 1)>::mma(acc, frag);
+  }
+}
+
+template <int NT, int KSTEPS>
+__device__ __forceinline__ void tri_sweep_warp(int warp, const double* lane_panel, double (&acc)[kMaxTriSlots][2]) {
+  switch (warp) {
+    case 0: tri_sweep<NT, 0, KSTEPS>(lane_panel, acc); break;
+    case 1: tri_sweep<NT, 1, KSTEPS>(lane_panel, acc); break;
+    case 2: tri_sweep<NT, 2, KSTEPS>(lane_panel, acc); break;
+    case 3: tri_sweep<NT, 3, KSTEPS>(lane_panel, acc); break;
+    case 4: tri_sweep<NT, 4, KSTEPS>(lane_panel, acc); break;
+    case 5: tri_sweep<NT, 5, KSTEPS>(lane_panel, acc); break;
+    case 6: tri_sweep<NT, 6, KSTEPS>(lane_panel, acc); break;
+    default: tri_sweep<NT, 7, KSTEPS>(lane_panel, acc); break;
+  }
+}
+
+template <int NT, int W>
+__device__ __forceinline__ void tri_store(const double (&acc)[kMaxTriSlots][2], double* gram, int n_red, int g, int q) {
+  TriTiles<NT, W, tile_begin(NT, W), tile_begin(NT, W + 1)>::store(acc, gram, n_red, g, q);
+}
+
+// ------------------------------------------------------------------ panel fill (group sum + f64 promotion)
+template <typename T, bool GLOBAL>
+__device__ __forceinline__ void fill_panel(const T* __restrict__ frames, int nf, int kf, int n_sites,
+                                           const int32_t* __restrict__ col_ptr,
+                                           const int32_t* __restrict__ col_sites, int col0, int n_red,
+                                           int width_pad, double* __restrict__ panel) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int t = warp; t < kf; t += kGramWarps) {
+    const T* fr = frames + (int64_t)t * n_sites * 3;
+    for (int x = lane; x < width_pad; x += 32) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      const int col = col0 + x;
+      if (t < nf && col < n_red) {
+        const int b = __ldg(col_ptr + col), e = __ldg(col_ptr + col + 1);
+        for (int m = b; m < e; ++m) {
+          const T* p = fr + 3 * __ldg(col_sites + m);
+          if constexpr (GLOBAL) {
+            s0 += to_f64(__ldg(p));
+            s1 += to_f64(__ldg(p + 1));
+            s2 += to_f64(__ldg(p + 2));
+          } else {
+            s0 += to_f64(p[0]);
+            s1 += to_f64(p[1]);
+            s2 += to_f64(p[2]);
+          }
+        }
       }
+      double* dst = panel + (t * 3) * kStride + x;
+      dst[0] = s0;
+      dst[kStride] = s1;
+      dst[2 * kStride] = s2;
     }
   }
 }
 
-template <typename T, int KF, int SLOTS, bool STAGED>
-__global__ void __launch_bounds__(kGramThreads, STAGED ? 2 : 1) gram_kernel(const __grid_constant__ GramParams p) {
+// ------------------------------------------------------------------ single block (n_red <= 128), TMA staged
+template <typename T, int KF, int NT>
+__global__ void __launch_bounds__(kGramThreads, 2) gram_tri_kernel(const __grid_constant__ GramParams p) {
   constexpr int KROWS = 3 * KF;
   constexpr int STAGES = 2;
+  static_assert(KROWS % 4 == 0, "k rows must be a multiple of the DMMA k");
   extern __shared__ __align__(128) unsigned char smem[];
+  double* panel = reinterpret_cast<double*>(smem);
+  size_t off = (size_t)KROWS * kStride * sizeof(double);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + off);
+  off += 64;
+  T* raw = reinterpret_cast<T*>(smem + off);
 
-  // ---- which block pair / k-split am I
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const double* lane_panel = panel + q * kStride + g;
+  double acc[kMaxTriSlots][2];
+#pragma unroll
+  for (int s = 0; s < kMaxTriSlots; ++s) acc[s][0] = acc[s][1] = 0.0;
+
+  const T* forces = reinterpret_cast<const T*>(p.forces);
+  const int64_t n_chunks = p.sch.n_chunks;
+  const int64_t first = blockIdx.x, step = gridDim.x;
+  FrameStager<T, STAGES> st;
+  st.init(raw, full, forces, (int64_t)p.n_sites * 3, p.sch);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) st.issue(first + (int64_t)s * step, s);
+  }
+  int stage = 0;
+  for (int64_t c = first; c < n_chunks; c += step) {
+    const int nf = p.sch.count(c);
+    if (nf > 0) {
+      st.wait(c, stage);
+      fill_panel<T, false>(st.stage_ptr(stage), nf, KF, p.n_sites, p.col_ptr, p.col_sites, 0, p.n_red, NT * 8, panel);
+    }
+    __syncthreads();  // panel complete, raw stage free
+    if (threadIdx.x == 0) st.issue(c + (int64_t)STAGES * step, stage);
+    if (nf > 0) tri_sweep_warp<NT, KROWS / 4>(warp, lane_panel, acc);
+    __syncthreads();  // panel free
+    stage = (stage + 1) % STAGES;
+  }
+  switch (warp) {
+    case 0: tri_store<NT, 0>(acc, p.gram, p.n_red, g, q); break;
+    case 1: tri_store<NT, 1>(acc, p.gram, p.n_red, g, q); break;
+    case 2: tri_store<NT, 2>(acc, p.gram, p.n_red, g, q); break;
+    case 3: tri_store<NT, 3>(acc, p.gram, p.n_red, g, q); break;
+    case 4: tri_store<NT, 4>(acc, p.gram, p.n_red, g, q); break;
+    case 5: tri_store<NT, 5>(acc, p.gram, p.n_red, g, q); break;
+    case 6: tri_store<NT, 6>(acc, p.gram, p.n_red, g, q); break;
+    default: tri_store<NT, 7>(acc, p.gram, p.n_red, g, q); break;
+  }
+}
+
+// ------------------------------------------------------------------ block pairs (any n_red), global gather
+// CTA = block pair (I <= J) x k-split; warp w owns tile rows {2w, 2w+1} x all 16 tile columns.
+template <typename T, int KF>
+__global__ void __launch_bounds__(kGramThreads, 1) gram_block_kernel(const __grid_constant__ GramParams p) {
+  constexpr int KROWS = 3 * KF;
+  extern __shared__ __align__(128) unsigned char smem[];
   const int pair = blockIdx.x % p.n_pairs;
   const int ksplit = blockIdx.x / p.n_pairs;
   int bi = 0, bj = 0;
   {
-    int rem = pair;
-    int rowlen = p.n_blocks;
+    int rem = pair, rowlen = p.n_blocks;
     while (rem >= rowlen) {
       rem -= rowlen;
       --rowlen;
@@ -174,98 +232,54 @@ __global__ void __launch_bounds__(kGramThreads, STAGED ? 2 : 1) gram_kernel(cons
     bj = bi + rem;
   }
   const bool diag = (bi == bj);
-  const int last = p.n_blocks - 1;
-  const int shape = diag ? (bi == last ? 3 : 0) : (bj == last ? 2 : 1);
   const int col0_i = bi * kBlockCols, col0_j = bj * kBlockCols;
-  const int width_i = min(kBlockCols, p.n_red - col0_i), width_j = min(kBlockCols, p.n_red - col0_j);
-  const int wpad_i = (width_i + 7) & ~7, wpad_j = (width_j + 7) & ~7;
-  const int stride = p.stride;
-
-  // ---- smem carve-up
   double* panel_i = reinterpret_cast<double*>(smem);
-  double* panel_j = diag ? panel_i : panel_i + KROWS * stride;
-  size_t off = (size_t)(STAGED ? 1 : 2) * KROWS * stride * sizeof(double);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + off);
-  off += 64;
-  T* raw = reinterpret_cast<T*>(smem + off);
+  double* panel_j = diag ? panel_i : panel_i + KROWS * kStride;
 
-  const int warp = threadIdx.x >> 5;
-  const WarpPlan& wp = p.plan[shape].warp[warp];
-  const int nslots = wp.nslots;
-  uint32_t desc[SLOTS];
-  {
-    int prev_row = -1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, q = lane & 3;
+  const double* lane_i = panel_i + q * kStride + g + warp * 16;
+  const double* lane_j = panel_j + q * kStride + g;
+  double acc[2][16][2];
 #pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      uint32_t d = 0;
-      if (s < nslots) {
-        int r = wp.row[s], c = wp.col[s];
-        d = (uint32_t)(r * 8) | ((uint32_t)(c * 8) << 8);
-        if (r != prev_row) d |= 0x80000000u;
-        prev_row = r;
-      }
-      desc[s] = d;
-    }
-  }
-  double acc[SLOTS][2];
+  for (int r = 0; r < 2; ++r)
 #pragma unroll
-  for (int s = 0; s < SLOTS; ++s) acc[s][0] = acc[s][1] = 0.0;
+    for (int c = 0; c < 16; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
 
   const T* forces = reinterpret_cast<const T*>(p.forces);
-  const int64_t n_chunks = p.sch.n_chunks;
-  const int64_t first = ksplit, step = p.k_splits;
-
-  if constexpr (STAGED) {
-    FrameStager<T, STAGES> st;
-    st.init(raw, full, forces, (int64_t)p.n_sites * 3, p.sch);
+  for (int64_t c = ksplit; c < p.sch.n_chunks; c += p.k_splits) {
+    const int nf = p.sch.count(c);
+    if (nf > 0) {
+      const T* src = forces + p.sch.start(c) * (int64_t)p.n_sites * 3;
+      fill_panel<T, true>(src, nf, KF, p.n_sites, p.col_ptr, p.col_sites, col0_i, p.n_red, kBlockCols, panel_i);
+      if (!diag)
+        fill_panel<T, true>(src, nf, KF, p.n_sites, p.col_ptr, p.col_sites, col0_j, p.n_red, kBlockCols, panel_j);
+    }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int s = 0; s < STAGES; ++s) st.issue(first + (int64_t)s * step, s);
-    }
-    int stage = 0;
-    for (int64_t c = first; c < n_chunks; c += step) {
-      const int nf = p.sch.count(c);
-      if (nf > 0) {
-        st.wait(c, stage);
-        fill_panel_staged<T>(st.stage_ptr(stage), nf, KF, p.n_sites, p.col_ptr, p.col_sites, col0_i, p.n_red,
-                             wpad_i, panel_i, stride);
-      }
-      __syncthreads();  // panel complete, raw stage free
-      if (threadIdx.x == 0) st.issue(c + (int64_t)STAGES * step, stage);
-      if (nf > 0) mma_sweep<SLOTS, KROWS>(panel_i, panel_i, stride, desc, nslots, acc);
-      __syncthreads();  // panel free
-      stage = (stage + 1) % STAGES;
-    }
-  } else {
-    for (int64_t c = first; c < n_chunks; c += step) {
-      const int nf = p.sch.count(c);
-      if (nf > 0) {
-        const int64_t t0 = p.sch.start(c);
-        fill_panel_global<T>(forces, t0, nf, KF, p.n_sites, p.col_ptr, p.col_sites, col0_i, p.n_red, wpad_i,
-                             panel_i, stride);
-        if (!diag)
-          fill_panel_global<T>(forces, t0, nf, KF, p.n_sites, p.col_ptr, p.col_sites, col0_j, p.n_red, wpad_j,
-                               panel_j, stride);
-      }
-      __syncthreads();
-      if (nf > 0) mma_sweep<SLOTS, KROWS>(panel_i, panel_j, stride, desc, nslots, acc);
-      __syncthreads();
-    }
-  }
-
-  // ---- epilogue: RED.ADD.F64 into the global Gram (upper block triangle)
-  const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+    if (nf > 0) {
+#pragma unroll 2
+      for (int kk = 0; kk < KROWS / 4; ++kk) {
+        const double a0 = lane_i[kk * 4 * kStride], a1 = lane_i[kk * 4 * kStride + 8];
 #pragma unroll
-  for (int s = 0; s < SLOTS; ++s) {
-    if (s < nslots) {
-      int r = (int)(desc[s] & 0xffu), c = (int)((desc[s] >> 8) & 0xffu);
-      int i = col0_i + r + g;
-      int j = col0_j + c + 2 * q;
-      if (i < p.n_red) {
-        double* row = p.gram + (int64_t)i * p.n_red;
-        if (j < p.n_red) atomicAdd(row + j, acc[s][0]);
-        if (j + 1 < p.n_red) atomicAdd(row + j + 1, acc[s][1]);
+        for (int cc = 0; cc < 16; ++cc) {
+          const double b = lane_j[kk * 4 * kStride + cc * 8];
+          dmma884(acc[0][cc][0], acc[0][cc][1], a0, b);
+          dmma884(acc[1][cc][0], acc[1][cc][1], a1, b);
+        }
       }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = col0_i + (warp * 2 + r) * 8 + g;
+    if (i >= p.n_red) continue;
+    double* row = p.gram + (int64_t)i * p.n_red;
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) {
+      const int j = col0_j + cc * 8 + 2 * q;
+      if (j < p.n_red) atomicAdd(row + j, acc[r][cc][0]);
+      if (j + 1 < p.n_red) atomicAdd(row + j + 1, acc[r][cc][1]);
     }
   }
 }
@@ -277,41 +291,55 @@ __global__ void symmetrize_kernel(double* g, int n) {
   if (i > j) g[idx] = g[(int64_t)j * n + i];
 }
 
+template <typename T, int KF, int NT>
+static int launch_tri(GramParams& p, size_t smem, int ctas, cudaStream_t stream) {
+  auto kern = gram_tri_kernel<T, KF, NT>;
+  AGF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ctas, kGramThreads, smem, stream>>>(p);
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}
+
 template <typename T, int KF>
 static int launch_gram(GramParams& p, cudaStream_t stream) {
-  const bool staged = (p.n_blocks == 1);
-  const int stride = staged ? panel_stride((p.n_red + 7) & ~7) : panel_stride(kBlockCols);
-  p.stride = stride;
   const int sms = sm_count();
   p.sch = make_schedule(p.forces, p.n_frames, (int64_t)p.n_sites * 3 * sizeof(T), KF);
-  if (staged) {
+  if (p.n_blocks == 1) {
     size_t stage_bytes = ((size_t)KF * p.n_sites * 3 * sizeof(T) + 15) / 16 * 16;
-    size_t smem = (size_t)3 * KF * stride * sizeof(double) + 64 + 2 * stage_bytes;
+    size_t smem = (size_t)3 * KF * kStride * sizeof(double) + 64 + 2 * stage_bytes;
     if (smem <= 113 * 1024) {
       int64_t want = p.sch.n_chunks;
-      p.k_splits = (int32_t)(want < 2 * sms ? (want < 1 ? 1 : want) : 2 * sms);
-      auto kern = gram_kernel<T, KF, 17, true>;
-      AGF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      kern<<<p.k_splits * p.n_pairs, kGramThreads, smem, stream>>>(p);
-      AGF_CUDA_TRY(cudaGetLastError());
-      return AGF_OK;
+      int ctas = (int)(want < 2 * sms ? (want < 1 ? 1 : want) : 2 * sms);
+      switch ((p.n_red + 7) / 8) {
+        case 1: return launch_tri<T, KF, 1>(p, smem, ctas, stream);
+        case 2: return launch_tri<T, KF, 2>(p, smem, ctas, stream);
+        case 3: return launch_tri<T, KF, 3>(p, smem, ctas, stream);
+        case 4: return launch_tri<T, KF, 4>(p, smem, ctas, stream);
+        case 5: return launch_tri<T, KF, 5>(p, smem, ctas, stream);
+        case 6: return launch_tri<T, KF, 6>(p, smem, ctas, stream);
+        case 7: return launch_tri<T, KF, 7>(p, smem, ctas, stream);
+        case 8: return launch_tri<T, KF, 8>(p, smem, ctas, stream);
+        case 9: return launch_tri<T, KF, 9>(p, smem, ctas, stream);
+        case 10: return launch_tri<T, KF, 10>(p, smem, ctas, stream);
+        case 11: return launch_tri<T, KF, 11>(p, smem, ctas, stream);
+        case 12: return launch_tri<T, KF, 12>(p, smem, ctas, stream);
+        case 13: return launch_tri<T, KF, 13>(p, smem, ctas, stream);
+        case 14: return launch_tri<T, KF, 14>(p, smem, ctas, stream);
+        case 15: return launch_tri<T, KF, 15>(p, smem, ctas, stream);
+        default: return launch_tri<T, KF, 16>(p, smem, ctas, stream);
+      }
     }
-    // frames too wide to stage two chunks: fall through to the gather variant
+    // frames too wide to stage two chunks in shared memory: use the gather variant
   }
-  {
-    p.stride = panel_stride(kBlockCols);
-    const int stride = p.stride;
-    size_t smem = (size_t)2 * 3 * KF * stride * sizeof(double) + 64;
-    int64_t ctas_wanted = (int64_t)sms * 2;
-    int64_t ks = (ctas_wanted + p.n_pairs - 1) / p.n_pairs;
-    if (ks > p.sch.n_chunks) ks = p.sch.n_chunks;
-    if (ks < 1) ks = 1;
-    p.k_splits = (int32_t)ks;
-    auto kern = gram_kernel<T, KF, 32, false>;
-    AGF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<p.k_splits * p.n_pairs, kGramThreads, smem, stream>>>(p);
-    AGF_CUDA_TRY(cudaGetLastError());
-  }
+  size_t smem = (size_t)2 * 3 * KF * kStride * sizeof(double);
+  int64_t ks = ((int64_t)sms * 2 + p.n_pairs - 1) / p.n_pairs;
+  if (ks > p.sch.n_chunks) ks = p.sch.n_chunks;
+  if (ks < 1) ks = 1;
+  p.k_splits = (int32_t)ks;
+  auto kern = gram_block_kernel<T, KF>;
+  AGF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<p.k_splits * p.n_pairs, kGramThreads, smem, stream>>>(p);
+  AGF_CUDA_TRY(cudaGetLastError());
   return AGF_OK;
 }
 
@@ -337,14 +365,8 @@ extern "C" int agf_gram_linear(const void* forces, int dtype, int64_t n_frames, 
   p.gram = gram;
   p.n_blocks = (n_red + kBlockCols - 1) / kBlockCols;
   p.n_pairs = p.n_blocks * (p.n_blocks + 1) / 2;
-  const int full_tiles = kBlockCols / 8;
-  const int last_tiles = ((n_red - (p.n_blocks - 1) * kBlockCols) + 7) / 8;
-  build_plan(p.plan[0], full_tiles, full_tiles, true);
-  build_plan(p.plan[1], full_tiles, full_tiles, false);
-  build_plan(p.plan[2], full_tiles, last_tiles, false);
-  build_plan(p.plan[3], last_tiles, last_tiles, true);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == AGF_F32) return launch_gram<float, 16>(p, s);
+  if (dtype == AGF_F32) return launch_gram<float, 12>(p, s);
   return launch_gram<double, 8>(p, s);
 }
 
