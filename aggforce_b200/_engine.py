@@ -274,6 +274,15 @@ class Frames:
                 pass
         return self._dev  # type: ignore[return-value]
 
+    def gather(self, frame_indices: np.ndarray) -> torch.Tensor:
+        """Selected frames ``(len(idx), n_sites, 3)`` on the device."""
+        idx = np.asarray(frame_indices, dtype=np.int64)
+        if self._dev is not None:
+            return self._dev[torch.as_tensor(idx, device=self._dev.device)].contiguous()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            return torch.from_numpy(np.ascontiguousarray(self._host[idx])).to(device())
+
     def prefix(self, n: int) -> torch.Tensor:
         """First ``n`` frames on the device."""
         n = min(n, self.n_frames)

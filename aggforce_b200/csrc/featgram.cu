@@ -1,0 +1,470 @@
+// Kernel (b): featurised Gram for qp_feat_linear_map with Multifeaturize([id_feat, gb_feat]).
+//
+// Replaces src/aggforce/qp/featlinearmap.py:361-370 of the reference together with the feature
+// generators it consumes (id_feat featlinearmap.py:553-627; gb_feat jaxfeat.py:20-567), which
+// materialise a (T, n_fg, n_feat) float32 tensor per bead (475 KB per frame at cln025).  Both
+// feature families are one-hot in the atom's constraint group, so the atom contraction
+// collapses to GROUP forces and the regression row of bead c, frame t, component d is
+//     v[g]               = Fg[t,g,d]                                              g < G
+//     v[G + ch*nb + k]   = g_k(d_ch) Fg[t,ch,d] + kbt m_ch g_k'(d_ch) u_ch[d]     ch < n_ch
+// with d_ch = |mean position of group ch - bead position|, u_ch the unit vector, m_ch the
+// group size, g_k the clipped Gaussian (jaxfeat.py:272-276) and g_k' its derivative (the
+// "reorder" divergence, jaxfeat.py:544-565, with the bead held fixed).  Nothing but the
+// trajectory itself is read from HBM: every CTA regenerates, in float64 and in shared memory,
+// the 128-column slabs of v it needs for its 128x128 block of  P_c = sum_{t,d} v v^T  and feeds
+// them to DMMA.8x8x4 (2 x 16 output tiles per warp, accumulators in registers across the CTA's
+// frame range, RED.ADD.F64 at the end).
+//
+// Also here: agf_feat_rows (the equality-constraint rows of featlinearmap.py:446-450 for a
+// handful of frames) and agf_feat_apply (application of the fitted map, featlinearmap.py:
+// 512-520 + map/core.py:428-430, without materialising per-frame weights).
+#include "common.cuh"
+
+namespace agf {
+
+constexpr int kFgThreads = 256;
+constexpr int kFgWarps = 8;
+constexpr int kFgBlock = 128;   // feature columns per block
+constexpr int kFgStride = 132;  // panel stride (conflict-free DMMA fragment loads)
+constexpr int kFgKF = 8;        // frames per chunk -> 24 panel rows, 6 k-steps
+
+struct FeatParams {
+  const void* coords;
+  const void* forces;
+  int64_t n_frames;
+  int32_t n_sites;
+  const int32_t* grp_ptr;    // [G+1] label -> member sites (CSR)
+  const int32_t* grp_sites;
+  int32_t n_groups;          // G (id features)
+  int32_t n_channels;        // gb channels (G or G-1: SURVEY Q5)
+  const int32_t* bead_ptr;   // [n_cg+1] CSR rows of the coordinate map
+  const int32_t* bead_sites;
+  const double* bead_w;
+  int32_t n_cg;
+  const double* centers;     // [nb]
+  int32_t nb;
+  double inv_width;
+  double clip;
+  double ln_inv_clip;        // -log(clip): Gaussian is exactly 0 once z^2 exceeds it
+  double kbt;
+  int32_t n_feat;            // G + nb * n_channels
+  int32_t n_blocks, n_pairs, k_splits;
+  double* gram;              // [n_cg, n_feat, n_feat] (+=), upper block triangle
+};
+
+template <typename T>
+__device__ __forceinline__ void group_sum(const T* __restrict__ frame, const int32_t* __restrict__ ptr,
+                                          const int32_t* __restrict__ sites, int g, double (&s)[3], double& m) {
+  s[0] = s[1] = s[2] = 0.0;
+  const int b = __ldg(ptr + g), e = __ldg(ptr + g + 1);
+  for (int i = b; i < e; ++i) {
+    const T* p = frame + 3 * __ldg(sites + i);
+    s[0] += to_f64(__ldg(p));
+    s[1] += to_f64(__ldg(p + 1));
+    s[2] += to_f64(__ldg(p + 2));
+  }
+  m = (double)(e - b);
+}
+
+// Gaussian bin k of a distance and its derivative (jaxfeat.py:235-236, 272-276).
+__device__ __forceinline__ void clipped_gauss(double d, double mu, double inv_w, double clip, double ln_inv_clip,
+                                              double& g, double& gp) {
+  const double z = (d - mu) * inv_w;
+  const double zz = z * z;
+  if (zz > ln_inv_clip + 1e-9) {  // exp(-zz) < clip: clipped to exactly zero (NaN falls through)
+    g = 0.0;
+    gp = 0.0;
+    return;
+  }
+  const double e = exp(-zz);
+  g = fmax(e, clip) - clip;
+  gp = (e > clip) ? -2.0 * z * inv_w * e : 0.0;
+  if (e != e) g = e;  // fmax drops NaN; keep it
+}
+
+// Fills panel rows (t,d) x 128 feature columns [col0, col0+128) for the chunk [t0, t0+nf).
+template <typename T>
+__device__ __forceinline__ void fill_feat_panel(const FeatParams& p, const T* __restrict__ coords,
+                                                const T* __restrict__ forces, int64_t t0, int nf, int col0,
+                                                const double (*__restrict__ bead_pos)[3], double* __restrict__ panel) {
+  const int G = p.n_groups, nb = p.nb;
+  const int col1 = min(col0 + kFgBlock, p.n_feat);
+  // id columns of this block: [col0, min(col1, G))
+  const int id_lo = min(col0, G), id_hi = min(col1, G);
+  const int n_id = id_hi - id_lo;
+  // gb channels intersecting the block
+  int ch_lo = 0, ch_hi = 0;
+  if (col1 > G) {
+    ch_lo = (max(col0, G) - G) / nb;
+    ch_hi = (col1 - G + nb - 1) / nb;
+  }
+  const int n_ch = ch_hi - ch_lo;
+  const int per_frame = n_id + n_ch;
+  const int64_t fstride = (int64_t)p.n_sites * 3;
+  // zero padding: columns beyond n_feat, rows beyond nf
+  const int width = col1 - col0;
+  for (int i = threadIdx.x; i < kFgKF * 3 * kFgBlock; i += blockDim.x) {
+    const int r = i / kFgBlock, x = i - r * kFgBlock;
+    if (x >= width || r >= nf * 3) panel[r * kFgStride + x] = 0.0;
+  }
+  for (int item = threadIdx.x; item < nf * per_frame; item += blockDim.x) {
+    const int t = item / per_frame, u = item - t * per_frame;
+    const T* fr_f = forces + (t0 + t) * fstride;
+    double* row = panel + (t * 3) * kFgStride;
+    if (u < n_id) {
+      const int g = id_lo + u;
+      double f[3], m;
+      group_sum<T>(fr_f, p.grp_ptr, p.grp_sites, g, f, m);
+      const int x = g - col0;
+      row[x] = f[0];
+      row[kFgStride + x] = f[1];
+      row[2 * kFgStride + x] = f[2];
+    } else {
+      const int ch = ch_lo + (u - n_id);
+      const T* fr_c = coords + (t0 + t) * fstride;
+      double f[3], pos[3], m;
+      group_sum<T>(fr_f, p.grp_ptr, p.grp_sites, ch, f, m);
+      group_sum<T>(fr_c, p.grp_ptr, p.grp_sites, ch, pos, m);
+      const double dx = pos[0] / m - bead_pos[t][0], dy = pos[1] / m - bead_pos[t][1],
+                   dz = pos[2] / m - bead_pos[t][2];
+      const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+      const double ux = dx / dist, uy = dy / dist, uz = dz / dist;  // NaN at dist == 0
+      const int fbase = G + ch * nb;
+      for (int k = 0; k < nb; ++k) {
+        const int col = fbase + k;
+        if (col < col0 || col >= col1) continue;
+        double g, gp;
+        clipped_gauss(dist, __ldg(p.centers + k), p.inv_width, p.clip, p.ln_inv_clip, g, gp);
+        const double c = p.kbt * m * gp;
+        const int x = col - col0;
+        row[x] = g * f[0] + c * ux;
+        row[kFgStride + x] = g * f[1] + c * uy;
+        row[2 * kFgStride + x] = g * f[2] + c * uz;
+      }
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void bead_positions(const FeatParams& p, const T* __restrict__ coords, int64_t t0, int nf,
+                                               int bead, double (*bead_pos)[3]) {
+  const int64_t fstride = (int64_t)p.n_sites * 3;
+  for (int i = threadIdx.x; i < kFgKF * 3; i += blockDim.x) {
+    const int t = i / 3, d = i - t * 3;
+    double s = 0.0;
+    if (t < nf) {
+      const T* fr = coords + (t0 + t) * fstride;
+      for (int k = __ldg(p.bead_ptr + bead); k < __ldg(p.bead_ptr + bead + 1); ++k)
+        s = fma(__ldg(p.bead_w + k), to_f64(__ldg(fr + 3 * __ldg(p.bead_sites + k) + d)), s);
+    }
+    bead_pos[t][d] = s;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kFgThreads, 1) feat_gram_kernel(const __grid_constant__ FeatParams p) {
+  constexpr int KROWS = 3 * kFgKF;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ double bead_pos[kFgKF][3];
+  // work item: (bead, block pair, k-split)
+  const int per_bead = p.n_pairs * p.k_splits;
+  const int bead = blockIdx.x / per_bead;
+  const int rem0 = blockIdx.x - bead * per_bead;
+  const int pair = rem0 % p.n_pairs, ksplit = rem0 / p.n_pairs;
+  int bi = 0, bj = 0;
+  {
+    int rem = pair, rowlen = p.n_blocks;
+    while (rem >= rowlen) {
+      rem -= rowlen;
+      --rowlen;
+      ++bi;
+    }
+    bj = bi + rem;
+  }
+  const bool diag = bi == bj;
+  double* panel_i = reinterpret_cast<double*>(smem);
+  double* panel_j = diag ? panel_i : panel_i + KROWS * kFgStride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
+  const double* lane_i = panel_i + q * kFgStride + g + warp * 16;
+  const double* lane_j = panel_j + q * kFgStride + g;
+  double acc[2][16][2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
+
+  const T* coords = reinterpret_cast<const T*>(p.coords);
+  const T* forces = reinterpret_cast<const T*>(p.forces);
+  const int64_t n_chunks = (p.n_frames + kFgKF - 1) / kFgKF;
+  for (int64_t c = ksplit; c < n_chunks; c += p.k_splits) {
+    const int64_t t0 = c * kFgKF;
+    const int nf = (int)min((int64_t)kFgKF, p.n_frames - t0);
+    bead_positions<T>(p, coords, t0, nf, bead, bead_pos);
+    __syncthreads();
+    fill_feat_panel<T>(p, coords, forces, t0, nf, bi * kFgBlock, bead_pos, panel_i);
+    if (!diag) fill_feat_panel<T>(p, coords, forces, t0, nf, bj * kFgBlock, bead_pos, panel_j);
+    __syncthreads();
+#pragma unroll 2
+    for (int kk = 0; kk < KROWS / 4; ++kk) {
+      const double a0 = lane_i[kk * 4 * kFgStride], a1 = lane_i[kk * 4 * kFgStride + 8];
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc) {
+        const double b = lane_j[kk * 4 * kFgStride + cc * 8];
+        dmma884(acc[0][cc][0], acc[0][cc][1], a0, b);
+        dmma884(acc[1][cc][0], acc[1][cc][1], a1, b);
+      }
+    }
+    __syncthreads();
+  }
+  double* gram = p.gram + (int64_t)bead * p.n_feat * p.n_feat;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = bi * kFgBlock + (warp * 2 + r) * 8 + g;
+    if (i >= p.n_feat) continue;
+    double* row = gram + (int64_t)i * p.n_feat;
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) {
+      const int j = bj * kFgBlock + cc * 8 + 2 * q;
+      if (j < p.n_feat) atomicAdd(row + j, acc[r][cc][0]);
+      if (j + 1 < p.n_feat) atomicAdd(row + j + 1, acc[r][cc][1]);
+    }
+  }
+}
+
+__global__ void symmetrize_batch_kernel(double* g, int n, int batch) {
+  const int64_t per = (int64_t)n * n;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per * batch) return;
+  const int64_t b = idx / per, r = idx - b * per;
+  const int i = (int)(r / n), j = (int)(r % n);
+  if (i > j) g[idx] = g[b * per + (int64_t)j * n + i];
+}
+
+// ---------------------------------------------------------------------------- equality rows
+// rows[s, c', f] = sum_a cmap[c', a] phi_c[frame_s, a, f]   (featlinearmap.py:446-450) for ONE bead c.
+// phi_c[t, a, :] is one-hot: id column label(a) = 1, gb columns label(a)*nb + k = g_k(d_label(a)).
+template <typename T>
+__global__ void feat_rows_kernel(const FeatParams p, const int64_t* __restrict__ frames, int n_sel, int bead,
+                                 const int32_t* __restrict__ label_of_site, double* __restrict__ rows) {
+  const int64_t total = (int64_t)n_sel * p.n_cg;
+  const T* coords = reinterpret_cast<const T*>(p.coords);
+  const int64_t fstride = (int64_t)p.n_sites * 3;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(idx / p.n_cg), cp = (int)(idx - (int64_t)s * p.n_cg);
+    const T* fr = coords + frames[s] * fstride;
+    double bp[3] = {0, 0, 0};
+    for (int k = p.bead_ptr[bead]; k < p.bead_ptr[bead + 1]; ++k)
+      for (int d = 0; d < 3; ++d) bp[d] = fma(p.bead_w[k], to_f64(fr[3 * p.bead_sites[k] + d]), bp[d]);
+    double* out = rows + idx * p.n_feat;
+    for (int f = 0; f < p.n_feat; ++f) out[f] = 0.0;
+    for (int k = p.bead_ptr[cp]; k < p.bead_ptr[cp + 1]; ++k) {
+      const double w = p.bead_w[k];
+      const int lab = label_of_site[p.bead_sites[k]];
+      out[lab] += w;
+      if (lab < p.n_channels) {
+        double pos[3], m;
+        group_sum<T>(fr, p.grp_ptr, p.grp_sites, lab, pos, m);
+        const double dx = pos[0] / m - bp[0], dy = pos[1] / m - bp[1], dz = pos[2] / m - bp[2];
+        const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+        for (int kb = 0; kb < p.nb; ++kb) {
+          double g, gp;
+          clipped_gauss(dist, p.centers[kb], p.inv_width, p.clip, p.ln_inv_clip, g, gp);
+          out[p.n_groups + lab * p.nb + kb] += w * g;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- featurised map application
+// mapped[t,c,:] = sum_g (coef_c[g] + sum_k coef_c[G+g*nb+k] g_k(d_g)) Fg[t,g,:]
+//               + sum_{g,k} coef_c[G+g*nb+k] m_g g_k'(d_g) u_g          (no kbt: SURVEY Q7)
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) feat_apply_kernel(const FeatParams p, const double* __restrict__ coefs,
+                                                         TO* __restrict__ out, double* sumsq) {
+  const int64_t total = p.n_frames * p.n_cg;
+  const T* coords = reinterpret_cast<const T*>(p.coords);
+  const T* forces = reinterpret_cast<const T*>(p.forces);
+  const int64_t fstride = (int64_t)p.n_sites * 3;
+  double sq = 0.0;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = idx / p.n_cg;
+    const int c = (int)(idx - t * p.n_cg);
+    const T* fc = coords + t * fstride;
+    const T* ff = forces + t * fstride;
+    const double* co = coefs + (int64_t)c * p.n_feat;
+    double bp[3] = {0, 0, 0};
+    for (int k = __ldg(p.bead_ptr + c); k < __ldg(p.bead_ptr + c + 1); ++k)
+      for (int d = 0; d < 3; ++d) bp[d] = fma(__ldg(p.bead_w + k), to_f64(__ldg(fc + 3 * __ldg(p.bead_sites + k) + d)), bp[d]);
+    double o[3] = {0, 0, 0};
+    for (int g = 0; g < p.n_groups; ++g) {
+      double f[3], m;
+      group_sum<T>(ff, p.grp_ptr, p.grp_sites, g, f, m);
+      double w = __ldg(co + g);
+      if (g < p.n_channels) {
+        double pos[3];
+        group_sum<T>(fc, p.grp_ptr, p.grp_sites, g, pos, m);
+        const double dx = pos[0] / m - bp[0], dy = pos[1] / m - bp[1], dz = pos[2] / m - bp[2];
+        const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+        double tr = 0.0;
+        for (int kb = 0; kb < p.nb; ++kb) {
+          double gg, gp;
+          clipped_gauss(dist, __ldg(p.centers + kb), p.inv_width, p.clip, p.ln_inv_clip, gg, gp);
+          const double ck = __ldg(co + p.n_groups + g * p.nb + kb);
+          w = fma(ck, gg, w);
+          tr = fma(ck, gp, tr);
+        }
+        tr *= m;  // NaN when the group sits exactly on the bead, as in the reference
+        o[0] += tr * (dx / dist);
+        o[1] += tr * (dy / dist);
+        o[2] += tr * (dz / dist);
+      }
+      o[0] = fma(w, f[0], o[0]);
+      o[1] = fma(w, f[1], o[1]);
+      o[2] = fma(w, f[2], o[2]);
+    }
+    for (int d = 0; d < 3; ++d) {
+      out[idx * 3 + d] = static_cast<TO>(o[d]);
+      const double r = (double)static_cast<TO>(o[d]);
+      sq += r * r;
+    }
+  }
+  if (sumsq) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sumsq, sq);
+  }
+}
+
+static int fill_params(FeatParams& p, const void* coords, const void* forces, int64_t n_frames, int32_t n_sites,
+                       const int32_t* grp_ptr, const int32_t* grp_sites, int32_t n_groups, int32_t n_channels,
+                       const int32_t* bead_ptr, const int32_t* bead_sites, const double* bead_w, int32_t n_cg,
+                       const double* centers, int32_t nb, double width, double clip, double kbt) {
+  AGF_REQUIRE(coords && grp_ptr && grp_sites && bead_ptr && bead_sites && bead_w && centers, "feat: null pointer");
+  AGF_REQUIRE(n_frames >= 0 && n_sites > 0 && n_groups > 0 && n_channels >= 0 && n_channels <= n_groups && n_cg > 0 &&
+                  nb > 0 && width > 0 && clip > 0 && clip < 1,
+              "feat: bad sizes/parameters");
+  memset(&p, 0, sizeof(p));
+  p.coords = coords;
+  p.forces = forces;
+  p.n_frames = n_frames;
+  p.n_sites = n_sites;
+  p.grp_ptr = grp_ptr;
+  p.grp_sites = grp_sites;
+  p.n_groups = n_groups;
+  p.n_channels = n_channels;
+  p.bead_ptr = bead_ptr;
+  p.bead_sites = bead_sites;
+  p.bead_w = bead_w;
+  p.n_cg = n_cg;
+  p.centers = centers;
+  p.nb = nb;
+  p.inv_width = 1.0 / width;
+  p.clip = clip;
+  p.ln_inv_clip = -log(clip);
+  p.kbt = kbt;
+  p.n_feat = n_groups + nb * n_channels;
+  p.n_blocks = (p.n_feat + kFgBlock - 1) / kFgBlock;
+  p.n_pairs = p.n_blocks * (p.n_blocks + 1) / 2;
+  return AGF_OK;
+}
+
+}  // namespace agf
+
+extern "C" int agf_gram_feat(const void* coords, const void* forces, int dtype, int64_t n_frames, int32_t n_sites,
+                             const int32_t* grp_ptr, const int32_t* grp_sites, int32_t n_groups,
+                             int32_t n_channels, const int32_t* bead_ptr, const int32_t* bead_sites,
+                             const double* bead_w, int32_t n_cg, const double* centers, int32_t nb, double width,
+                             double clip, double kbt, double* gram, void* stream) {
+  using namespace agf;
+  FeatParams p;
+  int rc = fill_params(p, coords, forces, n_frames, n_sites, grp_ptr, grp_sites, n_groups, n_channels, bead_ptr,
+                       bead_sites, bead_w, n_cg, centers, nb, width, clip, kbt);
+  if (rc) return rc;
+  AGF_REQUIRE(forces && gram, "agf_gram_feat: null pointer");
+  AGF_REQUIRE(dtype == AGF_F32 || dtype == AGF_F64, "agf_gram_feat: bad dtype");
+  if (n_frames == 0) return AGF_OK;
+  p.gram = gram;
+  const int64_t n_chunks = (n_frames + kFgKF - 1) / kFgKF;
+  int64_t items = (int64_t)n_cg * p.n_pairs;
+  int64_t ks = (2LL * sm_count() + items - 1) / items;
+  if (ks > n_chunks) ks = n_chunks;
+  if (ks < 1) ks = 1;
+  p.k_splits = (int32_t)ks;
+  const size_t smem = (size_t)2 * 3 * kFgKF * kFgStride * sizeof(double);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int grid = (int)(items * ks);
+  if (dtype == AGF_F32) {
+    AGF_CUDA_TRY(cudaFuncSetAttribute(feat_gram_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    feat_gram_kernel<float><<<grid, kFgThreads, smem, s>>>(p);
+  } else {
+    AGF_CUDA_TRY(cudaFuncSetAttribute(feat_gram_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    feat_gram_kernel<double><<<grid, kFgThreads, smem, s>>>(p);
+  }
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}
+
+extern "C" int agf_symmetrize_batch(double* gram, int32_t n, int32_t batch, void* stream) {
+  using namespace agf;
+  AGF_REQUIRE(gram && n > 0 && batch > 0, "agf_symmetrize_batch: bad arguments");
+  const int64_t total = (int64_t)n * n * batch;
+  symmetrize_batch_kernel<<<(int)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gram, n,
+                                                                                                        batch);
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}
+
+extern "C" int agf_feat_rows(const void* coords, int dtype, int32_t n_sites, const int64_t* frames, int32_t n_sel,
+                             int32_t bead, const int32_t* label_of_site, const int32_t* grp_ptr,
+                             const int32_t* grp_sites, int32_t n_groups, int32_t n_channels,
+                             const int32_t* bead_ptr, const int32_t* bead_sites, const double* bead_w, int32_t n_cg,
+                             const double* centers, int32_t nb, double width, double clip, double* rows,
+                             void* stream) {
+  using namespace agf;
+  FeatParams p;
+  int rc = fill_params(p, coords, nullptr, 1, n_sites, grp_ptr, grp_sites, n_groups, n_channels, bead_ptr,
+                       bead_sites, bead_w, n_cg, centers, nb, width, clip, 0.0);
+  if (rc) return rc;
+  AGF_REQUIRE(frames && label_of_site && rows && n_sel > 0 && bead >= 0 && bead < n_cg, "agf_feat_rows: bad arguments");
+  AGF_REQUIRE(dtype == AGF_F32 || dtype == AGF_F64, "agf_feat_rows: bad dtype");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int total = n_sel * n_cg;
+  const int blocks = (total + 63) / 64;
+  if (dtype == AGF_F32) feat_rows_kernel<float><<<blocks, 64, 0, s>>>(p, frames, n_sel, bead, label_of_site, rows);
+  else feat_rows_kernel<double><<<blocks, 64, 0, s>>>(p, frames, n_sel, bead, label_of_site, rows);
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}
+
+extern "C" int agf_feat_apply(const void* coords, const void* forces, int dtype, int64_t n_frames, int32_t n_sites,
+                              const int32_t* grp_ptr, const int32_t* grp_sites, int32_t n_groups,
+                              int32_t n_channels, const int32_t* bead_ptr, const int32_t* bead_sites,
+                              const double* bead_w, int32_t n_cg, const double* centers, int32_t nb, double width,
+                              double clip, const double* coefs, void* out, int out_dtype, double* sumsq,
+                              void* stream) {
+  using namespace agf;
+  FeatParams p;
+  int rc = fill_params(p, coords, forces, n_frames, n_sites, grp_ptr, grp_sites, n_groups, n_channels, bead_ptr,
+                       bead_sites, bead_w, n_cg, centers, nb, width, clip, 0.0);
+  if (rc) return rc;
+  AGF_REQUIRE(forces && coefs && out, "agf_feat_apply: null pointer");
+  AGF_REQUIRE((dtype == AGF_F32 || dtype == AGF_F64) && (out_dtype == AGF_F32 || out_dtype == AGF_F64),
+              "agf_feat_apply: bad dtype");
+  if (n_frames == 0) return AGF_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t total = n_frames * n_cg;
+  const int64_t want = (total + 255) / 256;
+  const int blocks = (int)(want < (int64_t)sm_count() * 8 ? want : (int64_t)sm_count() * 8);
+#define AGF_FA(TI, TO) \
+  feat_apply_kernel<TI, TO><<<blocks, 256, 0, s>>>(p, coefs, reinterpret_cast<TO*>(out), sumsq)
+  if (dtype == AGF_F32 && out_dtype == AGF_F64) AGF_FA(float, double);
+  else if (dtype == AGF_F32) AGF_FA(float, float);
+  else if (out_dtype == AGF_F64) AGF_FA(double, double);
+  else AGF_FA(double, float);
+#undef AGF_FA
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}

@@ -2,3 +2,14 @@
 from .qplinear import qp_linear_map, qp_form, make_bond_constraint_matrix  # noqa: F401
 from .basicagg import constraint_aware_uni_map  # noqa: F401
 from .solver import DEFAULT_SOLVER_OPTIONS, solve_equality_qp  # noqa: F401
+from .featlinearmap import (  # noqa: F401
+    FeatZipper,
+    Multifeaturize,
+    GeneralizedFeatures,
+    GeneralizedFeaturizer,
+    multifeaturize,
+    qp_feat_linear_map,
+    id_feat,
+)
+from .gbfeat import gb_feat, GbSpec  # noqa: F401
+from .jgauss import joptgauss_map  # noqa: F401

@@ -135,6 +135,57 @@ int agf_pair_screen(const void* xyz, const void* other, int dtype, int64_t n_fra
                     int32_t n_sites, int32_t n_other, double* m2, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * (b) featurised Gram for Multifeaturize([id_feat, gb_feat]).
+ * Replaces  src/aggforce/qp/featlinearmap.py:361-370 (einsum + kbt*div + reg.T @ reg) and the
+ * feature generators src/aggforce/qp/featlinearmap.py:553-627 (id_feat),
+ * src/aggforce/qp/jaxfeat.py:20-567 (gb_feat): features are evaluated in shared memory in
+ * float64 and never written to HBM.
+ *
+ *   coords, forces  device [n_frames, n_sites, 3] (same dtype)
+ *   grp_ptr/grp_sites  CSR label -> member sites, n_groups labels (id_feat's labels)
+ *   n_channels      gb channels: n_groups, or n_groups - 1 to reproduce the reference's dropped
+ *                   last channel (jaxfeat.py:115)
+ *   bead_ptr/bead_sites/bead_w  CSR rows of the coordinate map (bead positions)
+ *   centers         device f64 [nb] Gaussian centres (jaxfeat.py:235-236); width, clip as
+ *                   jaxfeat.py:272-276; kbt multiplies the divergence (featlinearmap.py:368)
+ *   gram            device f64 [n_cg, n_feat, n_feat] (+=), n_feat = n_groups + nb*n_channels,
+ *                   feature order [id | channel-major gb]; UPPER block triangle: call
+ *                   agf_symmetrize_batch afterwards.
+ */
+int agf_gram_feat(const void* coords, const void* forces, int dtype, int64_t n_frames,
+                  int32_t n_sites, const int32_t* grp_ptr, const int32_t* grp_sites,
+                  int32_t n_groups, int32_t n_channels, const int32_t* bead_ptr,
+                  const int32_t* bead_sites, const double* bead_w, int32_t n_cg,
+                  const double* centers, int32_t nb, double width, double clip, double kbt,
+                  double* gram, void* stream);
+
+int agf_symmetrize_batch(double* gram, int32_t n, int32_t batch, void* stream);
+
+/* Equality-constraint rows of one bead's feature QP for a few frames,
+ * rows[s, c', f] = sum_a cmap[c', a] phi_bead[frames[s], a, f]
+ * (src/aggforce/qp/featlinearmap.py:446-450).  frames: device int64 [n_sel];
+ * label_of_site: device int32 [n_sites]; rows: device f64 [n_sel, n_cg, n_feat] (overwritten).
+ */
+int agf_feat_rows(const void* coords, int dtype, int32_t n_sites, const int64_t* frames,
+                  int32_t n_sel, int32_t bead, const int32_t* label_of_site,
+                  const int32_t* grp_ptr, const int32_t* grp_sites, int32_t n_groups,
+                  int32_t n_channels, const int32_t* bead_ptr, const int32_t* bead_sites,
+                  const double* bead_w, int32_t n_cg, const double* centers, int32_t nb,
+                  double width, double clip, double* rows, void* stream);
+
+/* Application of the fitted featurised map (src/aggforce/qp/featlinearmap.py:512-520 +
+ * src/aggforce/map/core.py:428-430): out[t, c, :] = sum_a w[t,c,a] F[t,a,:] + trans[t,c,:] with
+ * per-frame weights w = phi . coef and trans = div . coef (no kbt factor, as the reference),
+ * never materialising w.  coefs: device f64 [n_cg, n_feat]; out [n_frames, n_cg, 3].
+ */
+int agf_feat_apply(const void* coords, const void* forces, int dtype, int64_t n_frames,
+                   int32_t n_sites, const int32_t* grp_ptr, const int32_t* grp_sites,
+                   int32_t n_groups, int32_t n_channels, const int32_t* bead_ptr,
+                   const int32_t* bead_sites, const double* bead_w, int32_t n_cg,
+                   const double* centers, int32_t nb, double width, double clip,
+                   const double* coefs, void* out, int out_dtype, double* sumsq, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Synthetic trajectory generator for benchmarks and tests (counter-based, so any
  * frame range of any sharding reproduces the same data):  frame0 = global index of the
  * first generated frame.  See aggforce_b200/synth.py for the model.

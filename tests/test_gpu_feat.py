@@ -1,0 +1,217 @@
+"""GPU parity for the featurised path (kernel b), the Gaussian maps (config 5) and sharding helpers."""
+import functools
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import pairs_to_set, rel_fro
+
+pytestmark = pytest.mark.gpu
+
+KBT = 0.6955215
+GB = dict(outer=8.0, inner=0.0, n_basis=7, width=1.0)
+
+
+@pytest.fixture(scope="module")
+def topo():
+    from aggforce_b200.synth import chignolin_topology
+
+    return chignolin_topology()
+
+
+@pytest.fixture(scope="module")
+def data(topo):
+    from aggforce_b200.synth import synth_trajectory_host
+
+    return synth_trajectory_host(topo, 40, seed=77)
+
+
+def _cmap(topo):
+    from aggforce_b200 import LinearMap
+
+    return LinearMap([[i] for i in topo.bead_atoms], n_fg_sites=topo.n_sites)
+
+
+def _oracle_features(coords, cm, cons, labels, bead, drop=True):
+    idf, idd = oracle.id_features(coords.shape[0], labels)
+    gf, gd = oracle.gb_features(coords, cm, cons, labels, bead, drop_last_channel=drop, **GB)
+    return np.concatenate([idf, gf], axis=2), np.concatenate([idd, gd], axis=1)
+
+
+def _featurizer():
+    from aggforce_b200.qp import Multifeaturize, gb_feat, id_feat
+    from aggforce_b200.util import Curry
+
+    return Multifeaturize([id_feat, Curry(gb_feat, **GB)])
+
+
+def test_feat_gram_matches_oracle(topo, data):
+    from aggforce_b200 import _engine
+    from aggforce_b200.qp.featlinearmap import _FusedContext, _fusable
+
+    coords, forces = data
+    cmap = _cmap(topo)
+    cons = topo.xh_constraints
+    ctx = _FusedContext(cmap, cons, _fusable(_featurizer()))
+    assert ctx.n_groups == 97 and ctx.n_channels == 96 and len(ctx.columns) == 97 + 7 * 96 == 769
+    grams = ctx.grams(_engine.Frames(coords), _engine.Frames(forces), KBT)
+    assert grams.shape == (10, 769, 769)
+    for bead in (0, 4, 9):
+        feats, divs = _oracle_features(coords, cmap.standard_matrix, cons, ctx.labels, bead)
+        ref = oracle.feat_gram(forces, feats, divs, KBT)
+        assert rel_fro(grams[bead], ref) < 1e-9
+        assert np.array_equal(grams[bead], grams[bead].T)
+    # equality rows for a handful of frames
+    frames = np.array([3, 17, 0, 39, 21])
+    for bead in (2, 7):
+        feats, _ = _oracle_features(coords, cmap.standard_matrix, cons, ctx.labels, bead)
+        a_ref, _ = oracle.feat_constraint_rows(feats, cmap.standard_matrix, bead, frames)
+        a = ctx.constraint_rows(_engine.Frames(coords), bead, frames)
+        assert np.abs(a - a_ref).max() < 1e-12
+
+
+def test_id_only_gram_matches_reference_recording(small_cln, golden, topo):
+    """qp_feat_linear_map(id_feat): Gram recorded from the REFERENCE (float32 there)."""
+    from aggforce_b200 import _engine
+    from aggforce_b200.qp import id_feat
+    from aggforce_b200.qp.featlinearmap import _FusedContext, _fusable
+
+    ref = np.load(golden / "ref_idfeat.npz")
+    cons = pairs_to_set(small_cln["cons10"])
+    ctx = _FusedContext(_cmap(topo), cons, _fusable(id_feat))
+    assert np.array_equal(ctx.labels, ref["ids"])
+    grams = ctx.grams(_engine.Frames(small_cln["coords"]), _engine.Frames(small_cln["forces"]), float(ref["kbt"]))
+    for bead in range(10):
+        assert rel_fro(grams[bead] + 10.0 * np.eye(97), ref["P"][bead]) < 5e-6
+    a = ctx.constraint_rows(_engine.Frames(small_cln["coords"]), 3, ref["frame_choice"])
+    assert np.array_equal(a, ref["A"][3])
+
+
+def test_qp_feat_linear_map_id_matches_reference(small_cln, golden, topo):
+    from aggforce_b200 import Trajectory
+    from aggforce_b200.qp import id_feat, qp_feat_linear_map
+
+    ref = np.load(golden / "ref_idfeat.npz")
+    cons = pairs_to_set(small_cln["cons10"])
+    traj = Trajectory(coords=small_cln["coords"], forces=small_cln["forces"])
+    tmap = qp_feat_linear_map(traj, _cmap(topo), id_feat, float(ref["kbt"]), constraints=cons, l2_regularization=1e1,
+                              constraint_frames=ref["frame_choice"])
+    coefs = np.stack(tmap.force_map.tags["coef_list"])
+    assert rel_fro(coefs, ref["coefs"]) < 1e-4  # reference Gram is float32
+    mapped = tmap(traj)
+    assert rel_fro(mapped.forces, ref["mapped_forces"]) < 1e-4
+    assert rel_fro(mapped.coords, small_cln["mapped_coords"]) < 1e-12
+
+
+@pytest.mark.parametrize("drop", [True, False])
+def test_qp_feat_linear_map_gb_end_to_end(topo, data, drop):
+    from aggforce_b200 import Trajectory, project_forces
+    from aggforce_b200.qp import Multifeaturize, gb_feat, id_feat, qp_feat_linear_map
+
+    coords, forces = data
+    cmap, cons = _cmap(topo), topo.xh_constraints
+    feat = Multifeaturize([id_feat, functools.partial(gb_feat, drop_last_channel=drop, **GB)])
+    frames = np.random.default_rng(42100).choice(len(coords), size=20, replace=False)
+    res = project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds=cons,
+                         method=qp_feat_linear_map, featurizer=feat, kbt=KBT, l2_regularization=1e3,
+                         constraint_frames=frames)
+    coefs = np.stack(res["tmap"].force_map.tags["coef_list"])
+    labels = id_feat(None, cmap, cons, return_ids=True)
+    cm = cmap.standard_matrix
+    ref_coefs, fs, ds = [], [], []
+    for bead in range(10):
+        feats, divs = _oracle_features(coords, cm, cons, labels, bead, drop)
+        p = oracle.feat_gram(forces, feats, divs, KBT, 1e3)
+        a, b = oracle.feat_constraint_rows(feats, cm, bead, frames)
+        ref_coefs.append(oracle.solve_equality_qp(p, a, b))
+        fs.append(feats)
+        ds.append(divs)
+    assert rel_fro(coefs, np.stack(ref_coefs)) < 1e-6
+    ref_mapped = oracle.feat_map_apply(forces, fs, ds, ref_coefs)
+    assert rel_fro(res["mapped_forces"], ref_mapped) < 1e-6
+    assert abs(res["residual"] / oracle.force_smoothness(ref_mapped) - 1) < 1e-6
+    # the CLAMap's scale/trans (reference-style materialised weights) give the same map
+    fm = res["tmap"].force_map
+    t = Trajectory(coords=coords[:6], forces=forces[:6])
+    from aggforce_b200.util import trjdot
+
+    slow = trjdot(t.forces, fm.scale(t.coords)) + fm.trans(t.coords)
+    assert rel_fro(slow, ref_mapped[:6]) < 1e-5  # float32 materialised features
+
+
+def test_generic_featurizer_path_equals_fused(small_cln, golden, topo):
+    from aggforce_b200 import Trajectory
+    from aggforce_b200.qp import id_feat, qp_feat_linear_map
+
+    ref = np.load(golden / "ref_idfeat.npz")
+    cons = pairs_to_set(small_cln["cons10"])
+    traj = Trajectory(coords=small_cln["coords"], forces=small_cln["forces"])
+
+    def custom(points, cmap, constraints):  # not recognised -> generic device path
+        return id_feat(points, cmap, constraints)
+
+    kw = dict(kbt=0.7, constraints=cons, l2_regularization=5.0, constraint_frames=ref["frame_choice"])
+    a = qp_feat_linear_map(traj, _cmap(topo), custom, **kw)
+    b = qp_feat_linear_map(traj, _cmap(topo), id_feat, **kw)
+    ca, cb = np.stack(a.force_map.tags["coef_list"]), np.stack(b.force_map.tags["coef_list"])
+    assert rel_fro(ca, cb) < 1e-9
+    assert rel_fro(a(traj).forces, b(traj).forces) < 1e-9
+
+
+def test_gb_feat_direct_api(topo, data):
+    from aggforce_b200.qp import gb_feat, id_feat
+
+    coords, _ = data
+    cmap, cons = _cmap(topo), topo.xh_constraints
+    out = gb_feat(coords[:5], cmap, cons, lazy=False, **GB)
+    labels = id_feat(None, cmap, cons, return_ids=True)
+    assert out["names"] is None and len(out["feats"]) == 10
+    for bead in (0, 9):
+        gf, gd = oracle.gb_features(coords[:5], cmap.standard_matrix, cons, labels, bead, **GB)
+        assert out["feats"][bead].dtype == np.float32 and out["feats"][bead].shape == gf.shape
+        assert np.abs(out["feats"][bead] - gf).max() < 1e-6
+        assert np.abs(out["divs"][bead] - gd).max() < 1e-5
+
+
+def test_joptgauss_with_injected_noise(topo, data):
+    from aggforce_b200 import Trajectory, joptgauss_map
+
+    coords, forces = data
+    cmap, cons = _cmap(topo), topo.xh_constraints
+    var, kbt = 0.25, KBT
+    noise = np.random.default_rng(5).standard_normal((len(coords), 10, 3))
+    tmap = joptgauss_map(Trajectory(coords=coords, forces=forces), cmap, var=var, kbt=kbt, constraints=cons,
+                         noise=noise, l2_regularization=1e2)
+    w = tmap.tmap.force_map.standard_matrix
+    assert w.shape == (10, 185)
+    full_c, full_f = oracle.gauss_augment(coords, forces, cmap.standard_matrix, var, kbt, noise.astype(np.float32))
+    aug_cm = np.zeros((10, 185))
+    aug_cm[np.arange(10), 175 + np.arange(10)] = 1
+    # the augmenter works in float32 like the reference's JCondNormal: compare on its own arrays
+    ref_w = oracle.qp_linear_weights(full_f.astype(np.float32), aug_cm, cons, 1e2)
+    assert rel_fro(w, ref_w) < 1e-4
+    out = tmap(Trajectory(coords=coords, forces=forces))  # fresh noise: shapes / finiteness only
+    assert out.coords.shape == (len(coords), 10, 3) and np.isfinite(out.forces).all()
+    # noised coordinates scatter around the mapped coordinates with the requested variance
+    resid = out.coords - oracle.apply_map(coords, cmap.standard_matrix)
+    assert abs(resid.var() / var - 1) < 0.2
+
+
+def test_condnormal_device_matches_closed_form(topo, data):
+    from aggforce_b200.trajectory import AugmentedTrajectory, CondNormal, Trajectory
+
+    coords, forces = data
+    cmap = _cmap(topo)
+    noise = np.random.default_rng(9).standard_normal((len(coords), 10, 3)).astype(np.float32)
+    aug = CondNormal(cov=0.4, premap=cmap, noise=noise)
+    at = AugmentedTrajectory.from_trajectory(Trajectory(coords=coords, forces=forces), kbt=0.6, augmenter=aug)
+    rc, rf = oracle.gauss_augment(coords, forces, cmap.standard_matrix, 0.4, 0.6, noise)
+    assert rel_fro(at.coords, rc) < 1e-6 and rel_fro(at.forces, rf) < 1e-6
+    # sample / log_gradient pair (reference tests/test_simplegausstraj.py:13-29 style, atol 2e-6 relative)
+    aug2 = CondNormal(cov=0.4, premap=cmap, noise=noise)
+    y = aug2.sample(coords)
+    gx, gy = aug2.log_gradient(coords, y)
+    assert np.allclose(gy, -(y - oracle.apply_map(coords, cmap.standard_matrix)) / 0.4, atol=1e-4)
+    assert np.allclose(gx[:, topo.bead_atoms], -gy, atol=1e-4)

@@ -199,3 +199,63 @@ def test_chunk_schedule_properties():
                 assert covered == T
                 for s, c in ch[1:]:
                     assert (4096 + off * fb + s * fb) % 16 == 0 or c == 0 or s == ch[1][0] and ch[0][1] >= 16
+
+
+def test_id_labels_match_reference_order(golden):
+    """the label ORDER (which decides the dropped gb channel, Q5) equals the reference's."""
+    from aggforce_b200 import LinearMap
+    from aggforce_b200.qp import id_feat
+    from aggforce_b200.synth import chignolin_topology
+
+    ref = json.loads((golden / "ref_sets.json").read_text())
+    for case in ref["cases"]:
+        cons = {frozenset(g) for g in case["constraints"]}
+        lab = id_feat(None, LinearMap([[0]], n_fg_sites=case["n"]), cons, return_ids=True)
+        assert lab.dtype == np.int32 and [int(v) for v in lab] == case["ref_labels"]
+    topo = chignolin_topology()
+    cmap = LinearMap([[i] for i in topo.bead_atoms], n_fg_sites=175)
+    assert [int(v) for v in id_feat(None, cmap, topo.xh_constraints, return_ids=True)] == ref["cln_ids"]
+    out = id_feat(np.zeros((3, 175, 3)), cmap, topo.xh_constraints)
+    assert out["feats"][0].shape == (3, 175, 97) and out["feats"][0].dtype == np.float32
+    assert out["feats"][0] is out["feats"][9] and out["divs"][0].shape == (3, 97, 3) and out["names"] is None
+    assert (out["feats"][0].sum(axis=2) == 1).all()
+
+
+def test_featzipper_and_multifeaturize():
+    from aggforce_b200.qp import FeatZipper, Multifeaturize
+
+    def f1(points, cmap, cons):
+        return {"feats": (np.full((2, 3, 1), b) for b in range(2)), "divs": (np.zeros((2, 1, 3)) for _ in range(2)),
+                "names": None}
+
+    def f2(points, cmap, cons):
+        return {"feats": [np.full((2, 3, 2), 10 + b) for b in range(2)], "divs": [np.ones((2, 2, 3))] * 2,
+                "names": None}
+
+    z = Multifeaturize([f1, f2])(None, None, None)
+    assert isinstance(z, FeatZipper) and z["names"] is None and set(z.keys()) == {"feats", "divs", "names"}
+    feats = list(z["feats"])
+    divs = list(z["divs"])
+    assert len(feats) == 2 and feats[1].shape == (2, 3, 3) and (feats[1][..., 0] == 1).all() and (feats[1][..., 1:] == 11).all()
+    assert divs[0].shape == (2, 3, 3)
+    with pytest.raises(KeyError):
+        z["nope"]
+    assert "Multifeaturize" in str(Multifeaturize([f1])) and "C0:" in repr(Multifeaturize([f1]))
+
+
+def test_fusable_featurizer_recognition():
+    import functools
+
+    from aggforce_b200.qp import Multifeaturize, gb_feat, id_feat
+    from aggforce_b200.qp.featlinearmap import _fusable
+    from aggforce_b200.util import Curry
+
+    plan = _fusable(Multifeaturize([id_feat, Curry(gb_feat, inner=0, outer=8, width=1, n_basis=7)]))
+    assert plan is not None and [b[0] for b in plan.blocks] == ["id", "gb"]
+    assert plan.spec.n_basis == 7 and plan.spec.drop_last_channel and plan.spec.n_channels(97) == 96
+    assert np.allclose(plan.spec.centers(), oracle.gb_centers(0, 8, 7))
+    assert [b[0] for b in _fusable(Multifeaturize([functools.partial(gb_feat, outer=6.0), id_feat])).blocks] == ["gb", "id"]
+    assert _fusable(id_feat) is not None
+    assert _fusable(lambda p, c, k: None) is None
+    assert _fusable(Multifeaturize([id_feat, id_feat])) is None
+    assert _fusable(Curry(gb_feat, 8.0)) is None  # positional args are not introspected
