@@ -389,6 +389,25 @@ def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float,
     return out, sumsq, flags
 
 
+def merge_moments(parts: Sequence[np.ndarray], n_pairs: int) -> np.ndarray:
+    """Population sd per pair from per-rank ``[count, mean(P), M2(P)]`` records (Chan's pairwise
+    update in float64); NaN moments stay NaN."""
+    cnt, mu, m2t = 0.0, np.zeros(n_pairs), np.zeros(n_pairs)
+    for part in parts:
+        tb, mb, m2b = part[0], part[1 : 1 + n_pairs], part[1 + n_pairs :]
+        if tb == 0:
+            continue
+        delta = mb - mu
+        tot = cnt + tb
+        m2t = m2t + m2b + delta * delta * cnt * tb / tot
+        mu = mu + delta * tb / tot
+        cnt = tot
+    with np.errstate(invalid="ignore"):
+        sd = np.sqrt(np.maximum(m2t, 0.0) / cnt)
+    sd[np.isnan(m2t)] = np.nan
+    return sd
+
+
 _SCREEN_FRAMES = 32
 _RESCREEN_FRAMES = 4096
 
@@ -473,17 +492,5 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
     else:
         mean, m2_local = np.zeros(n_pairs), np.zeros(n_pairs)
     parts = allgather_host(np.concatenate([[float(t_local)], mean, m2_local]))
-    cnt, mu, m2t = 0.0, np.zeros(n_pairs), np.zeros(n_pairs)
-    for part in parts:
-        tb, mb, m2b = part[0], part[1 : 1 + n_pairs], part[1 + n_pairs :]
-        if tb == 0:
-            continue
-        delta = mb - mu
-        tot = cnt + tb
-        m2t = m2t + m2b + delta * delta * cnt * tb / tot
-        mu = mu + delta * tb / tot
-        cnt = tot
-    with np.errstate(invalid="ignore"):
-        sd = np.sqrt(np.maximum(m2t, 0.0) / cnt)
-    sd[np.isnan(m2t)] = np.nan
+    sd = merge_moments(parts, n_pairs)
     return to_host(pairs).astype(np.int64), sd
