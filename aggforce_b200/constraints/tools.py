@@ -5,7 +5,8 @@ Same results as the reference's ``src/aggforce/constraints/tools.py``:
 """
 from __future__ import annotations
 
-from typing import Dict, Iterable
+import functools
+from typing import Dict, Iterable, Tuple
 
 from .hints import Constraints
 
@@ -45,6 +46,39 @@ def reduce_constraint_sets(constraints: Constraints) -> Constraints:
         if not pool:
             return out
         merged = frozenset(pool.pop())
+
+
+@functools.lru_cache(maxsize=64)
+def _merged_groups_cached(key: frozenset) -> Tuple[Tuple[int, ...], ...]:
+    parent: Dict[int, int] = {}
+
+    def find(a: int) -> int:
+        while parent[a] != a:
+            parent[a] = parent[parent[a]]
+            a = parent[a]
+        return a
+
+    for grp in key:
+        members = list(grp)
+        for v in members:
+            parent.setdefault(v, v)
+        for v in members[1:]:
+            ra, rb = find(members[0]), find(v)
+            if ra != rb:
+                parent[max(ra, rb)] = min(ra, rb)
+    comps: Dict[int, list] = {}
+    for v in parent:
+        comps.setdefault(find(v), []).append(v)
+    return tuple(sorted((tuple(sorted(int(x) for x in c)) for c in comps.values()), key=lambda g: g[0]))
+
+
+def merged_groups(constraints: Iterable[Iterable[int]]) -> Tuple[Tuple[int, ...], ...]:
+    """The partition ``reduce_constraint_sets`` computes, as sorted tuples ordered by anchor.
+
+    Union-find, memoised on the constraint set: the fit / map builders call this on every
+    ``project_forces`` and only need the partition, not the reference's set iteration order.
+    """
+    return _merged_groups_cached(frozenset(frozenset(g) for g in constraints))
 
 
 def constraint_lookup_dict(constraints: Iterable[Iterable[int]]) -> Dict[int, int]:

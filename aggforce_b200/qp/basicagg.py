@@ -8,7 +8,7 @@ from typing import Union
 
 import numpy as np
 
-from ..constraints import Constraints, reduce_constraint_sets
+from ..constraints import Constraints, merged_groups
 from ..map import LinearMap, SeperableTMap
 from ..trajectory import ForcesTrajectory
 
@@ -21,7 +21,7 @@ def constraint_aware_uni_map(
     """Each bead sums, unweighted, the forces of its own sites and of every site constrained
     (transitively) to one of them.  ``traj`` is ignored."""
     matrix = np.asarray(coord_map.standard_matrix)
-    groups = [sorted(g) for g in reduce_constraint_sets(set() if constraints is None else constraints)]
+    groups = merged_groups(set() if constraints is None else constraints)
     out = np.zeros_like(matrix)
     for bead, row in enumerate(matrix):
         members = set(np.nonzero(row)[0].tolist())

@@ -116,9 +116,17 @@ def _label_groups(n_fg_sites: int, constraints: Constraints) -> List[frozenset]:
     copy, then ``union`` with the singletons).  ``tests/test_host_logic.py`` pins the resulting
     label vectors against the reference on random inputs.
     """
-    groups = deepcopy(constraints)
-    groups = groups.union(frozenset([x]) for x in range(n_fg_sites))
-    return sorted(reduce_constraint_sets(groups))
+    key = (n_fg_sites, frozenset(frozenset(g) for g in constraints))
+    if key not in _LABEL_CACHE:
+        if len(_LABEL_CACHE) > 32:
+            _LABEL_CACHE.clear()
+        groups = deepcopy(constraints)
+        groups = groups.union(frozenset([x]) for x in range(n_fg_sites))
+        _LABEL_CACHE[key] = sorted(reduce_constraint_sets(groups))
+    return _LABEL_CACHE[key]
+
+
+_LABEL_CACHE: Dict[Any, List[frozenset]] = {}
 
 
 def id_feat(points, cmap: LinearMap, constraints: Constraints, return_ids: bool = False):

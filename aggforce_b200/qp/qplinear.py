@@ -9,7 +9,7 @@ from typing import Union
 import numpy as np
 
 from .. import _engine
-from ..constraints import Constraints, constraint_lookup_dict, reduce_constraint_sets
+from ..constraints import Constraints, constraint_lookup_dict, merged_groups
 from ..map import LinearMap, SeperableTMap
 from ..trajectory import ForcesTrajectory
 from .solver import DEFAULT_SOLVER_OPTIONS, SolverOptions, solve
@@ -23,7 +23,7 @@ def reduced_columns(n_sites: int, constraints: Constraints) -> np.ndarray:
     dependent member of a merged constraint group opens the next column; dependents reuse
     their anchor's (the smallest index of their group).
     """
-    anchor_of = constraint_lookup_dict(reduce_constraint_sets(constraints))
+    anchor_of = constraint_lookup_dict(merged_groups(constraints))
     cols = np.full(n_sites, -1, dtype=np.int64)
     free = [s for s in range(n_sites) if s not in anchor_of]
     cols[free] = np.arange(len(free))
