@@ -312,8 +312,19 @@ def csr_from_labels(labels: np.ndarray, n_groups: int) -> Tuple[np.ndarray, np.n
 # kernel wrappers
 # --------------------------------------------------------------------------------------
 def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Tensor:
-    """Kernel (a): all-reduced, symmetrised second-moment matrix (device f64 [n_red, n_red])."""
-    ptr_, sites = csr_from_labels(col_of_site, n_red)
+    """Kernel (a): all-reduced, symmetrised second-moment matrix (device f64 [n_red, n_red]).
+
+    Internally the reduced columns are ordered by group size (singles, pairs, ...) so that the
+    lanes of a warp walk member lists of equal length while they build the f64 panel; the result
+    is permuted back to the caller's column order.
+    """
+    col_of_site = np.asarray(col_of_site, dtype=np.int64)
+    sizes = np.bincount(col_of_site[col_of_site >= 0], minlength=n_red)
+    order = np.argsort(sizes, kind="stable")  # internal position -> caller's column
+    rank = np.empty(n_red, dtype=np.int64)
+    rank[order] = np.arange(n_red)
+    internal = np.where(col_of_site >= 0, rank[np.maximum(col_of_site, 0)], -1)
+    ptr_, sites = csr_from_labels(internal, n_red)
     d_ptr, d_sites = dev_i32(ptr_), dev_i32(sites)
     gram = torch.zeros((n_red, n_red), dtype=torch.float64, device=device())
     for _, piece in frames.pieces():
@@ -321,6 +332,9 @@ def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Te
                   ptr(d_sites), n_red, ptr(gram), stream_ptr())
     allreduce_sum_(gram)
     _lib.call("agf_symmetrize", ptr(gram), n_red, stream_ptr())
+    if not np.array_equal(order, np.arange(n_red)):
+        back = torch.as_tensor(rank, device=gram.device)
+        gram = gram[back][:, back]
     return gram
 
 

@@ -160,46 +160,174 @@ __device__ __forceinline__ void fill_panel(const T* __restrict__ frames, int nf,
 }
 
 // ------------------------------------------------------------------ single block (n_red <= 128), TMA staged
+// Warp-specialised CTA (one per SM): 8 MMA warps sweep panel[j & 1] while 4 fill warps convert
+// the next raw chunk into panel[(j+1) & 1] and keep the TMA ring full, so the DMMA pipe never
+// waits for a block-wide barrier.
+//   raw_full[s]   : TMA bulk copy of a chunk landed            (tx-count mbarrier)
+//   panel_full[b] : fill warps finished panel b                (1 arrival, after a named barrier)
+//   panel_empty[b]: all 8 MMA warps finished sweeping panel b  (8 arrivals)
+constexpr int kMmaWarps = 8;
+constexpr int kFillWarps = 8;
+constexpr int kTriThreads = (kMmaWarps + kFillWarps) * 32;
+constexpr int kFillThreads = kFillWarps * 32;
+constexpr int kRawStages = 3;
+
 template <typename T, int KF, int NT>
-__global__ void __launch_bounds__(kGramThreads, 2) gram_tri_kernel(const __grid_constant__ GramParams p) {
+__global__ void __launch_bounds__(kTriThreads, 1) gram_tri_kernel(const __grid_constant__ GramParams p) {
   constexpr int KROWS = 3 * KF;
-  constexpr int STAGES = 2;
+  constexpr int NCOLS = NT * 8;
   static_assert(KROWS % 4 == 0, "k rows must be a multiple of the DMMA k");
   extern __shared__ __align__(128) unsigned char smem[];
-  double* panel = reinterpret_cast<double*>(smem);
-  size_t off = (size_t)KROWS * kStride * sizeof(double);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + off);
+  double* panel0 = reinterpret_cast<double*>(smem);
+  size_t off = (size_t)2 * KROWS * kStride * sizeof(double);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off);
+  uint64_t* raw_full = bars;                // [kRawStages]
+  uint64_t* panel_full = bars + kRawStages; // [2]
+  uint64_t* panel_empty = panel_full + 2;   // [2]
   off += 64;
+  int32_t* s_ptr = reinterpret_cast<int32_t*>(smem + off);  // CSR copy: [n_red + 1] + [n_sites]
+  int32_t* s_sites = s_ptr + (p.n_red + 1);
+  off += (size_t)(p.n_red + 1 + p.n_sites) * 4;
+  off = (off + 127) / 128 * 128;
   T* raw = reinterpret_cast<T*>(smem + off);
+  const int64_t frame_elems = (int64_t)p.n_sites * 3;
+  const int64_t stage_elems = ((int64_t)KF * frame_elems * (int64_t)sizeof(T) + 15) / 16 * 16 / (int64_t)sizeof(T);
+
+  for (int i = threadIdx.x; i <= p.n_red; i += blockDim.x) s_ptr[i] = p.col_ptr[i];
+  for (int i = threadIdx.x; i < p.col_ptr[p.n_red]; i += blockDim.x) s_sites[i] = p.col_sites[i];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kRawStages; ++i) mbar_init(&raw_full[i], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&panel_full[i], 1);
+      mbar_init(&panel_empty[i], kMmaWarps);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* forces = reinterpret_cast<const T*>(p.forces);
+  // this CTA's chunks: c_j = first + j * step, skipping the head chunk when it is empty
+  const int64_t step = gridDim.x;
+  int64_t first = blockIdx.x;
+  if (first == 0 && p.sch.head == 0) first += step;
+  const int64_t n_mine = p.sch.n_chunks > first ? (p.sch.n_chunks - first + step - 1) / step : 0;
+
+  auto bulkable = [&](int64_t c) {
+    const int64_t bytes = (int64_t)p.sch.count(c) * frame_elems * (int64_t)sizeof(T);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(forces + p.sch.start(c) * frame_elems);
+    return c != 0 && bytes > 0 && (bytes % 16) == 0 && (a % 16) == 0;
+  };
+  auto issue = [&](int64_t j) {  // one thread: TMA for local chunk j (no-op when not bulk-copyable)
+    if (j >= n_mine) return;
+    const int64_t c = first + j * step;
+    if (!bulkable(c)) return;
+    const int stage = (int)(j % kRawStages);
+    const uint32_t bytes = (uint32_t)((int64_t)p.sch.count(c) * frame_elems * (int64_t)sizeof(T));
+    fence_proxy_async();
+    mbar_expect_tx(&raw_full[stage], bytes);
+    const char* src = reinterpret_cast<const char*>(forces + p.sch.start(c) * frame_elems);
+    char* dst = reinterpret_cast<char*>(raw + (int64_t)stage * stage_elems);
+    uint32_t done = 0;
+    while (done < bytes) {
+      const uint32_t piece = bytes - done < 65536u ? bytes - done : 65536u;
+      tma_bulk_g2s(dst + done, src + done, piece, &raw_full[stage]);
+      done += piece;
+    }
+  };
+
+  if (warp >= kMmaWarps) {
+    // ------------------------------------------------ fill warps
+    const int ft = threadIdx.x - kMmaWarps * 32;  // 0..127
+    if (ft == 0) {
+      for (int j = 0; j < kRawStages; ++j) issue(j);
+    }
+    uint32_t raw_phase = 0;  // bit s: parity to wait for on raw_full[s]
+    constexpr int TPC = (kFillThreads / NCOLS) < 1 ? 1 : ((kFillThreads / NCOLS) > KF ? KF : (kFillThreads / NCOLS));
+    const int my_x = ft < NCOLS * TPC ? ft % NCOLS : NCOLS, my_slot = ft / NCOLS;
+    int my_cnt = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    if (my_x < p.n_red) {
+      const int b = s_ptr[my_x];
+      my_cnt = s_ptr[my_x + 1] - b;
+      if (my_cnt > 0) m0 = 3 * s_sites[b];
+      if (my_cnt > 1) m1 = 3 * s_sites[b + 1];
+      if (my_cnt > 2) m2 = 3 * s_sites[b + 2];
+      if (my_cnt > 3) m3 = 3 * s_sites[b + 3];
+    }
+    for (int64_t j = 0; j < n_mine; ++j) {
+      const int64_t c = first + j * step;
+      const int nf = p.sch.count(c);
+      const int stage = (int)(j % kRawStages), pb = (int)(j & 1);
+      T* stage_ptr = raw + (int64_t)stage * stage_elems;
+      if (bulkable(c)) {
+        mbar_wait(&raw_full[stage], (raw_phase >> stage) & 1u);
+        raw_phase ^= (1u << stage);
+      } else {
+        const T* src = forces + p.sch.start(c) * frame_elems;
+        for (int64_t i = ft; i < (int64_t)nf * frame_elems; i += kFillThreads) stage_ptr[i] = src[i];
+        asm volatile("bar.sync 1, %0;" ::"n"(kFillThreads) : "memory");
+      }
+      mbar_wait(&panel_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
+      double* panel = panel0 + (size_t)pb * KROWS * kStride;
+      // thread = (column x, frame slot): the member list of x is read once, then the thread walks
+      // its frames with independent dependency chains (ILP instead of many resident warps)
+      if (my_x < NCOLS) {
+        if (my_cnt <= 4) {
+#pragma unroll 4
+          for (int t = my_slot; t < KF; t += TPC) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            if (t < nf) {
+              const T* fr = stage_ptr + (int64_t)t * frame_elems;
+              if (my_cnt > 0) { s0 = to_f64(fr[m0]); s1 = to_f64(fr[m0 + 1]); s2 = to_f64(fr[m0 + 2]); }
+              if (my_cnt > 1) { s0 += to_f64(fr[m1]); s1 += to_f64(fr[m1 + 1]); s2 += to_f64(fr[m1 + 2]); }
+              if (my_cnt > 2) { s0 += to_f64(fr[m2]); s1 += to_f64(fr[m2 + 1]); s2 += to_f64(fr[m2 + 2]); }
+              if (my_cnt > 3) { s0 += to_f64(fr[m3]); s1 += to_f64(fr[m3 + 1]); s2 += to_f64(fr[m3 + 2]); }
+            }
+            double* dst = panel + (t * 3) * kStride + my_x;
+            dst[0] = s0;
+            dst[kStride] = s1;
+            dst[2 * kStride] = s2;
+          }
+        } else {
+          for (int t = my_slot; t < KF; t += TPC) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            if (t < nf) {
+              const T* fr = stage_ptr + (int64_t)t * frame_elems;
+              for (int m = s_ptr[my_x]; m < s_ptr[my_x + 1]; ++m) {
+                const T* q = fr + 3 * s_sites[m];
+                s0 += to_f64(q[0]);
+                s1 += to_f64(q[1]);
+                s2 += to_f64(q[2]);
+              }
+            }
+            double* dst = panel + (t * 3) * kStride + my_x;
+            dst[0] = s0;
+            dst[kStride] = s1;
+            dst[2 * kStride] = s2;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kFillThreads) : "memory");  // panel written, raw stage drained
+      if (ft == 0) {
+        mbar_arrive(&panel_full[pb]);
+        issue(j + kRawStages);
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------- MMA warps
   const int g = lane >> 2, q = lane & 3;
-  const double* lane_panel = panel + q * kStride + g;
   double acc[kMaxTriSlots][2];
 #pragma unroll
   for (int s = 0; s < kMaxTriSlots; ++s) acc[s][0] = acc[s][1] = 0.0;
-
-  const T* forces = reinterpret_cast<const T*>(p.forces);
-  const int64_t n_chunks = p.sch.n_chunks;
-  const int64_t first = blockIdx.x, step = gridDim.x;
-  FrameStager<T, STAGES> st;
-  st.init(raw, full, forces, (int64_t)p.n_sites * 3, p.sch);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) st.issue(first + (int64_t)s * step, s);
-  }
-  int stage = 0;
-  for (int64_t c = first; c < n_chunks; c += step) {
-    const int nf = p.sch.count(c);
-    if (nf > 0) {
-      st.wait(c, stage);
-      fill_panel<T, false>(st.stage_ptr(stage), nf, KF, p.n_sites, p.col_ptr, p.col_sites, 0, p.n_red, NT * 8, panel);
-    }
-    __syncthreads();  // panel complete, raw stage free
-    if (threadIdx.x == 0) st.issue(c + (int64_t)STAGES * step, stage);
-    if (nf > 0) tri_sweep_warp<NT, KROWS / 4>(warp, lane_panel, acc);
-    __syncthreads();  // panel free
-    stage = (stage + 1) % STAGES;
+  for (int64_t j = 0; j < n_mine; ++j) {
+    const int pb = (int)(j & 1);
+    mbar_wait(&panel_full[pb], (uint32_t)((j >> 1) & 1));
+    const double* lane_panel = panel0 + (size_t)pb * KROWS * kStride + q * kStride + g;
+    tri_sweep_warp<NT, KROWS / 4>(warp, lane_panel, acc);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&panel_empty[pb]);
   }
   switch (warp) {
     case 0: tri_store<NT, 0>(acc, p.gram, p.n_red, g, q); break;
@@ -295,42 +423,58 @@ template <typename T, int KF, int NT>
 static int launch_tri(GramParams& p, size_t smem, int ctas, cudaStream_t stream) {
   auto kern = gram_tri_kernel<T, KF, NT>;
   AGF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<ctas, kGramThreads, smem, stream>>>(p);
+  kern<<<ctas, kTriThreads, smem, stream>>>(p);
   AGF_CUDA_TRY(cudaGetLastError());
   return AGF_OK;
 }
 
 template <typename T, int KF>
-static int launch_gram(GramParams& p, cudaStream_t stream) {
+static size_t tri_smem_bytes(const GramParams& p) {
+  size_t off = (size_t)2 * 3 * KF * kStride * sizeof(double) + 64 + (size_t)(p.n_red + 1 + p.n_sites) * 4;
+  off = (off + 127) / 128 * 128;
+  size_t stage_bytes = ((size_t)KF * p.n_sites * 3 * sizeof(T) + 15) / 16 * 16;
+  return off + kRawStages * stage_bytes;
+}
+
+template <typename T, int KF>
+static int dispatch_tri(GramParams& p, cudaStream_t stream) {
   const int sms = sm_count();
   p.sch = make_schedule(p.forces, p.n_frames, (int64_t)p.n_sites * 3 * sizeof(T), KF);
-  if (p.n_blocks == 1) {
-    size_t stage_bytes = ((size_t)KF * p.n_sites * 3 * sizeof(T) + 15) / 16 * 16;
-    size_t smem = (size_t)3 * KF * kStride * sizeof(double) + 64 + 2 * stage_bytes;
-    if (smem <= 113 * 1024) {
-      int64_t want = p.sch.n_chunks;
-      int ctas = (int)(want < 2 * sms ? (want < 1 ? 1 : want) : 2 * sms);
-      switch ((p.n_red + 7) / 8) {
-        case 1: return launch_tri<T, KF, 1>(p, smem, ctas, stream);
-        case 2: return launch_tri<T, KF, 2>(p, smem, ctas, stream);
-        case 3: return launch_tri<T, KF, 3>(p, smem, ctas, stream);
-        case 4: return launch_tri<T, KF, 4>(p, smem, ctas, stream);
-        case 5: return launch_tri<T, KF, 5>(p, smem, ctas, stream);
-        case 6: return launch_tri<T, KF, 6>(p, smem, ctas, stream);
-        case 7: return launch_tri<T, KF, 7>(p, smem, ctas, stream);
-        case 8: return launch_tri<T, KF, 8>(p, smem, ctas, stream);
-        case 9: return launch_tri<T, KF, 9>(p, smem, ctas, stream);
-        case 10: return launch_tri<T, KF, 10>(p, smem, ctas, stream);
-        case 11: return launch_tri<T, KF, 11>(p, smem, ctas, stream);
-        case 12: return launch_tri<T, KF, 12>(p, smem, ctas, stream);
-        case 13: return launch_tri<T, KF, 13>(p, smem, ctas, stream);
-        case 14: return launch_tri<T, KF, 14>(p, smem, ctas, stream);
-        case 15: return launch_tri<T, KF, 15>(p, smem, ctas, stream);
-        default: return launch_tri<T, KF, 16>(p, smem, ctas, stream);
-      }
-    }
-    // frames too wide to stage two chunks in shared memory: use the gather variant
+  const size_t smem = tri_smem_bytes<T, KF>(p);
+  int64_t want = p.sch.n_chunks;
+  int ctas = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
+  switch ((p.n_red + 7) / 8) {
+    case 1: return launch_tri<T, KF, 1>(p, smem, ctas, stream);
+    case 2: return launch_tri<T, KF, 2>(p, smem, ctas, stream);
+    case 3: return launch_tri<T, KF, 3>(p, smem, ctas, stream);
+    case 4: return launch_tri<T, KF, 4>(p, smem, ctas, stream);
+    case 5: return launch_tri<T, KF, 5>(p, smem, ctas, stream);
+    case 6: return launch_tri<T, KF, 6>(p, smem, ctas, stream);
+    case 7: return launch_tri<T, KF, 7>(p, smem, ctas, stream);
+    case 8: return launch_tri<T, KF, 8>(p, smem, ctas, stream);
+    case 9: return launch_tri<T, KF, 9>(p, smem, ctas, stream);
+    case 10: return launch_tri<T, KF, 10>(p, smem, ctas, stream);
+    case 11: return launch_tri<T, KF, 11>(p, smem, ctas, stream);
+    case 12: return launch_tri<T, KF, 12>(p, smem, ctas, stream);
+    case 13: return launch_tri<T, KF, 13>(p, smem, ctas, stream);
+    case 14: return launch_tri<T, KF, 14>(p, smem, ctas, stream);
+    case 15: return launch_tri<T, KF, 15>(p, smem, ctas, stream);
+    default: return launch_tri<T, KF, 16>(p, smem, ctas, stream);
   }
+}
+
+// KFBIG / KFSMALL: frames per chunk of the staged kernel (the larger one when it fits in smem).
+template <typename T, int KFBIG, int KFSMALL>
+static int launch_gram(GramParams& p, cudaStream_t stream) {
+  const int sms = sm_count();
+  const size_t budget = 226 * 1024;
+  if (p.n_blocks == 1) {
+    if (tri_smem_bytes<T, KFBIG>(p) <= budget) return dispatch_tri<T, KFBIG>(p, stream);
+    if (tri_smem_bytes<T, KFSMALL>(p) <= budget) return dispatch_tri<T, KFSMALL>(p, stream);
+    // frames too wide to stage in shared memory: use the gather variant
+  }
+  constexpr int KF = KFSMALL;
+  p.sch = make_schedule(p.forces, p.n_frames, (int64_t)p.n_sites * 3 * sizeof(T), KF);
   size_t smem = (size_t)2 * 3 * KF * kStride * sizeof(double);
   int64_t ks = ((int64_t)sms * 2 + p.n_pairs - 1) / p.n_pairs;
   if (ks > p.sch.n_chunks) ks = p.sch.n_chunks;
@@ -366,8 +510,8 @@ extern "C" int agf_gram_linear(const void* forces, int dtype, int64_t n_frames, 
   p.n_blocks = (n_red + kBlockCols - 1) / kBlockCols;
   p.n_pairs = p.n_blocks * (p.n_blocks + 1) / 2;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == AGF_F32) return launch_gram<float, 12>(p, s);
-  return launch_gram<double, 8>(p, s);
+  if (dtype == AGF_F32) return launch_gram<float, 16, 8>(p, s);
+  return launch_gram<double, 8, 4>(p, s);
 }
 
 extern "C" int agf_symmetrize(double* gram, int32_t n, void* stream) {
