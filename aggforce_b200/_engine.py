@@ -372,6 +372,14 @@ class CompiledMap:
                 relabel[z + 1 :] -= 1
                 inverse = relabel[inverse]
                 uniq = np.delete(uniq, z, axis=0)
+        # order unique columns by member count: the lanes of a warp then walk member lists of equal
+        # length (f32->f64 conversions issue per warp instruction, divergent lists would serialise)
+        sizes = np.bincount(inverse[inverse >= 0], minlength=uniq.shape[0])
+        order = np.argsort(sizes, kind="stable")
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        inverse = np.where(inverse >= 0, rank[np.maximum(inverse, 0)], -1)
+        uniq = uniq[order]
         ptr_, sites = csr_from_labels(inverse, uniq.shape[0])
         self.n_ucol, self.nnz = int(uniq.shape[0]), int(sites.size)
         self.ucol_ptr, self.ucol_sites = dev_i32(ptr_), dev_i32(sites)

@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(con
           mbar_expect_tx(&full[stage], (uint32_t)bytes);
           uint32_t done = 0;
           while (done < (uint32_t)bytes) {
-            const uint32_t piece = (uint32_t)bytes - done < 65536u ? (uint32_t)bytes - done : 65536u;
+            const uint32_t piece = (uint32_t)bytes - done < kBulkPiece ? (uint32_t)bytes - done : kBulkPiece;
             tma_bulk_g2s(reinterpret_cast<char*>(dst) + done, reinterpret_cast<const char*>(src) + done, piece,
                          &full[stage]);
             done += piece;

@@ -60,6 +60,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Arrive without the release fence (no MEMBAR.ALL.CTA).  Only for use right after a bar.sync that
+// already ordered the producers' shared-memory writes (BAR.SYNC drains pending STS).
+__device__ __forceinline__ void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -88,6 +94,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
       "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
+
+// One chunk is moved as several bulk copies of at most this many bytes (all completing on the
+// same mbarrier): the TMA unit overlaps independent copies, a single large one is latency bound.
+#ifndef AGF_BULK_PIECE
+#define AGF_BULK_PIECE 4096u
+#endif
+constexpr uint32_t kBulkPiece = AGF_BULK_PIECE;
 
 // ---------------------------------------------------------------- device: FP64 tensor core
 // D(8x8) += A(8x4, row) * B(4x8, col).  Fragment ownership (lane = 4*g + q):

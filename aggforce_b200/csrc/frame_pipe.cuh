@@ -89,7 +89,7 @@ struct FrameStager {
     // split into <= 64 KiB pieces (all multiples of 16 bytes)
     uint32_t off = 0;
     while (off < bytes) {
-      uint32_t piece = bytes - off < 65536u ? bytes - off : 65536u;
+      uint32_t piece = bytes - off < kBulkPiece ? bytes - off : kBulkPiece;
       tma_bulk_g2s(dst + off, src + off, piece, &full[stage]);
       off += piece;
     }
@@ -173,7 +173,7 @@ struct FrameRing {
           char* dst = reinterpret_cast<char*>(stage_ptr(stage));
           uint32_t off = 0;
           while (off < bytes) {
-            uint32_t piece = bytes - off < 65536u ? bytes - off : 65536u;
+            uint32_t piece = bytes - off < kBulkPiece ? bytes - off : kBulkPiece;
             tma_bulk_g2s(dst + off, src + off, piece, &full[stage]);
             off += piece;
           }

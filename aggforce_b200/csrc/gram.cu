@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kTriThreads, 1) gram_tri_kernel(const __grid_c
     char* dst = reinterpret_cast<char*>(raw + (int64_t)stage * stage_elems);
     uint32_t done = 0;
     while (done < bytes) {
-      const uint32_t piece = bytes - done < 65536u ? bytes - done : 65536u;
+      const uint32_t piece = bytes - done < kBulkPiece ? bytes - done : kBulkPiece;
       tma_bulk_g2s(dst + done, src + done, piece, &raw_full[stage]);
       done += piece;
     }
