@@ -18,6 +18,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes as C
+import hashlib
 import warnings
 from typing import Iterator, List, Optional, Sequence, Tuple
 
@@ -74,12 +75,31 @@ def to_host(t: torch.Tensor) -> np.ndarray:
     return host.numpy()
 
 
+_DEV_CACHE: "dict[tuple, torch.Tensor]" = {}
+
+
+def _dev_cached(arr: np.ndarray) -> torch.Tensor:
+    """Small read-only index / coefficient arrays are re-sent on every API call (CSR lists of the
+    same constraints, the same coordinate map ...): keep device copies keyed by content."""
+    key = (device().index, arr.dtype.str, arr.shape, hashlib.blake2b(arr.tobytes(), digest_size=16).digest())
+    hit = _DEV_CACHE.get(key)
+    if hit is None:
+        if len(_DEV_CACHE) > 256:
+            _DEV_CACHE.clear()
+        hit = torch.as_tensor(arr, device=device())
+        _DEV_CACHE[key] = hit
+    return hit
+
+
 def dev_i32(values: Sequence[int]) -> torch.Tensor:
-    return torch.as_tensor(np.asarray(values, dtype=np.int32), device=device())
+    return _dev_cached(np.ascontiguousarray(values, dtype=np.int32))
 
 
 def dev_f64(values) -> torch.Tensor:
-    return torch.as_tensor(np.ascontiguousarray(values, dtype=np.float64), device=device())
+    arr = np.ascontiguousarray(values, dtype=np.float64)
+    if arr.nbytes <= (1 << 20):
+        return _dev_cached(arr)
+    return torch.as_tensor(arr, device=device())
 
 
 # --------------------------------------------------------------------------------------

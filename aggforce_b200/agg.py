@@ -79,10 +79,16 @@ def project_forces(
         constraints=constrained_inds,
         **kwargs,
     )
-    if isinstance(traj_map, SeperableTMap) and isinstance(traj_map.force_map, LinearMap):
-        mapped_coords = traj_map.coord_map(coords_in)
-        mapped_forces, sumsq = traj_map.force_map.apply_with_sumsq(forces_in)
-        residual = _global_mean_sq(sumsq, mapped_forces.shape)
+    if (isinstance(traj_map, SeperableTMap) and isinstance(traj_map.force_map, LinearMap)
+            and isinstance(traj_map.coord_map, LinearMap)):
+        # both applications are enqueued back to back; one read returns NaN flags + residual sum
+        cm, fm = traj_map.coord_map, traj_map.force_map
+        fc, oc, sc = cm._launch(coords_in)
+        ff, of, sf = fm._launch(forces_in, want_sumsq=True)
+        status = torch.stack([sc, sf]).cpu().numpy()
+        mapped_coords = cm._finish(fc, oc, status[0])
+        mapped_forces = fm._finish(ff, of, status[1])
+        residual = _global_mean_sq(float(status[1][2]), mapped_forces.shape)
     else:
         mapped = traj_map(t)
         mapped_coords, mapped_forces = mapped.coords, mapped.forces

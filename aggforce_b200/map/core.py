@@ -105,19 +105,29 @@ class LinearMap:
                                                           keep_zero_columns=not self.handle_nans))
         return self._compiled[1]
 
-    def _apply(self, points, want_sumsq: bool = False):
+    def _launch(self, points, want_sumsq: bool = False):
+        """Enqueue the kernel; returns ``(frames, out_dev, status_dev)`` without synchronising.
+        ``status_dev`` is a float64[3] device tensor ``[saw_nan, nan_violation, sum(out**2)]``."""
         frames = _engine.Frames(points)
         out, sumsq, flags = _engine.map_apply(
             frames, self._compile(), nan_mode=1 if self.handle_nans else 0,
             nan_atol=self.nan_check_threshold, want_sumsq=want_sumsq,
         )
-        if self.handle_nans and int(flags[1].item()) != 0:
+        status = torch.cat([flags.to(torch.float64), sumsq if sumsq is not None else flags.new_zeros(1, dtype=torch.float64)])
+        return frames, out, status
+
+    def _finish(self, frames, out, status_host):
+        if self.handle_nans and status_host[1] != 0:
             raise ValueError(
                 "NaN handling is on and results seem to depend on NaN "
                 "positions in input array. Check input and standard_matrix."
             )
-        result = _engine.to_host(out) if frames.on_host else out
-        return result, sumsq
+        return _engine.to_host(out) if frames.on_host else out
+
+    def _apply(self, points, want_sumsq: bool = False):
+        frames, out, status = self._launch(points, want_sumsq)
+        host = status.cpu().numpy()  # one synchronising read: NaN flags and the residual sum together
+        return self._finish(frames, out, host), float(host[2])
 
     def __call__(self, points):
         """Map ``(n_steps, n_fg_sites, 3)`` points to ``(n_steps, n_cg_sites, 3)``."""
@@ -125,8 +135,7 @@ class LinearMap:
 
     def apply_with_sumsq(self, points):
         """``(mapped, sum(mapped**2))`` from one kernel launch (the residual of agg.py:291-297)."""
-        mapped, sumsq = self._apply(points, want_sumsq=True)
-        return mapped, float(sumsq.item())
+        return self._apply(points, want_sumsq=True)
 
     def flat_call(self, flattened):
         """Apply to ``(n_frames, n_fg_sites*3)`` input, returning ``(n_frames, n_cg_sites*3)``."""
