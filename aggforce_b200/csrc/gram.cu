@@ -48,24 +48,26 @@ __host__ __device__ constexpr int tile_begin(int nt, int w) {
   const int total = tri_tiles(nt), base = total / kGramWarps, extra = total % kGramWarps;
   return w * base + (w < extra ? w : extra);
 }
-__host__ __device__ constexpr int tile_row(int nt, int t) {
-  int r = 0, len = nt;
-  while (t >= len) {
-    t -= len;
-    --len;
-    ++r;
+// Tile order: two tile rows at a time, column by column -- (r,c), (r+1,c), (r,c+1), (r+1,c+1) ... --
+// so a warp's contiguous run of ~12 tiles touches 2 row fragments and ~6 column fragments
+// (0.67 shared-memory fragment loads per DMMA instead of 1.08 for single-row strips).
+__host__ __device__ constexpr int tile_rc(int nt, int t, bool want_row) {
+  int idx = 0;
+  for (int r0 = 0; r0 < nt; r0 += 2) {
+    const int r1 = r0 + 1;
+    for (int c = r0; c < nt; ++c) {
+      if (idx == t) return want_row ? r0 : c;
+      ++idx;
+      if (r1 < nt && c >= r1) {
+        if (idx == t) return want_row ? r1 : c;
+        ++idx;
+      }
+    }
   }
-  return r;
+  return 0;
 }
-__host__ __device__ constexpr int tile_col(int nt, int t) {
-  int r = 0, len = nt;
-  while (t >= len) {
-    t -= len;
-    --len;
-    ++r;
-  }
-  return r + t;
-}
+__host__ __device__ constexpr int tile_row(int nt, int t) { return tile_rc(nt, t, true); }
+__host__ __device__ constexpr int tile_col(int nt, int t) { return tile_rc(nt, t, false); }
 constexpr int kMaxTriSlots = (tri_tiles(16) + kGramWarps - 1) / kGramWarps;  // 17
 
 template <int NT, int W, int T, int END>
@@ -159,6 +161,25 @@ __device__ __forceinline__ void fill_panel(const T* __restrict__ frames, int nf,
   }
 }
 
+// 32-bit shared-memory accessors (no generic-address arithmetic in the fill loop)
+template <typename T>
+__device__ __forceinline__ double lds_as_f64(uint32_t addr);
+template <>
+__device__ __forceinline__ double lds_as_f64<float>(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return (double)v;
+}
+template <>
+__device__ __forceinline__ double lds_as_f64<double>(uint32_t addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
 // ------------------------------------------------------------------ single block (n_red <= 128), TMA staged
 // Warp-specialised CTA (one per SM): 8 MMA warps sweep panel[j & 1] while 4 fill warps convert
 // the next raw chunk into panel[(j+1) & 1] and keep the TMA ring full, so the DMMA pipe never
@@ -195,6 +216,7 @@ __global__ void __launch_bounds__(kTriThreads, 1) gram_tri_kernel(const __grid_c
 
   for (int i = threadIdx.x; i <= p.n_red; i += blockDim.x) s_ptr[i] = p.col_ptr[i];
   for (int i = threadIdx.x; i < p.col_ptr[p.n_red]; i += blockDim.x) s_sites[i] = p.col_sites[i];
+  for (int i = threadIdx.x; i < 2 * KROWS * kStride; i += blockDim.x) panel0[i] = 0.0;  // padding columns stay 0
   if (threadIdx.x == 0) {
     for (int i = 0; i < kRawStages; ++i) mbar_init(&raw_full[i], 1);
     for (int i = 0; i < 2; ++i) {
@@ -243,17 +265,36 @@ __global__ void __launch_bounds__(kTriThreads, 1) gram_tri_kernel(const __grid_c
       for (int j = 0; j < kRawStages; ++j) issue(j);
     }
     uint32_t raw_phase = 0;  // bit s: parity to wait for on raw_full[s]
-    constexpr int TPC = (kFillThreads / NCOLS) < 1 ? 1 : ((kFillThreads / NCOLS) > KF ? KF : (kFillThreads / NCOLS));
-    const int my_x = ft < NCOLS * TPC ? ft % NCOLS : NCOLS, my_slot = ft / NCOLS;
-    int my_cnt = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-    if (my_x < p.n_red) {
-      const int b = s_ptr[my_x];
-      my_cnt = s_ptr[my_x + 1] - b;
-      if (my_cnt > 0) m0 = 3 * s_sites[b];
-      if (my_cnt > 1) m1 = 3 * s_sites[b + 1];
-      if (my_cnt > 2) m2 = 3 * s_sites[b + 2];
-      if (my_cnt > 3) m3 = 3 * s_sites[b + 3];
+    // Work split: fill warp fw owns frames fw, fw+8, ... of every chunk; inside a frame the columns
+    // are processed in groups of 32 with lane = column.  Everything a lane needs about its columns
+    // (byte offsets of up to 4 member sites, member count, the group's largest count) is loaded
+    // once; columns arrive sorted by member count so the lanes of a group mostly agree.
+    constexpr int NG = (NCOLS + 31) / 32;
+    const int fw = ft >> 5;
+    int cnt[NG], wmax[NG];
+    uint32_t moff[NG][4], coff[NG];
+    bool generic = false;
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      const int x = gi * 32 + lane;
+      cnt[gi] = 0;
+      coff[gi] = (uint32_t)x * 8u;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) moff[gi][m] = 0;
+      if (x < p.n_red) {
+        const int b = s_ptr[x];
+        cnt[gi] = s_ptr[x + 1] - b;
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+          if (m < cnt[gi]) moff[gi][m] = (uint32_t)s_sites[b + m] * 3u * (uint32_t)sizeof(T);
+      }
+      int wm = cnt[gi];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wm = max(wm, __shfl_xor_sync(0xffffffffu, wm, o));
+      wmax[gi] = wm;
+      generic |= wm > 4;
     }
+    const uint32_t frame_bytes = (uint32_t)frame_elems * (uint32_t)sizeof(T);
     for (int64_t j = 0; j < n_mine; ++j) {
       const int64_t c = first + j * step;
       const int nf = p.sch.count(c);
@@ -269,42 +310,51 @@ __global__ void __launch_bounds__(kTriThreads, 1) gram_tri_kernel(const __grid_c
       }
       mbar_wait(&panel_empty[pb], (uint32_t)(((j >> 1) & 1) ^ 1));
       double* panel = panel0 + (size_t)pb * KROWS * kStride;
-      // thread = (column x, frame slot): the member list of x is read once, then the thread walks
-      // its frames with independent dependency chains (ILP instead of many resident warps)
-      if (my_x < NCOLS) {
-        if (my_cnt <= 4) {
-#pragma unroll 4
-          for (int t = my_slot; t < KF; t += TPC) {
+      const uint32_t raw_u32 = smem_u32(stage_ptr), panel_u32 = smem_u32(panel);
+      if (!generic) {
+        for (int t = fw; t < KF; t += kFillWarps) {
+          const uint32_t rbase = raw_u32 + (uint32_t)t * frame_bytes;
+          const uint32_t pbase = panel_u32 + (uint32_t)(t * 3 * kStride * 8);
+          const bool live = t < nf;
+#pragma unroll
+          for (int gi = 0; gi < NG; ++gi) {
             double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-            if (t < nf) {
-              const T* fr = stage_ptr + (int64_t)t * frame_elems;
-              if (my_cnt > 0) { s0 = to_f64(fr[m0]); s1 = to_f64(fr[m0 + 1]); s2 = to_f64(fr[m0 + 2]); }
-              if (my_cnt > 1) { s0 += to_f64(fr[m1]); s1 += to_f64(fr[m1 + 1]); s2 += to_f64(fr[m1 + 2]); }
-              if (my_cnt > 2) { s0 += to_f64(fr[m2]); s1 += to_f64(fr[m2 + 1]); s2 += to_f64(fr[m2 + 2]); }
-              if (my_cnt > 3) { s0 += to_f64(fr[m3]); s1 += to_f64(fr[m3 + 1]); s2 += to_f64(fr[m3 + 2]); }
-            }
-            double* dst = panel + (t * 3) * kStride + my_x;
-            dst[0] = s0;
-            dst[kStride] = s1;
-            dst[2 * kStride] = s2;
-          }
-        } else {
-          for (int t = my_slot; t < KF; t += TPC) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-            if (t < nf) {
-              const T* fr = stage_ptr + (int64_t)t * frame_elems;
-              for (int m = s_ptr[my_x]; m < s_ptr[my_x + 1]; ++m) {
-                const T* q = fr + 3 * s_sites[m];
-                s0 += to_f64(q[0]);
-                s1 += to_f64(q[1]);
-                s2 += to_f64(q[2]);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              if (m < wmax[gi]) {  // warp-uniform: one conversion sequence per group, not per lane
+                if (live && m < cnt[gi]) {
+                  const uint32_t a = rbase + moff[gi][m];
+                  s0 += lds_as_f64<T>(a);
+                  s1 += lds_as_f64<T>(a + (uint32_t)sizeof(T));
+                  s2 += lds_as_f64<T>(a + 2u * (uint32_t)sizeof(T));
+                }
               }
             }
-            double* dst = panel + (t * 3) * kStride + my_x;
-            dst[0] = s0;
-            dst[kStride] = s1;
-            dst[2 * kStride] = s2;
+            if (gi * 32 + lane < p.n_red) {
+              const uint32_t d = pbase + coff[gi];
+              sts_f64(d, s0);
+              sts_f64(d + kStride * 8, s1);
+              sts_f64(d + 2 * kStride * 8, s2);
+            }
           }
+        }
+      } else {
+        for (int item = ft; item < KF * NCOLS; item += kFillThreads) {
+          const int t = item / NCOLS, x = item - t * NCOLS;
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+          if (t < nf && x < p.n_red) {
+            const T* fr = stage_ptr + (int64_t)t * frame_elems;
+            for (int m = s_ptr[x]; m < s_ptr[x + 1]; ++m) {
+              const T* q = fr + 3 * s_sites[m];
+              s0 += to_f64(q[0]);
+              s1 += to_f64(q[1]);
+              s2 += to_f64(q[2]);
+            }
+          }
+          double* dst = panel + (t * 3) * kStride + x;
+          dst[0] = s0;
+          dst[kStride] = s1;
+          dst[2 * kStride] = s2;
         }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kFillThreads) : "memory");  // panel written, raw stage drained

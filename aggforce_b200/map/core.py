@@ -97,8 +97,14 @@ class LinearMap:
 
     # ------------------------------------------------------------------ application
     def _compile(self) -> _engine.CompiledMap:
-        digest = hashlib.blake2b(np.ascontiguousarray(self._standard_matrix).tobytes(), digest_size=16).digest()
-        digest += str(self._standard_matrix.dtype).encode() + bytes([bool(self.handle_nans)])
+        m = self._standard_matrix
+        # change detection for in-place edits of the matrix: full digest when small, strided sample
+        # (at most 64 Ki elements) plus the array identity when large (hashing 20 MB costs 20 ms)
+        flat = m.reshape(-1) if m.flags.c_contiguous else np.ascontiguousarray(m).reshape(-1)
+        stride = max(1, flat.size // 65536)
+        digest = hashlib.blake2b(np.ascontiguousarray(flat[::stride]).tobytes(), digest_size=16).digest()
+        digest += repr((m.shape, str(m.dtype), stride, m.ctypes.data if stride > 1 else 0,
+                        bool(self.handle_nans))).encode()
         if self._compiled is None or self._compiled[0] != digest:
             # plain mode keeps all-zero columns so that 0 * NaN = NaN exactly as numpy computes it
             self._compiled = (digest, _engine.CompiledMap(self._standard_matrix,
