@@ -197,10 +197,12 @@ def main() -> None:
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, sample_clocks=False):
+        # the sampler runs across warm-up AND the timed steps: the timed region alone lasts tens of
+        # milliseconds, less than one nvidia-smi sampling period
+        sampler = ClockSampler(local) if sample_clocks else None
         for _ in range(warmup):
             fn()
         barrier()
-        sampler = ClockSampler(local) if sample_clocks else None
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = _lib.LAUNCHES["count"]
         e0.record()
@@ -263,6 +265,10 @@ def main() -> None:
         "agf_map_apply": ("hbm", (12 * n + 24 * n_cg) * T, "B"),
         "agf_map_apply_sparse": ("hbm", None, "B"),
     }
+    # DRAM bytes per frame of each kernel from `ncu --set full` captures of this workload
+    # (dram__bytes_read.sum + dram__bytes_write.sum divided by the frames of the captured launch):
+    # profiles/r01_ncu_gram_ws.txt, profiles/r01_ncu_apply_v2.txt, profiles/r01_ncu_all_kernels_v1.txt
+    traffic_per_frame = {"agf_gram_linear": 2111.0, "agf_map_apply": 2333.3, "agf_pair_moments": 2109.6}
     kernels = {}
     for name, times in per_kernel.items():
         tot = float(np.sum(times))
@@ -281,13 +287,15 @@ def main() -> None:
             amount = ((2 * 10 + uni_nnz) * 12 + 3 * 24 * n_cg) * T
             entry.update(bound="hbm", achieved=amount / (tot * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
             entry["frac"] = entry["achieved"] / entry["peak"]
+        if name in traffic_per_frame:
+            entry["traffic"] = traffic_per_frame[name] * T
         kernels[name] = entry
     dominant = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
     roofline = None
     if dominant and "frac" in kernels[dominant]:
         k = kernels[dominant]
         roofline = {"kernel": dominant, "bound": k["bound"], "achieved": k["achieved"], "peak": k["peak"],
-                    "unit": k["unit"], "frac": k["frac"], "traffic": None,
+                    "unit": k["unit"], "frac": k["frac"], "traffic": k.get("traffic"),
                     "peak_source": ("FP64 DMMA microbenchmark measured on this pool "
                                     "(profiles/r01_fp64_hbm_microbench.json)") if k["bound"] == "tensor"
                     else f"MEASURED_PEAKS.json hbm_gbs ({hbm_src})"}
