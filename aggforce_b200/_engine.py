@@ -525,14 +525,20 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
             return empty
     run(done, t_local)
 
-    # ---- combine (Chan) across ranks in float64 on the host; P is O(n)
-    host = to_host(torch.cat([acc, shift[:, None]], dim=1))
-    s1, s2, c = host[:, 0], host[:, 1], host[:, 2]
+    # ---- per-rank (count, mean, M2) on the device, gathered across ranks, merged (Chan) in
+    #      float64 on the host; P is O(n).  One synchronising read.
     if t_local > 0:
-        mean = c + s1 / t_local
-        m2_local = s2 - s1 * s1 / t_local
+        mean = shift + acc[:, 0] / t_local
+        m2_local = acc[:, 1] - acc[:, 0] ** 2 / t_local
     else:
-        mean, m2_local = np.zeros(n_pairs), np.zeros(n_pairs)
-    parts = allgather_host(np.concatenate([[float(t_local)], mean, m2_local]))
+        mean, m2_local = torch.zeros_like(shift), torch.zeros_like(shift)
+    rec = torch.cat([torch.tensor([float(t_local)], dtype=torch.float64, device=dev), mean, m2_local])
+    if sharded():
+        dist = _dist()
+        outs = [torch.empty_like(rec) for _ in range(dist.get_world_size(_Sharding.group))]
+        dist.all_gather(outs, rec, group=_Sharding.group)
+        parts = list(to_host(torch.stack(outs)))
+    else:
+        parts = [to_host(rec)]
     sd = merge_moments(parts, n_pairs)
     return to_host(pairs).astype(np.int64), sd

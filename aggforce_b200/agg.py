@@ -85,10 +85,18 @@ def project_forces(
         cm, fm = traj_map.coord_map, traj_map.force_map
         fc, oc, sc = cm._launch(coords_in)
         ff, of, sf = fm._launch(forces_in, want_sumsq=True)
-        status = torch.stack([sc, sf]).cpu().numpy()
-        mapped_coords = cm._finish(fc, oc, status[0])
-        mapped_forces = fm._finish(ff, of, status[1])
-        residual = _global_mean_sq(float(status[1][2]), mapped_forces.shape)
+        # [flags_c(2), sumsq_c, flags_f(2), sumsq_f, n_elements]; under frame sharding the residual
+        # numerator / denominator are summed over ranks on the device before the single read
+        count = torch.tensor([float(np.prod(of.shape))], dtype=torch.float64, device=of.device)
+        packed = torch.cat([sc, sf, count])
+        if _engine.sharded():
+            tail = packed[5:7].clone()
+            _engine.allreduce_sum_(tail)
+            packed = torch.cat([packed[:5], tail])
+        status = packed.cpu().numpy()
+        mapped_coords = cm._finish(fc, oc, status[0:3])
+        mapped_forces = fm._finish(ff, of, status[3:6])
+        residual = float(status[5] / status[6])
     else:
         mapped = traj_map(t)
         mapped_coords, mapped_forces = mapped.coords, mapped.forces
