@@ -334,13 +334,16 @@ def csr_from_labels(labels: np.ndarray, n_groups: int) -> Tuple[np.ndarray, np.n
 def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Tensor:
     """Kernel (a): all-reduced, symmetrised second-moment matrix (device f64 [n_red, n_red]).
 
-    Internally the reduced columns are ordered by group size (singles, pairs, ...) so that the
-    lanes of a warp walk member lists of equal length while they build the f64 panel; the result
-    is permuted back to the caller's column order.
+    Internally the reduced columns are ordered by group size (largest first) so that the lanes of a
+    warp walk member lists of similar length while they build the f64 panel; the result is
+    permuted back to the caller's column order.
     """
     col_of_site = np.asarray(col_of_site, dtype=np.int64)
     sizes = np.bincount(col_of_site[col_of_site >= 0], minlength=n_red)
-    order = np.argsort(sizes, kind="stable")  # internal position -> caller's column
+    # largest groups first: with lane = column in 32-column groups the group holding the few
+    # 3- and 4-member columns is then also the one holding pairs, and the ragged last group holds
+    # singles -- the number of (warp-wide) f64 additions per frame drops from 33 to 12 at cln025
+    order = np.argsort(-sizes, kind="stable")  # internal position -> caller's column
     rank = np.empty(n_red, dtype=np.int64)
     rank[order] = np.arange(n_red)
     internal = np.where(col_of_site >= 0, rank[np.maximum(col_of_site, 0)], -1)

@@ -324,9 +324,21 @@ __global__ void __launch_bounds__(kTriThreads, 1) gram_tri_kernel(const __grid_c
               if (m < wmax[gi]) {  // warp-uniform: one conversion sequence per group, not per lane
                 if (live && m < cnt[gi]) {
                   const uint32_t a = rbase + moff[gi][m];
-                  s0 += lds_as_f64<T>(a);
-                  s1 += lds_as_f64<T>(a + (uint32_t)sizeof(T));
-                  s2 += lds_as_f64<T>(a + 2u * (uint32_t)sizeof(T));
+                  const double v0 = lds_as_f64<T>(a), v1 = lds_as_f64<T>(a + (uint32_t)sizeof(T)),
+                               v2 = lds_as_f64<T>(a + 2u * (uint32_t)sizeof(T));
+                  // The first member is assigned, not added: DADD shares the FP64 pipe with DMMA and
+                  // loses every arbitration against the MMA warps' DMMA stream (a DADD loop next to
+                  // DMMA-streaming warps runs 400x slower, tools/microbench/fill_bench.cu; F2F.F64.F32,
+                  // LDS and STS are unaffected), so the fill issues as few DADDs as possible.
+                  if (m == 0) {
+                    s0 = v0;
+                    s1 = v1;
+                    s2 = v2;
+                  } else {
+                    s0 += v0;
+                    s1 += v1;
+                    s2 += v2;
+                  }
                 }
               }
             }
