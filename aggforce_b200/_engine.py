@@ -91,6 +91,32 @@ def _dev_cached(arr: np.ndarray) -> torch.Tensor:
     return hit
 
 
+_D2H_STREAMS: dict = {}
+
+
+def start_d2h(t: torch.Tensor) -> torch.Tensor:
+    """Begin an asynchronous device -> pinned-host copy on a dedicated stream (so that it overlaps
+    later uploads on the copy stream: PCIe is full duplex).  Call :func:`finish_d2h` before reading."""
+    dev = torch.cuda.current_device()
+    if dev not in _D2H_STREAMS:
+        _D2H_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    ds = _D2H_STREAMS[dev]
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    with torch.cuda.stream(ds):
+        ds.wait_event(ev)
+        host.copy_(t, non_blocking=True)
+    t.record_stream(ds)
+    return host
+
+
+def finish_d2h() -> None:
+    ds = _D2H_STREAMS.get(torch.cuda.current_device())
+    if ds is not None:
+        ds.synchronize()
+
+
 def dev_i32(values: Sequence[int]) -> torch.Tensor:
     return _dev_cached(np.ascontiguousarray(values, dtype=np.int32))
 
@@ -364,7 +390,9 @@ def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Te
 class CompiledMap:
     """Device-side form of a (n_cg, n_fg) matrix for kernel (d)."""
 
-    def __init__(self, matrix: np.ndarray, keep_zero_columns: bool) -> None:
+    def __init__(self, matrix: np.ndarray, keep_zero_columns: bool, column_labels: Optional[np.ndarray] = None) -> None:
+        """``column_labels`` (optional, ``int[n_fg]``): a labelling under which equal labels are KNOWN to
+        have identical matrix columns (e.g. the reduced columns of a fit) -- skips the column search."""
         m = np.asarray(matrix)
         self.n_cg, self.n_fg = m.shape
         self.out_f32 = m.dtype == np.float32
@@ -384,7 +412,13 @@ class CompiledMap:
                 weights = m64[rows, cols]
             self.row_ptr, self.row_sites, self.row_w = dev_i32(ptr_), dev_i32(cols), dev_f64(weights)
             return
-        uniq, inverse = np.unique(m64.T, axis=0, return_inverse=True)
+        if column_labels is not None:
+            inverse = np.asarray(column_labels, dtype=np.int64)
+            firsts = np.full(int(inverse.max()) + 1, -1, dtype=np.int64)
+            firsts[inverse[::-1]] = np.arange(self.n_fg)[::-1]  # first site of every label
+            uniq = np.ascontiguousarray(m64.T[firsts])
+        else:
+            uniq, inverse = np.unique(m64.T, axis=0, return_inverse=True)
         inverse = np.asarray(inverse).reshape(-1)
         if not keep_zero_columns:
             zero = np.nonzero(~uniq.any(axis=1))[0]

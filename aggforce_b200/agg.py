@@ -84,7 +84,9 @@ def project_forces(
         # both applications are enqueued back to back; one read returns NaN flags + residual sum
         cm, fm = traj_map.coord_map, traj_map.force_map
         fc, oc, sc = cm._launch(coords_in)
+        host_c = _engine.start_d2h(oc) if fc.on_host else None  # downloads overlap the force upload
         ff, of, sf = fm._launch(forces_in, want_sumsq=True)
+        host_f = _engine.start_d2h(of) if ff.on_host else None
         # [flags_c(2), sumsq_c, flags_f(2), sumsq_f, n_elements]; under frame sharding the residual
         # numerator / denominator are summed over ranks on the device before the single read
         count = torch.tensor([float(np.prod(of.shape))], dtype=torch.float64, device=of.device)
@@ -94,8 +96,8 @@ def project_forces(
             _engine.allreduce_sum_(tail)
             packed = torch.cat([packed[:5], tail])
         status = packed.cpu().numpy()
-        mapped_coords = cm._finish(fc, oc, status[0:3])
-        mapped_forces = fm._finish(ff, of, status[3:6])
+        mapped_coords = cm._finish(fc, oc, status[0:3], host_c)
+        mapped_forces = fm._finish(ff, of, status[3:6], host_f)
         residual = float(status[5] / status[6])
     else:
         mapped = traj_map(t)

@@ -67,6 +67,7 @@ class LinearMap:
             raise ValueError("NaN checking can only be performed if standard_matrix is itself finite.")
         self.nan_check_threshold = nan_check_threshold
         self._compiled: Optional[Tuple[bytes, _engine.CompiledMap]] = None
+        self._column_labels: Optional[np.ndarray] = None  # set by fits that know the column structure
 
     # ------------------------------------------------------------------ descriptors
     @property
@@ -105,10 +106,13 @@ class LinearMap:
         digest = hashlib.blake2b(np.ascontiguousarray(flat[::stride]).tobytes(), digest_size=16).digest()
         digest += repr((m.shape, str(m.dtype), stride, m.ctypes.data if stride > 1 else 0,
                         bool(self.handle_nans))).encode()
+        if self._compiled is not None and self._compiled[0] != digest:
+            self._column_labels = None  # matrix was edited in place: the fit's column structure is stale
         if self._compiled is None or self._compiled[0] != digest:
             # plain mode keeps all-zero columns so that 0 * NaN = NaN exactly as numpy computes it
             self._compiled = (digest, _engine.CompiledMap(self._standard_matrix,
-                                                          keep_zero_columns=not self.handle_nans))
+                                                          keep_zero_columns=not self.handle_nans,
+                                                          column_labels=self._column_labels))
         return self._compiled[1]
 
     def _launch(self, points, want_sumsq: bool = False):
@@ -122,13 +126,19 @@ class LinearMap:
         status = torch.cat([flags.to(torch.float64), sumsq if sumsq is not None else flags.new_zeros(1, dtype=torch.float64)])
         return frames, out, status
 
-    def _finish(self, frames, out, status_host):
+    def _finish(self, frames, out, status_host, host_copy=None):
+        """``host_copy``: pinned tensor of an already started download (``_engine.start_d2h``)."""
         if self.handle_nans and status_host[1] != 0:
             raise ValueError(
                 "NaN handling is on and results seem to depend on NaN "
                 "positions in input array. Check input and standard_matrix."
             )
-        return _engine.to_host(out) if frames.on_host else out
+        if not frames.on_host:
+            return out
+        if host_copy is not None:
+            _engine.finish_d2h()
+            return host_copy.numpy()
+        return _engine.to_host(out)
 
     def _apply(self, points, want_sumsq: bool = False):
         frames, out, status = self._launch(points, want_sumsq)

@@ -99,4 +99,5 @@ def qp_linear_map(
             rows.append(x)
         reduced = np.stack(rows)
     force_map = LinearMap(reduced[:, cols])
+    force_map._column_labels = cols  # sites of one reduced column share their matrix column by construction
     return SeperableTMap(coord_map=coord_map, force_map=force_map)

@@ -43,7 +43,12 @@ def solve_equality_qp(P, A, b) -> Optional[np.ndarray]:
         cf = sl.cho_factor(P, lower=True, check_finite=False)
         pia = sl.cho_solve(cf, A.T, check_finite=False)
         s = A @ pia
-        lam = np.linalg.lstsq(s, b, rcond=None)[0]
+        try:  # A P^-1 A' is small (n_cg x n_cg) and SPD when A has full row rank
+            lam = sl.cho_solve(sl.cho_factor(s, lower=True, check_finite=False), b, check_finite=False)
+            if not np.isfinite(lam).all():
+                raise sl.LinAlgError("singular Schur complement")
+        except (sl.LinAlgError, np.linalg.LinAlgError, ValueError):
+            lam = np.linalg.lstsq(s, b, rcond=None)[0]
         x = pia @ lam
     except (sl.LinAlgError, np.linalg.LinAlgError):
         _, sv, vt = np.linalg.svd(A, full_matrices=True)
