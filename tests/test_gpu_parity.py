@@ -278,3 +278,32 @@ def test_abi_rejects_bad_arguments():
     with pytest.raises(_lib.AgfError):
         _lib.call("agf_gram_linear", None, 0, 10, 5, None, None, 3, None, None)
     assert "null pointer" in _lib.lib().agf_last_error().decode()
+
+
+# ------------------------------------------------------------------ BASELINE-size properties
+def test_full_size_properties_1m_frames(topo):
+    """configs[1] size (1 M frames): size-independent checks -- additivity of the Gram over frame
+    shards, the constraint set, the equality constraints of the fitted map, residual = mean square
+    of the mapped forces, linearity of the application."""
+    from aggforce_b200 import LinearMap, project_forces
+    from aggforce_b200.qp.qplinear import force_gram
+    from aggforce_b200.synth import synth_trajectory_device
+
+    T = 1_000_000
+    coords, forces = synth_trajectory_device(topo, T, seed=1234)
+    cmap = _cmap(topo)
+    res = project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds="auto",
+                         l2_regularization=1e3)
+    assert res["constraints"] == topo.xh_constraints
+    w = res["tmap"].force_map.standard_matrix
+    assert np.abs(_slice_matrix(topo) @ w.T - np.eye(10)).max() < 1e-9
+    mf = res["mapped_forces"]
+    assert mf.shape == (T, 10, 3)
+    assert abs(res["residual"] / float((mf ** 2).mean().item()) - 1) < 1e-12
+    whole, _ = force_gram(forces, topo.n_sites, topo.xh_constraints)
+    halves = sum(force_gram(forces[a:b], topo.n_sites, topo.xh_constraints)[0]
+                 for a, b in [(0, 500_001), (500_001, T)])
+    assert rel_fro(whole, halves) < 1e-12
+    sub = slice(123_456, 123_456 + 2_000)
+    assert rel_fro(mf[sub].cpu().numpy(), oracle.apply_map(forces[sub].cpu().numpy(), w)) < MAP_TOL
+    assert rel_fro(LinearMap(3.0 * w)(forces[sub]).cpu().numpy(), 3.0 * mf[sub].cpu().numpy()) < 1e-12
