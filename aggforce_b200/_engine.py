@@ -376,9 +376,17 @@ def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Te
     ptr_, sites = csr_from_labels(internal, n_red)
     d_ptr, d_sites = dev_i32(ptr_), dev_i32(sites)
     gram = torch.zeros((n_red, n_red), dtype=torch.float64, device=device())
+    workspace = None
     for _, piece in frames.pieces():
-        _lib.call("agf_gram_linear", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites, ptr(d_ptr),
-                  ptr(d_sites), n_red, ptr(gram), stream_ptr())
+        need = int(_lib.lib().agf_gram_linear_workspace_bytes(frames.n_sites, n_red, piece.shape[0]))
+        if need > 0:  # n_red > 128: pack group sums once, TMA-fed SYRK
+            if workspace is None or workspace.numel() < need:
+                workspace = torch.empty(need, dtype=torch.uint8, device=device())
+            _lib.call("agf_gram_linear_ws", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites, ptr(d_ptr),
+                      ptr(d_sites), n_red, ptr(gram), ptr(workspace), C.c_size_t(workspace.numel()), stream_ptr())
+        else:
+            _lib.call("agf_gram_linear", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites, ptr(d_ptr),
+                      ptr(d_sites), n_red, ptr(gram), stream_ptr())
     allreduce_sum_(gram)
     _lib.call("agf_symmetrize", ptr(gram), n_red, stream_ptr())
     if not np.array_equal(order, np.arange(n_red)):

@@ -20,6 +20,7 @@ _vp, _i32, _i64, _u64, _dbl, _flt = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
 # name -> argtypes; every function returns int status except the three noted below.
 SIGNATURES = {
     "agf_gram_linear": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _vp, _vp],
+    "agf_gram_linear_ws": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _vp, _vp, C.c_size_t, _vp],
     "agf_symmetrize": [_vp, _i32, _vp],
     "agf_map_apply": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, C.c_int, _vp, C.c_int, _dbl,
                       _vp, _vp],
@@ -37,7 +38,8 @@ SIGNATURES = {
                        _vp, _vp, C.c_int, _vp, _vp],
     "agf_synth_frames": [_vp, _vp, _vp, _i32, _i64, _i64, _u64, _flt, _flt, _flt, _vp, _vp, _vp],
 }
-PLAIN = {"agf_version": (C.c_int, []), "agf_last_error": (C.c_char_p, []), "agf_device_sm_count": (C.c_int, [])}
+PLAIN = {"agf_version": (C.c_int, []), "agf_last_error": (C.c_char_p, []), "agf_device_sm_count": (C.c_int, []),
+         "agf_gram_linear_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64])}
 
 
 class AgfError(RuntimeError):
