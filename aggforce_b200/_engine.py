@@ -117,6 +117,20 @@ def finish_d2h() -> None:
         ds.synchronize()
 
 
+_WORKSPACE: dict = {}
+
+
+def workspace(nbytes: int) -> torch.Tensor:
+    """Scratch buffer for the packed-panel kernels (grow-only, one per device; stream-ordered reuse)."""
+    dev = torch.cuda.current_device()
+    buf = _WORKSPACE.get(dev)
+    if buf is None or buf.numel() < nbytes:
+        _WORKSPACE[dev] = None
+        buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device())
+        _WORKSPACE[dev] = buf
+    return buf
+
+
 def dev_i32(values: Sequence[int]) -> torch.Tensor:
     return _dev_cached(np.ascontiguousarray(values, dtype=np.int32))
 
@@ -376,14 +390,12 @@ def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Te
     ptr_, sites = csr_from_labels(internal, n_red)
     d_ptr, d_sites = dev_i32(ptr_), dev_i32(sites)
     gram = torch.zeros((n_red, n_red), dtype=torch.float64, device=device())
-    workspace = None
     for _, piece in frames.pieces():
         need = int(_lib.lib().agf_gram_linear_workspace_bytes(frames.n_sites, n_red, piece.shape[0]))
         if need > 0:  # n_red > 128: pack group sums once, TMA-fed SYRK
-            if workspace is None or workspace.numel() < need:
-                workspace = torch.empty(need, dtype=torch.uint8, device=device())
+            ws = workspace(need)
             _lib.call("agf_gram_linear_ws", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites, ptr(d_ptr),
-                      ptr(d_sites), n_red, ptr(gram), ptr(workspace), C.c_size_t(workspace.numel()), stream_ptr())
+                      ptr(d_sites), n_red, ptr(gram), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
         else:
             _lib.call("agf_gram_linear", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites, ptr(d_ptr),
                       ptr(d_sites), n_red, ptr(gram), stream_ptr())
@@ -470,9 +482,19 @@ def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float,
                       ptr(cmap.row_ptr), ptr(cmap.row_sites), ptr(cmap.row_w), cmap.n_cg, ptr(o), dtype_code(o),
                       ptr(sumsq), nan_mode, float(nan_atol), ptr(flags), stream_ptr())
         else:
-            _lib.call("agf_map_apply", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites,
-                      ptr(cmap.ucol_ptr), ptr(cmap.ucol_sites), cmap.n_ucol, cmap.nnz, ptr(cmap.umat_t), cmap.n_cg,
-                      ptr(o), dtype_code(o), ptr(sumsq), nan_mode, float(nan_atol), ptr(flags), stream_ptr())
+            need = int(_lib.lib().agf_map_apply_workspace_bytes(dtype_code(piece), frames.n_sites, cmap.n_ucol,
+                                                                cmap.nnz, cmap.n_cg, piece.shape[0]))
+            if need > 0:  # too large for the shared-memory resident kernel: packed-panel DMMA GEMM
+                ws = workspace(need)
+                _lib.call("agf_map_apply_ws", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites,
+                          ptr(cmap.ucol_ptr), ptr(cmap.ucol_sites), cmap.n_ucol, cmap.nnz, ptr(cmap.umat_t),
+                          cmap.n_cg, ptr(o), dtype_code(o), ptr(sumsq), nan_mode, float(nan_atol), ptr(flags),
+                          ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+            else:
+                _lib.call("agf_map_apply", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites,
+                          ptr(cmap.ucol_ptr), ptr(cmap.ucol_sites), cmap.n_ucol, cmap.nnz, ptr(cmap.umat_t),
+                          cmap.n_cg, ptr(o), dtype_code(o), ptr(sumsq), nan_mode, float(nan_atol), ptr(flags),
+                          stream_ptr())
     return out, sumsq, flags
 
 

@@ -24,6 +24,8 @@ SIGNATURES = {
     "agf_symmetrize": [_vp, _i32, _vp],
     "agf_map_apply": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, C.c_int, _vp, C.c_int, _dbl,
                       _vp, _vp],
+    "agf_map_apply_ws": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, C.c_int, _vp, C.c_int, _dbl,
+                         _vp, _vp, C.c_size_t, _vp],
     "agf_map_apply_sparse": [_vp, C.c_int, _i64, _i32, _vp, _vp, _vp, _i32, _vp, C.c_int, _vp, C.c_int, _dbl, _vp,
                              _vp],
     "agf_pair_moments": [_vp, _vp, C.c_int, _i64, _i32, _i32, _vp, _i64, _vp, _vp, _vp],
@@ -31,6 +33,8 @@ SIGNATURES = {
     "agf_pair_screen": [_vp, _vp, C.c_int, _i64, _i32, _i32, _vp, _vp],
     "agf_gram_feat": [_vp, _vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _dbl, _dbl,
                       _dbl, _vp, _vp],
+    "agf_gram_feat_ws": [_vp, _vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _dbl,
+                         _dbl, _dbl, _vp, _vp, C.c_size_t, _vp],
     "agf_symmetrize_batch": [_vp, _i32, _i32, _vp],
     "agf_feat_rows": [_vp, C.c_int, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32,
                       _dbl, _dbl, _vp, _vp],
@@ -39,7 +43,9 @@ SIGNATURES = {
     "agf_synth_frames": [_vp, _vp, _vp, _i32, _i64, _i64, _u64, _flt, _flt, _flt, _vp, _vp, _vp],
 }
 PLAIN = {"agf_version": (C.c_int, []), "agf_last_error": (C.c_char_p, []), "agf_device_sm_count": (C.c_int, []),
-         "agf_gram_linear_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64])}
+         "agf_gram_linear_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64]),
+         "agf_map_apply_workspace_bytes": (C.c_size_t, [C.c_int, _i32, _i32, _i32, _i32, _i64]),
+         "agf_gram_feat_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i64])}
 
 
 class AgfError(RuntimeError):

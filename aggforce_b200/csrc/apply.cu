@@ -15,6 +15,7 @@
 //   * dense, large: tiled DFMA fallback with the map read through L2.
 // All arithmetic is f64 (the reference promotes f32 points x f64 matrix to f64).
 #include "frame_pipe.cuh"
+#include "panel.cuh"
 
 namespace agf {
 
@@ -369,7 +370,128 @@ __global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(con
   }
 }
 
-// ------------------------------------------------------------------------------------ dense large (fallback)
+// ------------------------------------------------------------------------------------ dense large: packed-panel GEMM
+// out[(t,d), c] = sum_x Xg[(t,d), x] U^T[x, c]  as a DMMA GEMM over packed panels (panel.cuh):
+//   apply_pack_kernel     : group sums + f64 promotion of 128 frames x 24 unique columns, one panel
+//                           per xyz component:  wsA[(frame block, d)][k-chunk][24 x][132 frames];
+//                           also the NaN probe (map/core.py:13-16) -- it reads every referenced value;
+//   apply_pack_map_kernel : U^T as  wsB[bead block][k-chunk][24 x][132 beads];
+//   apply_gemm_kernel     : CTA = (frame block, d) x bead block, contraction over all unique columns.
+// If the probe saw a NaN the slab is redone by the masking fallback kernel below (gated on the
+// workspace header), which implements the NaN protocol (map/core.py:219-240).
+struct ApplyWsHeader {
+  int32_t redo;   // a referenced input value was NaN
+  int32_t pad;
+  double sumsq;   // sum(out^2) of the GEMM result
+};
+constexpr size_t kApplyWsHeaderBytes = 256;
+
+template <typename TI>
+__global__ void __launch_bounds__(256) apply_pack_kernel(const TI* __restrict__ x, int64_t n_frames, int n_sites,
+                                                         const int32_t* __restrict__ ucol_ptr,
+                                                         const int32_t* __restrict__ ucol_sites, int n_ucol,
+                                                         int n_kchunks, double* __restrict__ ws_a,
+                                                         ApplyWsHeader* header, int nan_mode) {
+  const int fb = blockIdx.x / n_kchunks, kc = blockIdx.x - fb * n_kchunks;
+  const int64_t t0 = (int64_t)fb * kPanelCols;
+  bool saw_nan = false;
+  double* pan0 = ws_a + ((int64_t)(fb * 3) * n_kchunks + kc) * kPanelElems;
+  const int64_t dstep = (int64_t)n_kchunks * kPanelElems;
+  for (int item = threadIdx.x; item < kPanelRows * kPanelCols; item += blockDim.x) {
+    const int kr = item >> 7, m = item & 127;
+    const int u = kc * kPanelRows + kr;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    if (u < n_ucol && t0 + m < n_frames) {
+      const TI* fr = x + (t0 + m) * (int64_t)n_sites * 3;
+      const int b = __ldg(ucol_ptr + u), e = __ldg(ucol_ptr + u + 1);
+      for (int k = b; k < e; ++k) {
+        const TI* q = fr + 3 * __ldg(ucol_sites + k);
+        s0 += to_f64(__ldg(q));
+        s1 += to_f64(__ldg(q + 1));
+        s2 += to_f64(__ldg(q + 2));
+      }
+      saw_nan |= (s0 != s0) | (s1 != s1) | (s2 != s2);
+    }
+    double* dst = pan0 + kr * kPanelStride + m;
+    dst[0] = s0;
+    dst[dstep] = s1;
+    dst[2 * dstep] = s2;
+  }
+  if (saw_nan && nan_mode) atomicOr(&header->redo, 1);
+}
+
+__global__ void apply_pack_map_kernel(const double* __restrict__ umat_t, int n_ucol, int n_cg, int n_kchunks,
+                                      double* __restrict__ ws_b) {
+  const int nbk = blockIdx.x / n_kchunks, kc = blockIdx.x - nbk * n_kchunks;
+  double* pan = ws_b + (int64_t)blockIdx.x * kPanelElems;
+  for (int item = threadIdx.x; item < kPanelRows * kPanelCols; item += blockDim.x) {
+    const int kr = item >> 7, n = item & 127;
+    const int u = kc * kPanelRows + kr, c = nbk * kPanelCols + n;
+    pan[kr * kPanelStride + n] = (u < n_ucol && c < n_cg) ? __ldg(umat_t + (int64_t)u * n_cg + c) : 0.0;
+  }
+}
+
+struct ApplyGemmParams {
+  const double* ws_a;
+  const double* ws_b;
+  int64_t n_frames;
+  int32_t n_cg, n_kchunks, n_nblocks;
+  void* out;
+  ApplyWsHeader* header;
+};
+
+template <typename TO>
+__global__ void __launch_bounds__(kPanelThreads, 1) apply_gemm_kernel(const __grid_constant__ ApplyGemmParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // adjacent CTAs = the bead blocks of one (frame block, d): the A panels are fetched from HBM once
+  const int nbk = blockIdx.x % p.n_nblocks, mb = blockIdx.x / p.n_nblocks;
+  const int fb = mb / 3, d = mb - fb * 3;
+  const int64_t t0 = (int64_t)fb * kPanelCols;
+  const int64_t left = p.n_frames - t0;
+  const int ct_rows = left >= kPanelCols ? 16 : (int)((left + 7) / 8);
+  const int cols_left = p.n_cg - nbk * kPanelCols;
+  const int ct_cols = cols_left >= kPanelCols ? 16 : (cols_left + 7) / 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = warp, r1 = 15 - warp;
+  const uint32_t m0 = panel_row_mask(r0, ct_rows, ct_cols, false), m1 = panel_row_mask(r1, ct_rows, ct_cols, false);
+  PanelStream st;
+  st.a = p.ws_a + (int64_t)mb * p.n_kchunks * kPanelElems;
+  st.b = p.ws_b + (int64_t)nbk * p.n_kchunks * kPanelElems;
+  st.a_step = st.b_step = kPanelElems;
+  st.n = p.n_kchunks;
+  st.same = false;
+  double acc[2][16][2];
+  if (!panel_mainloop(smem, st, m0, m1, acc)) return;
+  const int g = lane >> 2, q = lane & 3;
+  TO* out = reinterpret_cast<TO*>(p.out);
+  double sq = 0.0;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const uint32_t m = r == 0 ? m0 : m1;
+    const int64_t t = t0 + (r == 0 ? r0 : r1) * 8 + g;
+    if (m == 0u || t >= p.n_frames) continue;
+    TO* orow = out + t * (int64_t)p.n_cg * 3 + d;
+#pragma unroll
+    for (int cc = 0; cc < 16; ++cc) {
+      if (!((m >> cc) & 1u)) continue;
+      const int c = nbk * kPanelCols + cc * 8 + 2 * q;
+      if (c < p.n_cg) {
+        store_out(orow + (int64_t)c * 3, acc[r][cc][0]);
+        const double v = (double)static_cast<TO>(acc[r][cc][0]);
+        sq += v * v;
+      }
+      if (c + 1 < p.n_cg) {
+        store_out(orow + (int64_t)(c + 1) * 3, acc[r][cc][1]);
+        const double v = (double)static_cast<TO>(acc[r][cc][1]);
+        sq += v * v;
+      }
+    }
+  }
+  sq = warp_sum(sq);
+  if (lane == 0 && sq != 0.0) atomicAdd(&p.header->sumsq, sq);
+}
+
+// ------------------------------------------------------------------------------------ dense large (NaN fallback / no workspace)
 // CTA = 8 frames (24 rows); thread = one bead c (strided); unique columns processed in
 // blocks of 64 whose group sums are staged in shared memory as xg[x][row].
 template <typename TI, typename TO>
@@ -378,8 +500,14 @@ __global__ void __launch_bounds__(256) apply_dense_big_kernel(const TI* __restri
                                                               const int32_t* __restrict__ ucol_sites, int n_ucol,
                                                               const double* __restrict__ umat_t, int n_cg,
                                                               TO* __restrict__ out, double* sumsq, int nan_mode,
-                                                              double nan_atol, int32_t* nan_flags) {
+                                                              double nan_atol, int32_t* nan_flags,
+                                                              const ApplyWsHeader* gate) {
   constexpr int FR = 8, ROWS = FR * 3, XB = 64;
+  if (gate != nullptr && gate->redo == 0) {
+    // the packed-panel GEMM already produced this slab: only publish its residual sum
+    if (blockIdx.x == 0 && threadIdx.x == 0 && sumsq) atomicAdd(sumsq, gate->sumsq);
+    return;
+  }
   __shared__ double xg[XB][ROWS];
   __shared__ double xn[XB][ROWS];
   __shared__ int s_has_nan;
@@ -460,17 +588,30 @@ __global__ void __launch_bounds__(256) apply_dense_big_kernel(const TI* __restri
   }
 }
 
+// Shared-memory footprint of the small dense kernel before its raw ring; 0 = does not apply.
+static size_t small_fixed_bytes(int n_ucol, int nnz, int n_cg) {
+  const int nt = (n_cg + 7) / 8;
+  if (n_cg > 64 || nt < 1) return 0;
+  const int ntk = nt <= 4 ? nt : (nt <= 6 ? 6 : 8);
+  const int su = panel_stride(ntk * 8);
+  const int xpad = (n_ucol + 3) & ~3;
+  size_t off = (size_t)xpad * su * sizeof(double) + (size_t)xpad * 16 + (size_t)(n_ucol + 1) * 4 + (size_t)nnz * 4;
+  off = (off + 15) / 16 * 16 + 2 * kMaxStages * sizeof(uint64_t);
+  return (off + 127) / 128 * 128;
+}
+static bool small_fits(int n_sites, int n_ucol, int nnz, int n_cg, size_t elem) {
+  const size_t off = small_fixed_bytes(n_ucol, nnz, n_cg);
+  const size_t stage_bytes = ((size_t)kOctet * n_sites * 3 * elem + 15) / 16 * 16;
+  return off != 0 && off + 4 * stage_bytes <= (size_t)224 * 1024;
+}
+
 template <typename TI, typename TO, int NT>
 static int launch_small(DenseSmallParams& p, cudaStream_t stream) {
   p.sch = make_schedule(p.x, p.n_frames, (int64_t)p.n_sites * 3 * sizeof(TI), kOctet);
-  const int su = panel_stride(NT * 8);
-  const int xpad = (p.n_ucol + 3) & ~3;
-  size_t off = (size_t)xpad * su * sizeof(double) + (size_t)xpad * 16 + (size_t)(p.n_ucol + 1) * 4 + (size_t)p.nnz * 4;
-  off = (off + 15) / 16 * 16 + 2 * kMaxStages * sizeof(uint64_t);
-  off = (off + 127) / 128 * 128;
+  const size_t off = small_fixed_bytes(p.n_ucol, p.nnz, p.n_cg);
   size_t stage_bytes = ((size_t)kOctet * p.n_sites * 3 * sizeof(TI) + 15) / 16 * 16;
   const size_t budget = 224 * 1024;
-  if (off + 4 * stage_bytes > budget) return 1;  // does not fit: caller uses the fallback
+  if (!small_fits(p.n_sites, p.n_ucol, p.nnz, p.n_cg, sizeof(TI))) return 1;  // caller uses the GEMM path
   int n_stages = (int)((budget - off) / stage_bytes);
   if (n_stages > kMaxStages) n_stages = kMaxStages;
   p.n_stages = n_stages;
@@ -502,11 +643,31 @@ static int dispatch_small(DenseSmallParams& p, cudaStream_t stream) {
   }
 }
 
+// Bytes of packed A panels per block of 128 frames, and of the packed map.
+static int64_t gemm_kchunks(int n_ucol) { return (n_ucol + kPanelRows - 1) / kPanelRows; }
+static int64_t gemm_fb_bytes(int n_ucol) { return 3 * gemm_kchunks(n_ucol) * (int64_t)kPanelBytes; }
+static int64_t gemm_map_bytes(int n_ucol, int n_cg) {
+  return (int64_t)panel_blocks(n_cg) * gemm_kchunks(n_ucol) * (int64_t)kPanelBytes;
+}
+
+template <typename TI, typename TO>
+static int launch_big(const TI* x, int64_t n_frames, int n_sites, const int32_t* ucol_ptr, const int32_t* ucol_sites,
+                      int n_ucol, const double* umat_t, int n_cg, TO* out, double* sumsq, int nan_mode,
+                      double nan_atol, int32_t* nan_flags, const ApplyWsHeader* gate, cudaStream_t stream) {
+  int64_t groups = (n_frames + 7) / 8;
+  int blocks = (int)(groups < (int64_t)sm_count() * 4 ? groups : (int64_t)sm_count() * 4);
+  if (blocks < 1) blocks = 1;
+  apply_dense_big_kernel<TI, TO><<<blocks, 256, 0, stream>>>(x, n_frames, n_sites, ucol_ptr, ucol_sites, n_ucol, umat_t,
+                                                             n_cg, out, sumsq, nan_mode, nan_atol, nan_flags, gate);
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}
+
 template <typename TI, typename TO>
 static int apply_typed(const void* points, int64_t n_frames, int32_t n_sites, const int32_t* ucol_ptr,
                        const int32_t* ucol_sites, int32_t n_ucol, int32_t nnz, const double* umat_t, int32_t n_cg,
-                       void* out, double* sumsq, int nan_mode, double nan_atol, int32_t* nan_flags,
-                       cudaStream_t stream) {
+                       void* out, double* sumsq, int nan_mode, double nan_atol, int32_t* nan_flags, void* workspace,
+                       size_t workspace_bytes, cudaStream_t stream) {
   DenseSmallParams p;
   memset(&p, 0, sizeof(p));
   p.x = points;
@@ -526,38 +687,101 @@ static int apply_typed(const void* points, int64_t n_frames, int32_t n_sites, co
   int rc = 1;
   if (n_cg <= 64 && nnz >= 0) rc = dispatch_small<TI, TO>(p, stream);
   if (rc <= 0) return rc;
-  int64_t groups = (n_frames + 7) / 8;
-  int blocks = (int)(groups < (int64_t)sm_count() * 4 ? groups : (int64_t)sm_count() * 4);
-  if (blocks < 1) blocks = 1;
-  apply_dense_big_kernel<TI, TO><<<blocks, 256, 0, stream>>>(
-      reinterpret_cast<const TI*>(points), n_frames, n_sites, ucol_ptr, ucol_sites, n_ucol, umat_t, n_cg,
-      reinterpret_cast<TO*>(out), sumsq, nan_mode, nan_atol, nan_flags);
+  const TI* x = reinterpret_cast<const TI*>(points);
+  TO* o = reinterpret_cast<TO*>(out);
+  const int64_t fixed = (int64_t)kApplyWsHeaderBytes + gemm_map_bytes(n_ucol, n_cg);
+  const int64_t fb_bytes = gemm_fb_bytes(n_ucol);
+  if (workspace == nullptr || (int64_t)workspace_bytes < fixed + fb_bytes)
+    return launch_big<TI, TO>(x, n_frames, n_sites, ucol_ptr, ucol_sites, n_ucol, umat_t, n_cg, o, sumsq, nan_mode,
+                              nan_atol, nan_flags, nullptr, stream);
+  // ---- packed-panel GEMM over slabs of frames
+  char* wsp = reinterpret_cast<char*>(workspace);
+  ApplyWsHeader* header = reinterpret_cast<ApplyWsHeader*>(wsp);
+  double* ws_b = reinterpret_cast<double*>(wsp + kApplyWsHeaderBytes);
+  double* ws_a = reinterpret_cast<double*>(wsp + fixed);
+  const int n_kchunks = (int)gemm_kchunks(n_ucol), n_nblocks = panel_blocks(n_cg);
+  apply_pack_map_kernel<<<n_nblocks * n_kchunks, 256, 0, stream>>>(umat_t, n_ucol, n_cg, n_kchunks, ws_b);
   AGF_CUDA_TRY(cudaGetLastError());
+  AGF_CUDA_TRY(cudaFuncSetAttribute(apply_gemm_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem));
+  const int64_t slab_fb = ((int64_t)workspace_bytes - fixed) / fb_bytes;
+  const int64_t slab_frames = slab_fb * kPanelCols;
+  for (int64_t f0 = 0; f0 < n_frames; f0 += slab_frames) {
+    const int64_t nf = n_frames - f0 < slab_frames ? n_frames - f0 : slab_frames;
+    const int64_t fbs = (nf + kPanelCols - 1) / kPanelCols;
+    const TI* xs = x + f0 * (int64_t)n_sites * 3;
+    TO* os = o + f0 * (int64_t)n_cg * 3;
+    AGF_CUDA_TRY(cudaMemsetAsync(header, 0, sizeof(ApplyWsHeader), stream));
+    AGF_REQUIRE(fbs * n_kchunks < (int64_t)1 << 31 && fbs * 3 * n_nblocks < (int64_t)1 << 31, "agf_map_apply: slab too large");
+    apply_pack_kernel<TI><<<(unsigned)(fbs * n_kchunks), 256, 0, stream>>>(xs, nf, n_sites, ucol_ptr, ucol_sites, n_ucol,
+                                                                         n_kchunks, ws_a, header, nan_mode);
+    AGF_CUDA_TRY(cudaGetLastError());
+    ApplyGemmParams gp;
+    gp.ws_a = ws_a;
+    gp.ws_b = ws_b;
+    gp.n_frames = nf;
+    gp.n_cg = n_cg;
+    gp.n_kchunks = n_kchunks;
+    gp.n_nblocks = n_nblocks;
+    gp.out = os;
+    gp.header = header;
+    apply_gemm_kernel<TO><<<(unsigned)(fbs * 3 * n_nblocks), kPanelThreads, kPanelSmem, stream>>>(gp);
+    AGF_CUDA_TRY(cudaGetLastError());
+    // publishes the residual sum, or redoes the slab with the NaN protocol if the probe fired
+    if (sumsq != nullptr || nan_mode != 0) {
+      rc = launch_big<TI, TO>(xs, nf, n_sites, ucol_ptr, ucol_sites, n_ucol, umat_t, n_cg, os, sumsq, nan_mode, nan_atol,
+                              nan_flags, header, stream);
+      if (rc) return rc;
+    }
+  }
   return AGF_OK;
 }
 
 }  // namespace agf
 
-extern "C" int agf_map_apply(const void* points, int in_dtype, int64_t n_frames, int32_t n_sites,
-                             const int32_t* ucol_ptr, const int32_t* ucol_sites, int32_t n_ucol, int32_t nnz,
-                             const double* umat_t, int32_t n_cg, void* out, int out_dtype, double* sumsq,
-                             int nan_mode, double nan_atol, int32_t* nan_flags, void* stream) {
+extern "C" size_t agf_map_apply_workspace_bytes(int in_dtype, int32_t n_sites, int32_t n_ucol, int32_t nnz,
+                                                int32_t n_cg, int64_t n_frames) {
+  using namespace agf;
+  if (n_sites <= 0 || n_ucol <= 0 || n_cg <= 0 || n_frames <= 0) return 0;
+  if (small_fits(n_sites, n_ucol, nnz, n_cg, in_dtype == AGF_F32 ? 4 : 8)) return 0;
+  const int64_t fixed = (int64_t)kApplyWsHeaderBytes + gemm_map_bytes(n_ucol, n_cg);
+  const int64_t fb_bytes = gemm_fb_bytes(n_ucol);
+  int64_t fbs = (n_frames + kPanelCols - 1) / kPanelCols;
+  const int64_t cap = ((int64_t)2 << 30) / fb_bytes;  // slabs of at most 2 GiB
+  if (fbs > cap) fbs = cap < 1 ? 1 : cap;
+  return (size_t)(fixed + fbs * fb_bytes);
+}
+
+extern "C" int agf_map_apply_ws(const void* points, int in_dtype, int64_t n_frames, int32_t n_sites,
+                                const int32_t* ucol_ptr, const int32_t* ucol_sites, int32_t n_ucol, int32_t nnz,
+                                const double* umat_t, int32_t n_cg, void* out, int out_dtype, double* sumsq,
+                                int nan_mode, double nan_atol, int32_t* nan_flags, void* workspace,
+                                size_t workspace_bytes, void* stream) {
   using namespace agf;
   AGF_REQUIRE(points && ucol_ptr && ucol_sites && umat_t && out, "agf_map_apply: null pointer");
   AGF_REQUIRE(n_frames >= 0 && n_sites > 0 && n_ucol > 0 && n_cg > 0 && nnz > 0, "agf_map_apply: bad sizes");
   AGF_REQUIRE(nan_mode == 0 || nan_flags != nullptr, "agf_map_apply: nan_mode 1 needs nan_flags");
   AGF_REQUIRE((in_dtype == AGF_F32 || in_dtype == AGF_F64) && (out_dtype == AGF_F32 || out_dtype == AGF_F64),
               "agf_map_apply: bad dtype");
+  AGF_REQUIRE(workspace == nullptr || (reinterpret_cast<uintptr_t>(workspace) % 256) == 0,
+              "agf_map_apply: workspace must be 256-byte aligned");
   if (n_frames == 0) return AGF_OK;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 #define AGF_APPLY(TI, TO)                                                                                      \
   return apply_typed<TI, TO>(points, n_frames, n_sites, ucol_ptr, ucol_sites, n_ucol, nnz, umat_t, n_cg, out, \
-                             sumsq, nan_mode, nan_atol, nan_flags, s)
+                             sumsq, nan_mode, nan_atol, nan_flags, workspace, workspace_bytes, s)
   if (in_dtype == AGF_F32 && out_dtype == AGF_F64) AGF_APPLY(float, double);
   if (in_dtype == AGF_F32 && out_dtype == AGF_F32) AGF_APPLY(float, float);
   if (in_dtype == AGF_F64 && out_dtype == AGF_F64) AGF_APPLY(double, double);
   AGF_APPLY(double, float);
 #undef AGF_APPLY
+}
+
+extern "C" int agf_map_apply(const void* points, int in_dtype, int64_t n_frames, int32_t n_sites,
+                             const int32_t* ucol_ptr, const int32_t* ucol_sites, int32_t n_ucol, int32_t nnz,
+                             const double* umat_t, int32_t n_cg, void* out, int out_dtype, double* sumsq,
+                             int nan_mode, double nan_atol, int32_t* nan_flags, void* stream) {
+  return agf_map_apply_ws(points, in_dtype, n_frames, n_sites, ucol_ptr, ucol_sites, n_ucol, nnz, umat_t, n_cg, out,
+                          out_dtype, sumsq, nan_mode, nan_atol, nan_flags, nullptr, 0, stream);
 }
 
 extern "C" int agf_map_apply_sparse(const void* points, int in_dtype, int64_t n_frames, int32_t n_sites,

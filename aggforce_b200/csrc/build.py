@@ -10,7 +10,7 @@ from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent
 SOURCES = ["common.cu", "gram.cu", "apply.cu", "pairs.cu", "featgram.cu", "synth.cu"]
-HEADERS = ["common.cuh", "frame_pipe.cuh", "../../include/agf_b200.h"]
+HEADERS = ["common.cuh", "frame_pipe.cuh", "panel.cuh", "../../include/agf_b200.h"]
 LIB = CSRC / "libagf_b200.so"
 STAMP = CSRC / ".libagf_b200.stamp"
 

@@ -19,6 +19,7 @@
 // handful of frames) and agf_feat_apply (application of the fitted map, featlinearmap.py:
 // 512-520 + map/core.py:428-430, without materialising per-frame weights).
 #include "common.cuh"
+#include "panel.cuh"
 
 namespace agf {
 
@@ -231,6 +232,69 @@ __global__ void __launch_bounds__(kFgThreads, 1) feat_gram_kernel(const __grid_c
   }
 }
 
+// ---------------------------------------------------------------------------- workspace variant
+// feat_pack_kernel evaluates every regression row ONCE -- group sums, group mean positions,
+// distance to the bead, clipped Gaussians and their derivative, all in float64 -- and writes it as
+// packed DMMA panels  ws[chunk][bead][block][24 rows][132]  (panel.cuh); the batched panel SYRK
+// (gram.cu: panel_syrk_kernel, batch = beads) then contracts them.  Against the fused kernel
+// above this removes the 7x re-evaluation of every feature slab, skips the mirrored half of the
+// diagonal blocks and all but one tile column of the nearly empty last block (n_feat 769 = 6*128+1).
+template <typename T>
+__global__ void __launch_bounds__(256) feat_pack_kernel(const __grid_constant__ FeatParams p, double* __restrict__ ws) {
+  __shared__ double bead_pos[kPanelKF][3];
+  const int64_t chunk = blockIdx.x / p.n_cg;
+  const int bead = blockIdx.x - (int)(chunk * p.n_cg);
+  const int64_t t0 = chunk * kPanelKF;
+  const int nf = (int)min((int64_t)kPanelKF, p.n_frames - t0);
+  const T* coords = reinterpret_cast<const T*>(p.coords);
+  const T* forces = reinterpret_cast<const T*>(p.forces);
+  const int64_t fstride = (int64_t)p.n_sites * 3;
+  double* slab = ws + ((int64_t)chunk * p.n_cg + bead) * p.n_blocks * kPanelElems;  // [block][24][132]
+  bead_positions<T>(p, coords, t0, nf, bead, bead_pos);
+  // rows of frames past the end contribute nothing
+  if (nf < kPanelKF) {
+    const int rows0 = nf * 3, nrows = kPanelRows - rows0;
+    for (int i = threadIdx.x; i < p.n_blocks * nrows * kPanelCols; i += blockDim.x) {
+      const int blk = i / (nrows * kPanelCols), rem = i - blk * nrows * kPanelCols;
+      const int r = rows0 + rem / kPanelCols, x = rem % kPanelCols;
+      slab[(int64_t)blk * kPanelElems + r * kPanelStride + x] = 0.0;
+    }
+  }
+  __syncthreads();
+  const int G = p.n_groups, nb = p.nb;
+  for (int item = threadIdx.x; item < nf * G; item += blockDim.x) {
+    const int t = item / G, g = item - t * G;
+    const T* fr_f = forces + (t0 + t) * fstride;
+    double f[3], m;
+    group_sum<T>(fr_f, p.grp_ptr, p.grp_sites, g, f, m);
+    {
+      double* dst = slab + (int64_t)(g >> 7) * kPanelElems + (t * 3) * kPanelStride + (g & 127);
+      dst[0] = f[0];
+      dst[kPanelStride] = f[1];
+      dst[2 * kPanelStride] = f[2];
+    }
+    if (g < p.n_channels) {
+      const T* fr_c = coords + (t0 + t) * fstride;
+      double pos[3];
+      group_sum<T>(fr_c, p.grp_ptr, p.grp_sites, g, pos, m);
+      const double dx = pos[0] / m - bead_pos[t][0], dy = pos[1] / m - bead_pos[t][1],
+                   dz = pos[2] / m - bead_pos[t][2];
+      const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+      const double ux = dx / dist, uy = dy / dist, uz = dz / dist;  // NaN at dist == 0
+      for (int k = 0; k < nb; ++k) {
+        const int col = G + g * nb + k;
+        double gk, gp;
+        clipped_gauss(dist, __ldg(p.centers + k), p.inv_width, p.clip, p.ln_inv_clip, gk, gp);
+        const double c = p.kbt * m * gp;
+        double* dst = slab + (int64_t)(col >> 7) * kPanelElems + (t * 3) * kPanelStride + (col & 127);
+        dst[0] = gk * f[0] + c * ux;
+        dst[kPanelStride] = gk * f[1] + c * uy;
+        dst[2 * kPanelStride] = gk * f[2] + c * uz;
+      }
+    }
+  }
+}
+
 __global__ void symmetrize_batch_kernel(double* g, int n, int batch) {
   const int64_t per = (int64_t)n * n;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -404,6 +468,61 @@ extern "C" int agf_gram_feat(const void* coords, const void* forces, int dtype, 
     feat_gram_kernel<double><<<grid, kFgThreads, smem, s>>>(p);
   }
   AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}
+
+extern "C" size_t agf_gram_feat_workspace_bytes(int32_t n_groups, int32_t n_channels, int32_t nb, int32_t n_cg,
+                                                int64_t n_frames) {
+  using namespace agf;
+  if (n_groups <= 0 || n_channels < 0 || nb <= 0 || n_cg <= 0 || n_frames <= 0) return 0;
+  const int64_t n_feat = (int64_t)n_groups + (int64_t)nb * n_channels;
+  const int64_t per_chunk = (int64_t)n_cg * panel_blocks((int)n_feat) * kPanelBytes;
+  const int64_t chunks = (n_frames + kPanelKF - 1) / kPanelKF;
+  const int64_t cap = (int64_t)2 << 30;  // slabs of at most 2 GiB
+  int64_t want = chunks * per_chunk;
+  if (want > cap) want = cap / per_chunk * per_chunk;
+  if (want < per_chunk) want = per_chunk;
+  return (size_t)want;
+}
+
+extern "C" int agf_gram_feat_ws(const void* coords, const void* forces, int dtype, int64_t n_frames, int32_t n_sites,
+                                const int32_t* grp_ptr, const int32_t* grp_sites, int32_t n_groups,
+                                int32_t n_channels, const int32_t* bead_ptr, const int32_t* bead_sites,
+                                const double* bead_w, int32_t n_cg, const double* centers, int32_t nb, double width,
+                                double clip, double kbt, double* gram, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  using namespace agf;
+  FeatParams p;
+  int rc = fill_params(p, coords, forces, n_frames, n_sites, grp_ptr, grp_sites, n_groups, n_channels, bead_ptr,
+                       bead_sites, bead_w, n_cg, centers, nb, width, clip, kbt);
+  if (rc) return rc;
+  AGF_REQUIRE(forces && gram, "agf_gram_feat_ws: null pointer");
+  AGF_REQUIRE(dtype == AGF_F32 || dtype == AGF_F64, "agf_gram_feat_ws: bad dtype");
+  const int64_t per_chunk = (int64_t)n_cg * p.n_blocks * kPanelBytes;
+  if (workspace == nullptr || (int64_t)workspace_bytes < per_chunk)
+    return agf_gram_feat(coords, forces, dtype, n_frames, n_sites, grp_ptr, grp_sites, n_groups, n_channels, bead_ptr,
+                         bead_sites, bead_w, n_cg, centers, nb, width, clip, kbt, gram, stream);
+  AGF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) % 16) == 0, "agf_gram_feat_ws: workspace must be 16-byte aligned");
+  if (n_frames == 0) return AGF_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t slab_chunks = (int64_t)workspace_bytes / per_chunk;
+  const int64_t slab_frames = slab_chunks * kPanelKF;
+  const size_t elem = dtype == AGF_F32 ? 4 : 8;
+  const size_t frame_bytes = (size_t)n_sites * 3 * elem;
+  for (int64_t f0 = 0; f0 < n_frames; f0 += slab_frames) {
+    const int64_t nf = n_frames - f0 < slab_frames ? n_frames - f0 : slab_frames;
+    const int64_t chunks = (nf + kPanelKF - 1) / kPanelKF;
+    p.coords = reinterpret_cast<const char*>(coords) + (size_t)f0 * frame_bytes;
+    p.forces = reinterpret_cast<const char*>(forces) + (size_t)f0 * frame_bytes;
+    p.n_frames = nf;
+    const int64_t grid = chunks * n_cg;
+    AGF_REQUIRE(grid < (int64_t)1 << 31, "agf_gram_feat_ws: slab too large");
+    if (dtype == AGF_F32) feat_pack_kernel<float><<<(unsigned)grid, 256, 0, s>>>(p, reinterpret_cast<double*>(workspace));
+    else feat_pack_kernel<double><<<(unsigned)grid, 256, 0, s>>>(p, reinterpret_cast<double*>(workspace));
+    AGF_CUDA_TRY(cudaGetLastError());
+    rc = launch_panel_syrk(reinterpret_cast<const double*>(workspace), chunks, p.n_feat, n_cg, gram, s);
+    if (rc) return rc;
+  }
   return AGF_OK;
 }
 

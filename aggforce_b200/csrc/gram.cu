@@ -18,6 +18,7 @@
 // columns).  Larger systems: CTAs enumerate 128x128 block pairs (I <= J) and each warp owns a
 // static 2 x 16 tile rectangle; operands are gathered from global memory (compute bound by 60x).
 #include "frame_pipe.cuh"
+#include "panel.cuh"
 
 namespace agf {
 
@@ -485,10 +486,9 @@ __global__ void __launch_bounds__(kGramThreads, 1) gram_block_kernel(const __gri
 //                      f64 adds and no block-wide barrier beside the DMMA stream.
 // The workspace costs 66.5 KB of HBM traffic per frame at n_red = 2600 against 20 Mflop of DMMA
 // work: irrelevant for a kernel that is compute bound by 60x.
-constexpr int kWsKF = 8;
-constexpr int kWsRows = 3 * kWsKF;
-constexpr int kWsPanel = kWsRows * kStride;  // doubles per (chunk, block)
-constexpr int kWsStages = 4;
+constexpr int kWsKF = kPanelKF;
+constexpr int kWsPanel = kPanelElems;  // doubles per (chunk, block)
+static_assert(kStride == kPanelStride && kBlockCols == kPanelCols, "panel geometry");
 
 template <typename T>
 __global__ void __launch_bounds__(256) gram_pack_kernel(const T* __restrict__ forces, int64_t n_frames, int n_sites,
@@ -524,99 +524,97 @@ __global__ void __launch_bounds__(256) gram_pack_kernel(const T* __restrict__ fo
 struct SyrkWsParams {
   const double* ws;
   int64_t n_chunks;
-  int32_t n_red, n_blocks, n_pairs, k_splits;
+  int32_t n, n_blocks, n_pairs, k_splits, batch;
   double* gram;
 };
 
-__global__ void __launch_bounds__(288, 1) gram_syrk_ws_kernel(const __grid_constant__ SyrkWsParams p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty = full + kWsStages;
-  double* stages = reinterpret_cast<double*>(smem + 128);  // [kWsStages][2][kWsPanel]
-  const int pair = blockIdx.x % p.n_pairs;
-  const int ksplit = blockIdx.x / p.n_pairs;
-  int bi = 0, bj = 0;
-  {
-    int rem = pair, rowlen = p.n_blocks;
+// Block pair of work item `pair`, heaviest first: off-diagonal pairs of full blocks, then
+// diagonal blocks (17/32 of the tiles), then everything touching a narrow last block.
+__device__ __forceinline__ void syrk_pair(int pair, int n_blocks, bool last_narrow, int& bi, int& bj) {
+  const int nf = last_narrow ? n_blocks - 1 : n_blocks;
+  const int n_off = nf * (nf - 1) / 2;
+  if (pair < n_off) {
+    int rem = pair, rowlen = nf - 1;
+    bi = 0;
     while (rem >= rowlen) {
       rem -= rowlen;
       --rowlen;
       ++bi;
     }
-    bj = bi + rem;
+    bj = bi + 1 + rem;
+  } else if (pair < n_off + nf) {
+    bi = bj = pair - n_off;
+  } else {
+    bi = pair - n_off - nf;  // 0 .. n_blocks-1 against the last block
+    bj = n_blocks - 1;
   }
+}
+
+__global__ void __launch_bounds__(kPanelThreads, 1) panel_syrk_kernel(const __grid_constant__ SyrkWsParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  // consecutive CTAs = the block pairs of one (k-split, batch item): they stream the same chunks
+  // at the same time, so every panel is fetched from HBM once and re-read through L2
+  const int pair = blockIdx.x % p.n_pairs;
+  const int rest = blockIdx.x / p.n_pairs;
+  const int bt = rest % p.batch, ksplit = rest / p.batch;
+  const int ct_last = (p.n - (p.n_blocks - 1) * kPanelCols + 7) / 8;
+  int bi, bj;
+  syrk_pair(pair, p.n_blocks, ct_last < 16, bi, bj);
   const bool diag = bi == bj;
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kWsStages; ++i) {
-      mbar_init(&full[i], 1);
-      mbar_init(&empty[i], kGramWarps);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
+  const int ct_i = bi == p.n_blocks - 1 ? ct_last : 16, ct_j = bj == p.n_blocks - 1 ? ct_last : 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_mine = p.n_chunks > ksplit ? (p.n_chunks - ksplit + p.k_splits - 1) / p.k_splits : 0;
-  constexpr uint32_t kPanelBytes = kWsPanel * sizeof(double);
-  if (warp == kGramWarps) {
-    if (lane == 0) {
-      for (int64_t j = 0; j < n_mine; ++j) {
-        const int64_t c = ksplit + j * p.k_splits;
-        const int stage = (int)(j % kWsStages);
-        mbar_wait(&empty[stage], (uint32_t)(((j / kWsStages) & 1) ^ 1));
-        double* dst = stages + (size_t)stage * 2 * kWsPanel;
-        const double* src_i = p.ws + ((int64_t)c * p.n_blocks + bi) * kWsPanel;
-        const double* src_j = p.ws + ((int64_t)c * p.n_blocks + bj) * kWsPanel;
-        mbar_expect_tx(&full[stage], diag ? kPanelBytes : 2 * kPanelBytes);
-        for (uint32_t off = 0; off < kPanelBytes; off += kBulkPiece) {
-          const uint32_t piece = kPanelBytes - off < kBulkPiece ? kPanelBytes - off : kBulkPiece;
-          tma_bulk_g2s(reinterpret_cast<char*>(dst) + off, reinterpret_cast<const char*>(src_i) + off, piece,
-                       &full[stage]);
-          if (!diag)
-            tma_bulk_g2s(reinterpret_cast<char*>(dst + kWsPanel) + off, reinterpret_cast<const char*>(src_j) + off,
-                         piece, &full[stage]);
-        }
-      }
-    }
-    return;
-  }
-  const int g = lane >> 2, q = lane & 3;
+  const int r0 = warp, r1 = 15 - warp;
+  const uint32_t m0 = panel_row_mask(r0, ct_i, ct_j, diag), m1 = panel_row_mask(r1, ct_i, ct_j, diag);
+  PanelStream st;
+  const int64_t chunk_step = (int64_t)p.batch * p.n_blocks * kPanelElems;
+  const double* base = p.ws + ((int64_t)ksplit * p.batch + bt) * p.n_blocks * kPanelElems;
+  st.a = base + (int64_t)bi * kPanelElems;
+  st.b = base + (int64_t)bj * kPanelElems;
+  st.a_step = st.b_step = chunk_step * p.k_splits;
+  st.n = p.n_chunks > ksplit ? (p.n_chunks - ksplit + p.k_splits - 1) / p.k_splits : 0;
+  st.same = diag;
   double acc[2][16][2];
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int c = 0; c < 16; ++c) acc[r][c][0] = acc[r][c][1] = 0.0;
-  for (int64_t j = 0; j < n_mine; ++j) {
-    const int stage = (int)(j % kWsStages);
-    mbar_wait(&full[stage], (uint32_t)((j / kWsStages) & 1));
-    const double* panel_i = stages + (size_t)stage * 2 * kWsPanel;
-    const double* panel_j = diag ? panel_i : panel_i + kWsPanel;
-    const double* lane_i = panel_i + q * kStride + g + warp * 16;
-    const double* lane_j = panel_j + q * kStride + g;
-#pragma unroll 2
-    for (int kk = 0; kk < kWsRows / 4; ++kk) {
-      const double a0 = lane_i[kk * 4 * kStride], a1 = lane_i[kk * 4 * kStride + 8];
-#pragma unroll
-      for (int cc = 0; cc < 16; ++cc) {
-        const double b = lane_j[kk * 4 * kStride + cc * 8];
-        dmma884(acc[0][cc][0], acc[0][cc][1], a0, b);
-        dmma884(acc[1][cc][0], acc[1][cc][1], a1, b);
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[stage]);
-  }
+  if (!panel_mainloop(smem, st, m0, m1, acc)) return;
+  const int g = lane >> 2, q = lane & 3;
+  double* gram = p.gram + (int64_t)bt * p.n * p.n;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
-    const int i = bi * kBlockCols + (warp * 2 + r) * 8 + g;
-    if (i >= p.n_red) continue;
-    double* row = p.gram + (int64_t)i * p.n_red;
+    const uint32_t m = r == 0 ? m0 : m1;
+    const int i = bi * kPanelCols + (r == 0 ? r0 : r1) * 8 + g;
+    if (m == 0u || i >= p.n) continue;
+    double* row = gram + (int64_t)i * p.n;
 #pragma unroll
     for (int cc = 0; cc < 16; ++cc) {
-      const int j2 = bj * kBlockCols + cc * 8 + 2 * q;
-      if (j2 < p.n_red) atomicAdd(row + j2, acc[r][cc][0]);
-      if (j2 + 1 < p.n_red) atomicAdd(row + j2 + 1, acc[r][cc][1]);
+      if (!((m >> cc) & 1u)) continue;
+      const int j2 = bj * kPanelCols + cc * 8 + 2 * q;
+      if (j2 < p.n) atomicAdd(row + j2, acc[r][cc][0]);
+      if (j2 + 1 < p.n) atomicAdd(row + j2 + 1, acc[r][cc][1]);
     }
   }
+}
+
+int launch_panel_syrk(const double* ws, int64_t n_chunks, int32_t n, int32_t batch, double* gram,
+                      cudaStream_t stream) {
+  if (n_chunks <= 0) return AGF_OK;
+  SyrkWsParams p;
+  p.ws = ws;
+  p.n_chunks = n_chunks;
+  p.n = n;
+  p.n_blocks = panel_blocks(n);
+  p.n_pairs = p.n_blocks * (p.n_blocks + 1) / 2;
+  p.batch = batch;
+  p.gram = gram;
+  // enough CTAs for ~4 waves so that the cheap (diagonal / narrow) items at the end of every
+  // (k-split, batch) group fill in behind the full ones
+  const int64_t items = (int64_t)p.n_pairs * batch;
+  int64_t ks = (4LL * sm_count() + items - 1) / items;
+  if (ks > n_chunks) ks = n_chunks;
+  if (ks < 1) ks = 1;
+  p.k_splits = (int32_t)ks;
+  AGF_CUDA_TRY(cudaFuncSetAttribute(panel_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPanelSmem));
+  panel_syrk_kernel<<<(unsigned)(items * ks), kPanelThreads, kPanelSmem, stream>>>(p);
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
 }
 
 __global__ void symmetrize_kernel(double* g, int n) {
@@ -751,9 +749,6 @@ extern "C" int agf_gram_linear_ws(const void* forces, int dtype, int64_t n_frame
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int64_t slab_chunks = (int64_t)workspace_bytes / per_chunk;
   const int64_t slab_frames = slab_chunks * kWsKF;
-  const int n_pairs = (int)(n_blocks * (n_blocks + 1) / 2);
-  const size_t smem = 128 + (size_t)kWsStages * 2 * kWsPanel * sizeof(double);
-  AGF_CUDA_TRY(cudaFuncSetAttribute(gram_syrk_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const size_t elem = dtype == AGF_F32 ? 4 : 8;
   for (int64_t f0 = 0; f0 < n_frames; f0 += slab_frames) {
     const int64_t nf = n_frames - f0 < slab_frames ? n_frames - f0 : slab_frames;
@@ -770,19 +765,8 @@ extern "C" int agf_gram_linear_ws(const void* forces, int dtype, int64_t n_frame
                                                                    col_ptr, col_sites, n_red, (int)n_blocks,
                                                                    reinterpret_cast<double*>(workspace));
     AGF_CUDA_TRY(cudaGetLastError());
-    SyrkWsParams p;
-    p.ws = reinterpret_cast<const double*>(workspace);
-    p.n_chunks = chunks;
-    p.n_red = n_red;
-    p.n_blocks = (int)n_blocks;
-    p.n_pairs = n_pairs;
-    int64_t ks = (2LL * sm_count() + n_pairs - 1) / n_pairs;
-    if (ks > chunks) ks = chunks;
-    if (ks < 1) ks = 1;
-    p.k_splits = (int)ks;
-    p.gram = gram;
-    gram_syrk_ws_kernel<<<n_pairs * p.k_splits, 288, smem, s>>>(p);
-    AGF_CUDA_TRY(cudaGetLastError());
+    int rc = launch_panel_syrk(reinterpret_cast<const double*>(workspace), chunks, n_red, 1, gram, s);
+    if (rc) return rc;
   }
   return AGF_OK;
 }

@@ -20,6 +20,8 @@ from copy import deepcopy
 from queue import Empty, SimpleQueue
 from typing import Any, Callable, ClassVar, Dict, Final, Generator, Iterable, List, Optional, Tuple, Union
 
+import ctypes as C
+
 import numpy as np
 import scipy.sparse as ss
 import torch
@@ -272,8 +274,12 @@ class _FusedContext:
             assert t0 == t1 and c.shape == f.shape
             if c.dtype != f.dtype:
                 c, f = c.to(torch.float64), f.to(torch.float64)
-            _lib.call("agf_gram_feat", _engine.ptr(c), _engine.ptr(f), _engine.dtype_code(c), c.shape[0], self.n_fg,
-                      *self._common(), float(kbt), _engine.ptr(gram), _engine.stream_ptr())
+            need = int(_lib.lib().agf_gram_feat_workspace_bytes(self.n_groups, self.n_channels, self.nb, self.n_cg,
+                                                                c.shape[0]))
+            ws = _engine.workspace(need)
+            _lib.call("agf_gram_feat_ws", _engine.ptr(c), _engine.ptr(f), _engine.dtype_code(c), c.shape[0], self.n_fg,
+                      *self._common(), float(kbt), _engine.ptr(gram), _engine.ptr(ws), C.c_size_t(ws.numel()),
+                      _engine.stream_ptr())
         _engine.allreduce_sum_(gram)
         _lib.call("agf_symmetrize_batch", _engine.ptr(gram), nf, self.n_cg, _engine.stream_ptr())
         host = _engine.to_host(gram)

@@ -104,6 +104,22 @@ int agf_map_apply(const void* points, int in_dtype, int64_t n_frames, int32_t n_
                   const double* umat_t, int32_t n_cg, void* out, int out_dtype, double* sumsq,
                   int nan_mode, double nan_atol, int32_t* nan_flags, void* stream);
 
+/* Same contract with a caller-provided scratch buffer for maps too large for the shared-memory
+ * resident kernel (n_cg > 64, e.g. 500 beads x 2600 unique columns): group sums are packed once
+ * into f64 operand panels and a TMA-fed DMMA GEMM contracts them (about 8x faster than the
+ * fallback at that size).  `workspace`: device memory, 256-byte aligned, size from
+ * agf_map_apply_workspace_bytes (0 = not needed, the small kernel applies); frames are processed in
+ * slabs, so any size >= header + packed map + one 128-frame block works.  NULL / too small =
+ * agf_map_apply.
+ */
+size_t agf_map_apply_workspace_bytes(int in_dtype, int32_t n_sites, int32_t n_ucol, int32_t nnz,
+                                     int32_t n_cg, int64_t n_frames);
+int agf_map_apply_ws(const void* points, int in_dtype, int64_t n_frames, int32_t n_sites,
+                     const int32_t* ucol_ptr, const int32_t* ucol_sites, int32_t n_ucol, int32_t nnz,
+                     const double* umat_t, int32_t n_cg, void* out, int out_dtype, double* sumsq,
+                     int nan_mode, double nan_atol, int32_t* nan_flags, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* Sparse-row form for slice / uniform maps (a few non-zeros per bead): CSR rows
  *   row_ptr device int32 [n_cg + 1], row_sites device int32 [nnz], row_weights device f64 [nnz].
  * Only the referenced sites are read.  Same outputs / NaN semantics as agf_map_apply with
@@ -170,6 +186,20 @@ int agf_gram_feat(const void* coords, const void* forces, int dtype, int64_t n_f
                   const int32_t* bead_sites, const double* bead_w, int32_t n_cg,
                   const double* centers, int32_t nb, double width, double clip, double kbt,
                   double* gram, void* stream);
+
+/* Same contract with a caller-provided scratch buffer (device, 16-byte aligned, size from
+ * agf_gram_feat_workspace_bytes; frames are processed in slabs so any size >= one 8-frame chunk
+ * works): every regression row is evaluated once, written as packed f64 operand panels and
+ * contracted by a batched TMA-fed DMMA SYRK.  NULL / too small = agf_gram_feat.
+ */
+size_t agf_gram_feat_workspace_bytes(int32_t n_groups, int32_t n_channels, int32_t nb, int32_t n_cg,
+                                     int64_t n_frames);
+int agf_gram_feat_ws(const void* coords, const void* forces, int dtype, int64_t n_frames,
+                     int32_t n_sites, const int32_t* grp_ptr, const int32_t* grp_sites,
+                     int32_t n_groups, int32_t n_channels, const int32_t* bead_ptr,
+                     const int32_t* bead_sites, const double* bead_w, int32_t n_cg,
+                     const double* centers, int32_t nb, double width, double clip, double kbt,
+                     double* gram, void* workspace, size_t workspace_bytes, void* stream);
 
 int agf_symmetrize_batch(double* gram, int32_t n, int32_t batch, void* stream);
 

@@ -20,6 +20,11 @@ ctx.grams(c, f, 0.6955215); torch.cuda.synchronize()
 t0 = time.perf_counter(); g = ctx.grams(c, f, 0.6955215); torch.cuda.synchronize(); dt = time.perf_counter() - t0
 nf = g.shape[1]
 flop = 10 * 3 * nf * (nf + 1) * T
+from aggforce_b200 import _lib
+_lib.timing(True); ctx.grams(c, f, 0.6955215)
+recs = _lib.timing_records(); _lib.timing(False)
+kms = sum(ms for name, ms in recs if name.startswith("agf_gram_feat"))
+print(f"feat gram kernels only: {kms:.1f} ms  {T/kms*1e3:.3e} frames/s  {flop/kms/1e9:.2f} TFLOP/s algorithmic ({flop/kms/1e9/37.15*100:.1f}% of DMMA peak)")
 print(f"feat gram: n_feat {nf}, T {T}: {dt*1e3:.1f} ms  {T/dt:.3e} frames/s  {flop/dt/1e12:.2f} TFLOP/s algorithmic ({flop/dt/1e12/37.15*100:.1f}% of DMMA peak)")
 t0 = time.perf_counter()
 res = agf.project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds=topo.xh_constraints,

@@ -39,7 +39,18 @@ rng = np.random.default_rng(0)
 red = rng.normal(size=(500, n_red))
 lm = agf.LinearMap(red[:, cols])
 ms = timeit(lambda: lm(forces))
-print(f"dense apply (n_ucol {n_red}): {ms:.2f} ms  {T/ms*1e3:.3e} frames/s")
+aflop = 6 * 500 * n_red * T
+print(f"dense apply (n_ucol {n_red}): {ms:.2f} ms  {T/ms*1e3:.3e} frames/s  {aflop/ms/1e9:.2f} TFLOP/s ({aflop/ms/1e9/37.15*100:.1f}% of DMMA peak)")
+lmn = agf.LinearMap(red[:, cols], handle_nans=False)
+ms = timeit(lambda: lmn(forces))
+print(f"dense apply, handle_nans=False: {ms:.2f} ms")
+fn = forces[:4096].clone(); fn[5, 7, 1] = float("nan"); fn[4000, 4999, 2] = float("nan")
+red0 = red.copy(); red0[:, cols[7]] = 0.0; red0[:, cols[4999]] = 0.0
+lm0 = agf.LinearMap(red0[:, cols])
+on = lm0(fn).cpu().numpy()
+fz = fn.cpu().numpy().copy(); fz[np.isnan(fz)] = 0.0
+refn = oracle.apply_map(fz, red0[:, cols])
+print("apply with NaNs under zero columns: rel fro", np.linalg.norm(on - refn) / np.linalg.norm(refn))
 out = lm(forces[:32]).cpu().numpy()
 refo = oracle.apply_map(forces[:32].cpu().numpy(), red[:, cols])
 print("apply parity rel fro", np.linalg.norm(out - refo) / np.linalg.norm(refo))
