@@ -452,37 +452,34 @@ __global__ void __launch_bounds__(kPanelThreads, 1) apply_gemm_kernel(const __gr
   const int cols_left = p.n_cg - nbk * kPanelCols;
   const int ct_cols = cols_left >= kPanelCols ? 16 : (cols_left + 7) / 8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = warp, r1 = 15 - warp;
-  const uint32_t m0 = panel_row_mask(r0, ct_rows, ct_cols, false), m1 = panel_row_mask(r1, ct_rows, ct_cols, false);
+  const int r0 = panel_warp_row(warp);
+  const uint32_t m = warp < kPanelMmaWarps ? panel_row_mask(r0, ct_rows, ct_cols, false) : 0u;
   PanelStream st;
   st.a = p.ws_a + (int64_t)mb * p.n_kchunks * kPanelElems;
   st.b = p.ws_b + (int64_t)nbk * p.n_kchunks * kPanelElems;
   st.a_step = st.b_step = kPanelElems;
   st.n = p.n_kchunks;
   st.same = false;
-  double acc[2][16][2];
-  if (!panel_mainloop(smem, st, m0, m1, acc)) return;
+  double acc[16][2];
+  if (!panel_mainloop<false>(smem, st, m, acc)) return;
   const int g = lane >> 2, q = lane & 3;
   TO* out = reinterpret_cast<TO*>(p.out);
   double sq = 0.0;
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const uint32_t m = r == 0 ? m0 : m1;
-    const int64_t t = t0 + (r == 0 ? r0 : r1) * 8 + g;
-    if (m == 0u || t >= p.n_frames) continue;
+  const int64_t t = t0 + r0 * 8 + g;
+  if (m != 0u && t < p.n_frames) {
     TO* orow = out + t * (int64_t)p.n_cg * 3 + d;
 #pragma unroll
     for (int cc = 0; cc < 16; ++cc) {
       if (!((m >> cc) & 1u)) continue;
       const int c = nbk * kPanelCols + cc * 8 + 2 * q;
       if (c < p.n_cg) {
-        store_out(orow + (int64_t)c * 3, acc[r][cc][0]);
-        const double v = (double)static_cast<TO>(acc[r][cc][0]);
+        store_out(orow + (int64_t)c * 3, acc[cc][0]);
+        const double v = (double)static_cast<TO>(acc[cc][0]);
         sq += v * v;
       }
       if (c + 1 < p.n_cg) {
-        store_out(orow + (int64_t)(c + 1) * 3, acc[r][cc][1]);
-        const double v = (double)static_cast<TO>(acc[r][cc][1]);
+        store_out(orow + (int64_t)(c + 1) * 3, acc[cc][1]);
+        const double v = (double)static_cast<TO>(acc[cc][1]);
         sq += v * v;
       }
     }

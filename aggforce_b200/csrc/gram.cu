@@ -563,8 +563,8 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_syrk_kernel(const __gr
   const bool diag = bi == bj;
   const int ct_i = bi == p.n_blocks - 1 ? ct_last : 16, ct_j = bj == p.n_blocks - 1 ? ct_last : 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = warp, r1 = 15 - warp;
-  const uint32_t m0 = panel_row_mask(r0, ct_i, ct_j, diag), m1 = panel_row_mask(r1, ct_i, ct_j, diag);
+  const int r0 = panel_warp_row(warp);
+  const uint32_t m = warp < kPanelMmaWarps ? panel_row_mask(r0, ct_i, ct_j, diag) : 0u;
   PanelStream st;
   const int64_t chunk_step = (int64_t)p.batch * p.n_blocks * kPanelElems;
   const double* base = p.ws + ((int64_t)ksplit * p.batch + bt) * p.n_blocks * kPanelElems;
@@ -573,23 +573,18 @@ __global__ void __launch_bounds__(kPanelThreads, 1) panel_syrk_kernel(const __gr
   st.a_step = st.b_step = chunk_step * p.k_splits;
   st.n = p.n_chunks > ksplit ? (p.n_chunks - ksplit + p.k_splits - 1) / p.k_splits : 0;
   st.same = diag;
-  double acc[2][16][2];
-  if (!panel_mainloop(smem, st, m0, m1, acc)) return;
+  double acc[16][2];
+  if (!panel_mainloop<true>(smem, st, m, acc)) return;
   const int g = lane >> 2, q = lane & 3;
-  double* gram = p.gram + (int64_t)bt * p.n * p.n;
+  const int i = bi * kPanelCols + r0 * 8 + g;
+  if (m == 0u || i >= p.n) return;
+  double* row = p.gram + (int64_t)bt * p.n * p.n + (int64_t)i * p.n;
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const uint32_t m = r == 0 ? m0 : m1;
-    const int i = bi * kPanelCols + (r == 0 ? r0 : r1) * 8 + g;
-    if (m == 0u || i >= p.n) continue;
-    double* row = gram + (int64_t)i * p.n;
-#pragma unroll
-    for (int cc = 0; cc < 16; ++cc) {
-      if (!((m >> cc) & 1u)) continue;
-      const int j2 = bj * kPanelCols + cc * 8 + 2 * q;
-      if (j2 < p.n) atomicAdd(row + j2, acc[r][cc][0]);
-      if (j2 + 1 < p.n) atomicAdd(row + j2 + 1, acc[r][cc][1]);
-    }
+  for (int cc = 0; cc < 16; ++cc) {
+    if (!((m >> cc) & 1u)) continue;
+    const int j2 = bj * kPanelCols + cc * 8 + 2 * q;
+    if (j2 < p.n) atomicAdd(row + j2, acc[cc][0]);
+    if (j2 + 1 < p.n) atomicAdd(row + j2 + 1, acc[cc][1]);
   }
 }
 

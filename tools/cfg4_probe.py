@@ -41,6 +41,11 @@ lm = agf.LinearMap(red[:, cols])
 ms = timeit(lambda: lm(forces))
 aflop = 6 * 500 * n_red * T
 print(f"dense apply (n_ucol {n_red}): {ms:.2f} ms  {T/ms*1e3:.3e} frames/s  {aflop/ms/1e9:.2f} TFLOP/s ({aflop/ms/1e9/37.15*100:.1f}% of DMMA peak)")
+_lib.timing(True); lm(forces); recs = _lib.timing_records(); _lib.timing(False)
+print("  entry points:", ", ".join(f"{n} {ms:.2f} ms" for n, ms in recs))
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable(); lm(forces); lm(forces); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
 lmn = agf.LinearMap(red[:, cols], handle_nans=False)
 ms = timeit(lambda: lmn(forces))
 print(f"dense apply, handle_nans=False: {ms:.2f} ms")
