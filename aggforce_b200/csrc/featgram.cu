@@ -239,9 +239,14 @@ __global__ void __launch_bounds__(kFgThreads, 1) feat_gram_kernel(const __grid_c
 // (gram.cu: panel_syrk_kernel, batch = beads) then contracts them.  Against the fused kernel
 // above this removes the 7x re-evaluation of every feature slab, skips the mirrored half of the
 // diagonal blocks and all but one tile column of the nearly empty last block (n_feat 769 = 6*128+1).
+// Phase 1 (thread per (frame, group)): group force, distance to the bead and unit vector into
+// shared memory.  Phase 2 (thread per (frame, feature column)): one clipped Gaussian each, stores
+// of consecutive threads fall on consecutive addresses of a panel row.
 template <typename T>
 __global__ void __launch_bounds__(256) feat_pack_kernel(const __grid_constant__ FeatParams p, double* __restrict__ ws) {
+  extern __shared__ __align__(16) unsigned char fp_smem[];
   __shared__ double bead_pos[kPanelKF][3];
+  double* s_grp = reinterpret_cast<double*>(fp_smem);  // [kPanelKF][G][8]: f[3], dist, m*u[3], pad
   const int64_t chunk = blockIdx.x / p.n_cg;
   const int bead = blockIdx.x - (int)(chunk * p.n_cg);
   const int64_t t0 = chunk * kPanelKF;
@@ -264,34 +269,48 @@ __global__ void __launch_bounds__(256) feat_pack_kernel(const __grid_constant__ 
   const int G = p.n_groups, nb = p.nb;
   for (int item = threadIdx.x; item < nf * G; item += blockDim.x) {
     const int t = item / G, g = item - t * G;
-    const T* fr_f = forces + (t0 + t) * fstride;
     double f[3], m;
-    group_sum<T>(fr_f, p.grp_ptr, p.grp_sites, g, f, m);
-    {
-      double* dst = slab + (int64_t)(g >> 7) * kPanelElems + (t * 3) * kPanelStride + (g & 127);
-      dst[0] = f[0];
-      dst[kPanelStride] = f[1];
-      dst[2 * kPanelStride] = f[2];
-    }
+    group_sum<T>(forces + (t0 + t) * fstride, p.grp_ptr, p.grp_sites, g, f, m);
+    double* rec = s_grp + (size_t)item * 8;
+    rec[0] = f[0];
+    rec[1] = f[1];
+    rec[2] = f[2];
     if (g < p.n_channels) {
-      const T* fr_c = coords + (t0 + t) * fstride;
       double pos[3];
-      group_sum<T>(fr_c, p.grp_ptr, p.grp_sites, g, pos, m);
+      group_sum<T>(coords + (t0 + t) * fstride, p.grp_ptr, p.grp_sites, g, pos, m);
       const double dx = pos[0] / m - bead_pos[t][0], dy = pos[1] / m - bead_pos[t][1],
                    dz = pos[2] / m - bead_pos[t][2];
       const double dist = sqrt(dx * dx + dy * dy + dz * dz);
-      const double ux = dx / dist, uy = dy / dist, uz = dz / dist;  // NaN at dist == 0
-      for (int k = 0; k < nb; ++k) {
-        const int col = G + g * nb + k;
-        double gk, gp;
-        clipped_gauss(dist, __ldg(p.centers + k), p.inv_width, p.clip, p.ln_inv_clip, gk, gp);
-        const double c = p.kbt * m * gp;
-        double* dst = slab + (int64_t)(col >> 7) * kPanelElems + (t * 3) * kPanelStride + (col & 127);
-        dst[0] = gk * f[0] + c * ux;
-        dst[kPanelStride] = gk * f[1] + c * uy;
-        dst[2 * kPanelStride] = gk * f[2] + c * uz;
-      }
+      rec[3] = dist;
+      rec[4] = m * (dx / dist);  // NaN at dist == 0
+      rec[5] = m * (dy / dist);
+      rec[6] = m * (dz / dist);
     }
+  }
+  __syncthreads();
+  const int n_feat = p.n_feat;
+  for (int item = threadIdx.x; item < nf * n_feat; item += blockDim.x) {
+    const int t = item / n_feat, col = item - t * n_feat;
+    double v0, v1, v2;
+    if (col < G) {
+      const double* rec = s_grp + (size_t)(t * G + col) * 8;
+      v0 = rec[0];
+      v1 = rec[1];
+      v2 = rec[2];
+    } else {
+      const int ch = (col - G) / nb, k = (col - G) - ch * nb;
+      const double* rec = s_grp + (size_t)(t * G + ch) * 8;
+      double gk, gp;
+      clipped_gauss(rec[3], __ldg(p.centers + k), p.inv_width, p.clip, p.ln_inv_clip, gk, gp);
+      const double c = p.kbt * gp;
+      v0 = gk * rec[0] + c * rec[4];
+      v1 = gk * rec[1] + c * rec[5];
+      v2 = gk * rec[2] + c * rec[6];
+    }
+    double* dst = slab + (int64_t)(col >> 7) * kPanelElems + (t * 3) * kPanelStride + (col & 127);
+    dst[0] = v0;
+    dst[kPanelStride] = v1;
+    dst[2 * kPanelStride] = v2;
   }
 }
 
@@ -509,6 +528,12 @@ extern "C" int agf_gram_feat_ws(const void* coords, const void* forces, int dtyp
   const int64_t slab_frames = slab_chunks * kPanelKF;
   const size_t elem = dtype == AGF_F32 ? 4 : 8;
   const size_t frame_bytes = (size_t)n_sites * 3 * elem;
+  const size_t pack_smem = (size_t)kPanelKF * n_groups * 8 * sizeof(double);
+  if (pack_smem > (size_t)200 * 1024)  // > 3200 constraint groups: per-frame records do not fit in shared memory
+    return agf_gram_feat(coords, forces, dtype, n_frames, n_sites, grp_ptr, grp_sites, n_groups, n_channels, bead_ptr,
+                         bead_sites, bead_w, n_cg, centers, nb, width, clip, kbt, gram, stream);
+  AGF_CUDA_TRY(cudaFuncSetAttribute(feat_pack_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem));
+  AGF_CUDA_TRY(cudaFuncSetAttribute(feat_pack_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pack_smem));
   for (int64_t f0 = 0; f0 < n_frames; f0 += slab_frames) {
     const int64_t nf = n_frames - f0 < slab_frames ? n_frames - f0 : slab_frames;
     const int64_t chunks = (nf + kPanelKF - 1) / kPanelKF;
@@ -517,8 +542,10 @@ extern "C" int agf_gram_feat_ws(const void* coords, const void* forces, int dtyp
     p.n_frames = nf;
     const int64_t grid = chunks * n_cg;
     AGF_REQUIRE(grid < (int64_t)1 << 31, "agf_gram_feat_ws: slab too large");
-    if (dtype == AGF_F32) feat_pack_kernel<float><<<(unsigned)grid, 256, 0, s>>>(p, reinterpret_cast<double*>(workspace));
-    else feat_pack_kernel<double><<<(unsigned)grid, 256, 0, s>>>(p, reinterpret_cast<double*>(workspace));
+    if (dtype == AGF_F32)
+      feat_pack_kernel<float><<<(unsigned)grid, 256, pack_smem, s>>>(p, reinterpret_cast<double*>(workspace));
+    else
+      feat_pack_kernel<double><<<(unsigned)grid, 256, pack_smem, s>>>(p, reinterpret_cast<double*>(workspace));
     AGF_CUDA_TRY(cudaGetLastError());
     rc = launch_panel_syrk(reinterpret_cast<const double*>(workspace), chunks, p.n_feat, n_cg, gram, s);
     if (rc) return rc;

@@ -101,10 +101,11 @@ class LinearMap:
         m = self._standard_matrix
         # change detection for in-place edits of the matrix: full digest when small, strided sample
         # (at most 64 Ki elements) plus the array identity when large (hashing 20 MB costs 20 ms)
-        flat = m.reshape(-1) if m.flags.c_contiguous else np.ascontiguousarray(m).reshape(-1)
-        stride = max(1, flat.size // 65536)
-        digest = hashlib.blake2b(np.ascontiguousarray(flat[::stride]).tobytes(), digest_size=16).digest()
-        digest += repr((m.shape, str(m.dtype), stride, m.ctypes.data if stride > 1 else 0,
+        # (strided 2-D sampling: no copy whatever the memory layout of the matrix)
+        rs, cs = max(1, m.shape[0] // 256), max(1, m.shape[1] // 256)
+        sampled = rs > 1 or cs > 1
+        digest = hashlib.blake2b(np.ascontiguousarray(m[::rs, ::cs]).tobytes(), digest_size=16).digest()
+        digest += repr((m.shape, str(m.dtype), rs, cs, m.ctypes.data if sampled else 0,
                         bool(self.handle_nans))).encode()
         if self._compiled is not None and self._compiled[0] != digest:
             self._column_labels = None  # matrix was edited in place: the fit's column structure is stale
