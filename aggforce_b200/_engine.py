@@ -221,7 +221,15 @@ def global_count(local: int) -> int:
 class Frames:
     """A ``(n_frames, n_sites, 3)`` array as the kernels see it (see module docstring)."""
 
+    def __new__(cls, array=None, *args, **kwargs):
+        # virtual frame sources (subclasses, e.g. the Gaussian-augmented frames) pass through unchanged
+        if cls is Frames and isinstance(array, Frames) and type(array) is not Frames:
+            return array
+        return super().__new__(cls)
+
     def __init__(self, array) -> None:
+        if array is self:
+            return
         inner = getattr(array, "frames", None)
         if isinstance(inner, Frames):  # agg._Shared: reuse the upload made by project_forces
             array = inner

@@ -40,6 +40,8 @@ SIGNATURES = {
                       _dbl, _dbl, _vp, _vp],
     "agf_feat_apply": [_vp, _vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _dbl, _dbl,
                        _vp, _vp, C.c_int, _vp, _vp],
+    "agf_gauss_augment": [_vp, _vp, C.c_int, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _dbl, _dbl, _vp, _u64,
+                          C.c_uint32, _i64, _vp, _vp, _vp],
     "agf_synth_frames": [_vp, _vp, _vp, _i32, _i64, _i64, _u64, _flt, _flt, _flt, _vp, _vp, _vp],
 }
 PLAIN = {"agf_version": (C.c_int, []), "agf_last_error": (C.c_char_p, []), "agf_device_sm_count": (C.c_int, []),

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from ..trajectory import AugmentedTrajectory, Augmenter, CoordsTrajectory, ForcesTrajectory, Trajectory
-from .core import CLAMap
+from .core import CLAMap, LinearMap
 
 ArrayTransform = Callable[[Any], Any]
 _T_TMap = TypeVar("_T_TMap", bound="TMap")
@@ -96,6 +96,17 @@ class AugmentedTMap(TMap):
         self.kbt: Final = kbt
 
     def __call__(self, t: Trajectory) -> Trajectory:
+        new_draw = getattr(self.augmenter, "new_draw", None)
+        if (new_draw is not None and isinstance(self.tmap, SeperableTMap) and isinstance(self.tmap.coord_map, LinearMap)
+                and isinstance(self.tmap.force_map, LinearMap)):
+            # device augmenter + linear maps: augmented coordinates / forces are generated slab by slab
+            # in front of the apply kernel (same noise realisation for both), never materialised
+            from ..trajectory.gausstraj import AugmentedFrames
+
+            draw = new_draw()
+            coords = AugmentedFrames(t.coords, self.augmenter, self.kbt, draw, "coords")
+            forces = AugmentedFrames(t.forces, self.augmenter, self.kbt, draw, "forces")
+            return Trajectory(coords=self.tmap.coord_map(coords), forces=self.tmap.force_map(forces))
         return self.tmap(AugmentedTrajectory.from_trajectory(t=t, kbt=self.kbt, augmenter=self.augmenter))
 
     def astype(self, *args, **kwargs) -> "AugmentedTMap":

@@ -3,17 +3,21 @@
 ``joptgauss_map``: augment the trajectory with one noise site per bead (``y = A x + eps``), fit
 an optimal LINEAR force map on the augmented trajectory whose coordinate map isolates the
 noise sites (kernel (a) on ``n_fg + n_cg`` columns), and wrap it so that applying it to a plain
-trajectory first re-augments with fresh noise.  The augmentation runs on the device
-(``trajectory.gausstraj.CondNormal``); the reference's JAX ``JCondNormal`` is replaced by its
-closed form.
+trajectory first re-augments with fresh noise.  The augmentation is one fused kernel
+(``agf_gauss_augment``; the reference's JAX ``JCondNormal`` is replaced by its closed form) that
+runs slab by slab in front of the Gram / apply kernels, so the augmented arrays are never
+materialised.
 """
 from __future__ import annotations
 
 from typing import Optional
 
+from types import SimpleNamespace
+
 from ..constraints import Constraints
-from ..map import AugmentedTMap, LinearMap, lmap_augvariables
-from ..trajectory import AugmentedTrajectory, CondNormal, Trajectory
+from ..map import AugmentedTMap, LinearMap
+from ..trajectory import CondNormal, Trajectory
+from ..trajectory.gausstraj import AugmentedFrames
 from .qplinear import qp_linear_map
 
 
@@ -39,7 +43,11 @@ def joptgauss_map(
     The returned map is stochastic: every application draws new noise.
     """
     augmenter = CondNormal(cov=var, premap=coord_map, seed=seed, noise=noise)
-    aug_traj = AugmentedTrajectory.from_trajectory(t=traj, augmenter=augmenter, kbt=kbt)
-    aug_coord_map = lmap_augvariables(aug_traj)
-    aug_tmap = qp_linear_map(traj=aug_traj, coord_map=aug_coord_map, constraints=constraints, **kwargs)
+    # the reference materialises AugmentedTrajectory.from_trajectory(traj) (jgauss.py:129-133); here the
+    # augmented forces are generated slab by slab while the Gram kernel consumes them
+    n_real, n_new = coord_map.n_fg_sites, coord_map.n_cg_sites
+    aug_forces = AugmentedFrames(traj.forces, augmenter, kbt, augmenter.new_draw(), "forces")
+    aug_coord_map = LinearMap([[s] for s in range(n_real, n_real + n_new)], n_fg_sites=n_real + n_new)
+    aug_tmap = qp_linear_map(traj=SimpleNamespace(forces=aug_forces), coord_map=aug_coord_map,
+                             constraints=constraints, **kwargs)
     return AugmentedTMap(aug_tmap=aug_tmap, augmenter=augmenter, kbt=kbt)

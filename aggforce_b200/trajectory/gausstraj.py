@@ -6,8 +6,10 @@
 ``CondNormal``: ``y = A x + eps, eps ~ N(0, var I)`` with ``A`` a ``LinearMap`` -- the B200
 replacement for the reference's JAX ``JCondNormal`` (``jaxgausstraj.py:99-402``), whose autodiff
 log-gradients have the closed form ``grad_y = -(y - A x)/var``, ``grad_x = A^T (y - A x)/var``.
-Noise is drawn on the device (counter-free torch Philox generator, seeded); it cannot match
-JAX's threefry stream, so parity tests inject the draw through ``noise=``.
+Sampling and both augmented arrays come from one fused kernel (``agf_gauss_augment``,
+csrc/augment.cu); noise is drawn in-kernel (Philox keyed by seed / global frame / bead / draw id, so
+frame slabs and ranks reproduce it) and cannot match JAX's threefry stream: parity tests inject
+the draw through ``noise=``.
 """
 from __future__ import annotations
 
@@ -61,7 +63,6 @@ class CondNormal(Augmenter):
         self.cov = float(cov)
         self.seed = int(np.random.default_rng().integers(0, 10**6)) if seed is None else int(seed)
         self.dtype = np.dtype(np.float32 if dtype is None else dtype)
-        self._gen: Optional[torch.Generator] = None
         self._noise = noise
 
     # -- helpers
@@ -70,16 +71,6 @@ class CondNormal(Augmenter):
 
     def _mean(self, source):
         return source if self.premap is None else self.premap(source)
-
-    def _draw(self, shape, device) -> torch.Tensor:
-        if self._noise is not None:
-            z = torch.as_tensor(self._noise).to(device=device, dtype=self._tdtype())
-            self._noise = None
-            return z
-        if self._gen is None:
-            self._gen = torch.Generator(device=device)
-            self._gen.manual_seed(self.seed)
-        return torch.randn(shape, generator=self._gen, device=device, dtype=self._tdtype())
 
     def _back(self, eps: torch.Tensor):
         """A^T eps for the pre-map (identity when premap is None)."""
@@ -91,8 +82,8 @@ class CondNormal(Augmenter):
     def sample(self, source):
         host = not (isinstance(source, torch.Tensor) and source.is_cuda)
         dev = _engine.device()
-        mean = torch.as_tensor(self._mean(source)).to(device=dev, dtype=self._tdtype())
-        y = mean + np.sqrt(self.cov) * self._draw(mean.shape, dev)
+        x = torch.as_tensor(source).to(device=dev)
+        y = self.augment_device(x, None, 0.0, self.new_draw())[0][:, x.shape[1]:].contiguous()
         return _engine.to_host(y) if host else y
 
     def log_gradient(self, source, generated):
@@ -106,24 +97,137 @@ class CondNormal(Augmenter):
             return _engine.to_host(wrt_source), _engine.to_host(wrt_generated)
         return wrt_source, wrt_generated
 
+    # -- fused device path (csrc/augment.cu)
+    def new_draw(self) -> "NoiseDraw":
+        """Token identifying ONE noise realisation: every ``augment_device`` call made with it --
+        whatever the frame slab -- sees the same noise (Philox keyed by seed / frame / bead / draw
+        id, or the injected array)."""
+        noise = None
+        if self._noise is not None:
+            noise = torch.as_tensor(self._noise).to(device=_engine.device(), dtype=self._tdtype()).contiguous()
+            self._noise = None
+        self._n_draws = getattr(self, "_n_draws", 0) + 1
+        return NoiseDraw(self._n_draws, noise)
+
+    def n_new_sites(self, n_sites: int) -> int:
+        return n_sites if self.premap is None else int(self.premap.n_cg_sites)
+
+    def _map_csr(self, n_sites: int):
+        """Device CSR of the pre-map rows and of its transpose."""
+        cached = getattr(self, "_csr", None)
+        if cached is not None and cached[0] == n_sites:
+            return cached[1]
+        m = np.eye(n_sites) if self.premap is None else np.asarray(self.premap.standard_matrix, dtype=np.float64)
+        if m.shape[1] != n_sites:
+            raise ValueError(f"premap expects {m.shape[1]} sites but the array has {n_sites}")
+
+        def csr(mat):
+            rows, cols = np.nonzero(mat)
+            ptr_ = np.zeros(mat.shape[0] + 1, dtype=np.int32)
+            np.cumsum(np.bincount(rows, minlength=mat.shape[0]), out=ptr_[1:])
+            if rows.size == 0:  # keep the device arrays non-empty
+                return _engine.dev_i32(ptr_), _engine.dev_i32([0]), _engine.dev_f64([0.0])
+            return _engine.dev_i32(ptr_), _engine.dev_i32(cols), _engine.dev_f64(mat[rows, cols])
+
+        arrays = (*csr(m), *csr(np.ascontiguousarray(m.T)), m.shape[0])
+        self._csr = (n_sites, arrays)
+        return arrays
+
+    def augment_device(self, coords: Optional[torch.Tensor], forces: Optional[torch.Tensor], kbt: float,
+                       draw: "NoiseDraw", frame0: int = 0):
+        """Augmented device arrays for a slab of frames starting at global frame ``frame0``; either
+        input may be ``None`` (its output is then ``None``)."""
+        from .. import _lib
+
+        td = self._tdtype()
+        ref = coords if coords is not None else forces
+        n_frames, n_sites = int(ref.shape[0]), int(ref.shape[1])
+        bp, bs, bw, sp, sb, sw, n_new = self._map_csr(n_sites)
+        prep = lambda t: None if t is None else t.to(td).contiguous()  # noqa: E731
+        coords, forces = prep(coords), prep(forces)
+        mk = lambda t: None if t is None else torch.empty((n_frames, n_sites + n_new, 3), dtype=td, device=t.device)  # noqa: E731
+        oc, of = mk(coords), mk(forces)
+        noise = None
+        if draw.noise is not None:
+            noise = draw.noise[frame0 : frame0 + n_frames]
+            if tuple(noise.shape) != (n_frames, n_new, 3):
+                raise ValueError(f"injected noise has shape {tuple(draw.noise.shape)}; frames {frame0}.."
+                                 f"{frame0 + n_frames} of (n_frames, {n_new}, 3) are needed")
+        p = _engine.ptr
+        _lib.call("agf_gauss_augment", p(coords), p(forces), _lib.F32 if td == torch.float32 else _lib.F64,
+                  n_frames, n_sites, p(bp), p(bs), p(bw), n_new, p(sp), p(sb), p(sw), self.cov, float(kbt), p(noise),
+                  self.seed, draw.index, int(frame0), p(oc), p(of), _engine.stream_ptr())
+        return oc, of
+
     def augment(self, coords, forces, kbt: float):
         """Augmented ``(coords, forces)`` in one device pass (trajectory/core.py:382-389 of the reference)."""
         host = not (isinstance(coords, torch.Tensor) and coords.is_cuda)
         dev = _engine.device()
-        td = self._tdtype()
-        x = torch.as_tensor(coords).to(device=dev, dtype=td)
-        f = torch.as_tensor(forces).to(device=dev, dtype=td)
-        mean = torch.as_tensor(self._mean(x)).to(dtype=td)
-        eps = np.sqrt(self.cov) * self._draw(mean.shape, dev)
-        back = torch.as_tensor(self._back(eps)).to(dtype=td)
-        full_coords = torch.cat([x, mean + eps], dim=1)
-        full_forces = torch.cat([f + (kbt / self.cov) * back, (-kbt / self.cov) * eps], dim=1)
+        x = torch.as_tensor(coords).to(device=dev)
+        f = torch.as_tensor(forces).to(device=dev)
+        full_coords, full_forces = self.augment_device(x, f, kbt, self.new_draw())
         if host:
             return _engine.to_host(full_coords), _engine.to_host(full_forces)
         return full_coords, full_forces
 
     def astype(self, dtype, *args, **kwargs) -> "CondNormal":  # noqa: ARG002
         return self.__class__(cov=self.cov, premap=self.premap, seed=self.seed, dtype=dtype)
+
+
+class NoiseDraw:
+    """One noise realisation of a ``CondNormal`` (see ``CondNormal.new_draw``)."""
+
+    def __init__(self, index: int, noise: Optional[torch.Tensor]) -> None:
+        self.index = int(index)
+        self.noise = noise
+
+
+_AUG_SLAB_BYTES = 512 << 20
+
+
+class AugmentedFrames(_engine.Frames):
+    """Virtual ``(n_frames, n_fg + n_new, 3)`` frame source: the augmented coordinates OR forces of
+    ``CondNormal``, generated slab by slab by ``agf_gauss_augment`` while a kernel consumes them.
+    The augmented arrays of config 5 (2 000 atoms + 200 noise sites, 2 M frames: 53 GB each next
+    to 48 GB each of input) are never materialised."""
+
+    def __init__(self, source, augmenter: Optional[CondNormal] = None, kbt: float = 0.0,
+                 draw: Optional[NoiseDraw] = None, which: str = "coords") -> None:
+        if source is self:  # _engine.Frames(aug) passes an existing instance through
+            return
+        assert augmenter is not None and draw is not None and which in ("coords", "forces")
+        self._src = _engine.Frames(source)
+        self._augmenter, self._kbt, self._draw, self._which = augmenter, float(kbt), draw, which
+        self._dev, self._host = None, None
+        self.n_frames = self._src.n_frames
+        self.n_sites = self._src.n_sites + augmenter.n_new_sites(self._src.n_sites)
+
+    @property
+    def on_host(self) -> bool:
+        return self._src.on_host
+
+    @property
+    def np_dtype(self):
+        return self._augmenter.dtype.type
+
+    def pieces(self, start: int = 0, stop: Optional[int] = None):
+        frame_bytes = self.n_sites * 3 * self._augmenter.dtype.itemsize
+        per = max(4, (_AUG_SLAB_BYTES // frame_bytes) // 4 * 4)
+        for t0, piece in self._src.pieces(start, stop):
+            for a in range(0, piece.shape[0], per):
+                sub = piece[a : a + per]
+                c, f = (sub, None) if self._which == "coords" else (None, sub)
+                oc, of = self._augmenter.augment_device(c, f, self._kbt, self._draw, frame0=t0 + a)
+                yield t0 + a, (oc if self._which == "coords" else of)
+
+    def resident(self) -> torch.Tensor:
+        return torch.cat([p for _, p in self.pieces()])
+
+    def gather(self, frame_indices) -> torch.Tensor:
+        raise NotImplementedError("augmented frames are generated in slabs; gather from a materialised trajectory")
+
+    def prefix(self, n: int) -> torch.Tensor:
+        return torch.cat([p for _, p in self.pieces(0, n)])
 
 
 # drop-in name of the reference's JAX class

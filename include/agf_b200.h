@@ -203,6 +203,27 @@ int agf_gram_feat_ws(const void* coords, const void* forces, int dtype, int64_t 
 
 int agf_symmetrize_batch(double* gram, int32_t n, int32_t batch, void* stream);
 
+/* ------------------------------------------------------------------------------------
+ * Gaussian augmentation for joptgauss_map:  y = A x + eps,  eps ~ N(0, var I).
+ * Replaces  src/aggforce/trajectory/core.py:353-390 (AugmentedTrajectory._augment) and the JAX
+ * augmenter behind it, src/aggforce/trajectory/jaxgausstraj.py:232-284 (sample + autodiff
+ * log-gradients; closed form as in simplegausstraj.py:108-110):
+ *     out_coords = [x ; A x + eps]     out_forces = [F + kbt A^T eps / var ; -kbt eps / var]
+ *   coords, forces   device [n_frames, n_sites, 3], dtype f32 or f64 (either may be NULL when
+ *                    its output is NULL)
+ *   bead_*           CSR rows of A (bead -> sites, weights); site_*: CSR rows of A^T
+ *   noise            device [n_frames, n_cg, 3] standard normals in the array dtype, or NULL to
+ *                    draw them in-kernel: Philox4x32-10 keyed by (seed, frame0 + t, bead, draw),
+ *                    so any slab / rank reproduces the same noise for the same key
+ *   out_coords/out_forces  device [n_frames, n_sites + n_cg, 3], same dtype, or NULL
+ */
+int agf_gauss_augment(const void* coords, const void* forces, int dtype, int64_t n_frames,
+                      int32_t n_sites, const int32_t* bead_ptr, const int32_t* bead_sites,
+                      const double* bead_w, int32_t n_cg, const int32_t* site_ptr,
+                      const int32_t* site_beads, const double* site_w, double var, double kbt,
+                      const void* noise, uint64_t seed, uint32_t draw, int64_t frame0,
+                      void* out_coords, void* out_forces, void* stream);
+
 /* Equality-constraint rows of one bead's feature QP for a few frames,
  * rows[s, c', f] = sum_a cmap[c', a] phi_bead[frames[s], a, f]
  * (src/aggforce/qp/featlinearmap.py:446-450).  frames: device int64 [n_sel];

@@ -215,3 +215,33 @@ def test_condnormal_device_matches_closed_form(topo, data):
     gx, gy = aug2.log_gradient(coords, y)
     assert np.allclose(gy, -(y - oracle.apply_map(coords, cmap.standard_matrix)) / 0.4, atol=1e-4)
     assert np.allclose(gx[:, topo.bead_atoms], -gy, atol=1e-4)
+
+
+def test_joptgauss_slabs_reproduce_the_same_noise(topo, data, monkeypatch):
+    """The augmented arrays are generated slab by slab (never materialised): Philox noise keyed by
+    (seed, global frame, bead, draw) makes the fit independent of the slab size, and the fused
+    kernel agrees with the closed form on device-resident input."""
+    from aggforce_b200 import Trajectory, joptgauss_map
+    from aggforce_b200.trajectory import gausstraj
+
+    coords, forces = data
+    cmap, cons = _cmap(topo), topo.xh_constraints
+    traj = Trajectory(coords=coords, forces=forces)
+    whole = joptgauss_map(traj, cmap, var=0.3, kbt=KBT, constraints=cons, seed=11, l2_regularization=1e2)
+    monkeypatch.setattr(gausstraj, "_AUG_SLAB_BYTES", 185 * 12 * 40)  # 40 frames per slab
+    slabbed = joptgauss_map(traj, cmap, var=0.3, kbt=KBT, constraints=cons, seed=11, l2_regularization=1e2)
+    w0, w1 = whole.tmap.force_map.standard_matrix, slabbed.tmap.force_map.standard_matrix
+    assert rel_fro(w1, w0) < 1e-10
+    other = joptgauss_map(traj, cmap, var=0.3, kbt=KBT, constraints=cons, seed=12, l2_regularization=1e2)
+    assert rel_fro(other.tmap.force_map.standard_matrix, w0) > 1e-6  # a different seed is a different draw
+    # application: same draw for coordinates and forces, device tensors in -> device tensors out
+    dc, df = torch.as_tensor(coords, device="cuda"), torch.as_tensor(forces, device="cuda")
+    out = slabbed(Trajectory(coords=dc, forces=df))
+    assert out.coords.is_cuda and tuple(out.forces.shape) == (len(coords), 10, 3)
+    noise = np.random.default_rng(2).standard_normal((len(coords), 10, 3)).astype(np.float32)
+    aug = gausstraj.CondNormal(cov=0.3, premap=cmap, noise=noise)
+    draw = aug.new_draw()
+    got_c = torch.cat([p for _, p in gausstraj.AugmentedFrames(dc, aug, KBT, draw, "coords").pieces()]).cpu().numpy()
+    got_f = torch.cat([p for _, p in gausstraj.AugmentedFrames(df, aug, KBT, draw, "forces").pieces()]).cpu().numpy()
+    rc, rf = oracle.gauss_augment(coords, forces, cmap.standard_matrix, 0.3, KBT, noise)
+    assert rel_fro(got_c, rc) < 1e-6 and rel_fro(got_f, rf) < 1e-6

@@ -1,0 +1,185 @@
+"""GPU parity of the packed-panel entry points (agf_gram_linear_ws, agf_map_apply_ws,
+agf_gram_feat_ws) called directly through the C ABI: slab processing with deliberately small
+workspaces, narrow / exact / ragged last blocks, the NaN redo path of the GEMM apply, and
+agreement with the workspace-free kernels.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import rel_fro
+
+pytestmark = pytest.mark.gpu
+
+PANEL_BYTES = 24 * 132 * 8
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _groups(rng, n_sites, n_groups):
+    cons = set()
+    free = list(rng.permutation(n_sites))
+    for _ in range(n_groups):
+        k = int(rng.integers(2, 5))
+        if len(free) < k:
+            break
+        cons.add(frozenset(int(free.pop()) for _ in range(k)))
+    return cons
+
+
+@pytest.mark.parametrize("n_sites,n_groups,n_frames", [(129, 0, 21), (140, 5, 64), (256, 0, 9), (300, 20, 77),
+                                                       (640, 60, 33)])
+@pytest.mark.parametrize("slab_chunks", [1, 3, 1000])
+def test_gram_linear_ws_slabs(n_sites, n_groups, n_frames, slab_chunks):
+    from aggforce_b200 import _engine, _lib
+
+    rng = np.random.default_rng(n_sites + n_frames)
+    cons = _groups(rng, n_sites, n_groups)
+    cols = oracle.group_columns(n_sites, cons)
+    n_red = int(cols.max()) + 1
+    forces = rng.normal(0, 40.0, size=(n_frames, n_sites, 3)).astype(np.float32)
+    ptr_, sites = _engine.csr_from_labels(cols, n_red)
+    d_f = torch.as_tensor(forces, device="cuda")
+    d_ptr, d_sites = torch.as_tensor(ptr_, device="cuda"), torch.as_tensor(sites, device="cuda")
+    gram = torch.zeros((n_red, n_red), dtype=torch.float64, device="cuda")
+    n_blocks = (n_red + 127) // 128
+    ws = torch.empty(slab_chunks * n_blocks * PANEL_BYTES, dtype=torch.uint8, device="cuda")
+    _lib.call("agf_gram_linear_ws", _p(d_f), _lib.F32, n_frames, n_sites, _p(d_ptr), _p(d_sites), n_red, _p(gram),
+              _p(ws), C.c_size_t(ws.numel()), _stream())
+    _lib.call("agf_symmetrize", _p(gram), n_red, _stream())
+    ref = oracle.gram_linear(forces, cons)
+    assert rel_fro(gram.cpu().numpy(), ref) < 1e-9
+    # the workspace-free kernel computes the same matrix
+    plain = torch.zeros_like(gram)
+    _lib.call("agf_gram_linear", _p(d_f), _lib.F32, n_frames, n_sites, _p(d_ptr), _p(d_sites), n_red, _p(plain),
+              _stream())
+    _lib.call("agf_symmetrize", _p(plain), n_red, _stream())
+    assert rel_fro(gram.cpu().numpy(), plain.cpu().numpy()) < 1e-13
+
+
+def _apply_ws(x, m, ws_bytes, nan_mode=0, out_dtype=torch.float64, want_sumsq=True):
+    from aggforce_b200 import _engine, _lib
+
+    cm = _engine.CompiledMap(m, keep_zero_columns=nan_mode == 0)
+    assert not cm.sparse
+    d_x = torch.as_tensor(x, device="cuda")
+    out = torch.full((x.shape[0], m.shape[0], 3), 7.0, dtype=out_dtype, device="cuda")
+    sumsq = torch.zeros(1, dtype=torch.float64, device="cuda") if want_sumsq else None
+    flags = torch.zeros(2, dtype=torch.int32, device="cuda")
+    need = int(_lib.lib().agf_map_apply_workspace_bytes(_engine.dtype_code(d_x), x.shape[1], cm.n_ucol, cm.nnz,
+                                                        cm.n_cg, x.shape[0]))
+    ws = None
+    if ws_bytes is not None:
+        ws = torch.empty(need if ws_bytes == "full" else ws_bytes(cm), dtype=torch.uint8, device="cuda")
+    _lib.call("agf_map_apply_ws", _p(d_x), _engine.dtype_code(d_x), x.shape[0], x.shape[1], _p(cm.ucol_ptr),
+              _p(cm.ucol_sites), cm.n_ucol, cm.nnz, _p(cm.umat_t), cm.n_cg, _p(out), _engine.dtype_code(out),
+              _p(sumsq), nan_mode, 1e-6, _p(flags), _p(ws), C.c_size_t(0 if ws is None else ws.numel()), _stream())
+    return out.cpu().numpy(), None if sumsq is None else float(sumsq.item()), flags.cpu().numpy(), need
+
+
+def _one_block_ws(cm):
+    kch = (cm.n_ucol + 23) // 24
+    return 256 + ((cm.n_cg + 127) // 128) * kch * PANEL_BYTES + 3 * kch * PANEL_BYTES
+
+
+@pytest.mark.parametrize("n_cg,n_fg,n_frames", [(70, 90, 33), (65, 700, 128), (129, 260, 300), (300, 700, 419)])
+@pytest.mark.parametrize("in_dtype", [np.float32, np.float64])
+def test_map_apply_ws_gemm(n_cg, n_fg, n_frames, in_dtype):
+    rng = np.random.default_rng(n_cg + n_fg)
+    m = rng.normal(size=(n_cg, n_fg))
+    m[:, n_fg // 3] = m[:, 1]
+    x = rng.normal(0, 30, size=(n_frames, n_fg, 3)).astype(in_dtype)
+    ref = oracle.apply_map(x, m)
+    full, sumsq, flags, need = _apply_ws(x, m, "full")
+    assert need > 0
+    assert rel_fro(full, ref) < 1e-12
+    assert abs(sumsq / float((ref ** 2).sum()) - 1) < 1e-12
+    assert not flags.any()
+    slabbed, sumsq2, _, _ = _apply_ws(x, m, _one_block_ws)  # one 128-frame block per slab
+    assert np.array_equal(slabbed, full)
+    assert abs(sumsq2 / sumsq - 1) < 1e-12
+    fallback, sumsq3, _, _ = _apply_ws(x, m, None)  # no workspace: DFMA fallback kernel
+    assert rel_fro(fallback, ref) < 1e-12 and abs(sumsq3 / sumsq - 1) < 1e-12
+    f32, _, _, _ = _apply_ws(x, m, "full", out_dtype=torch.float32, want_sumsq=False)
+    assert f32.dtype == np.float32 and rel_fro(f32, ref) < 1e-6
+
+
+def test_map_apply_ws_nan_protocol():
+    """NaNs under all-zero map columns are ignored (redo path of the GEMM apply); NaNs under
+    non-zero columns raise the violation flag; plain mode propagates NaN like numpy."""
+    rng = np.random.default_rng(3)
+    n_cg, n_fg, n_frames = 80, 200, 300
+    m = rng.normal(size=(n_cg, n_fg))
+    m[:, 17] = 0.0
+    m[:, 150] = 0.0
+    x = rng.normal(0, 10, size=(n_frames, n_fg, 3)).astype(np.float32)
+    m[:, 60] = 1e-9  # referenced, but its weight mass is below the protocol's atol
+    x[5, 17, 1] = np.nan
+    x[299, 150, :] = np.nan
+    x[10, 60, 2] = np.nan  # read by the pack kernel -> the slab is redone with the masking kernel
+    clean = np.nan_to_num(x, nan=0.0)
+    out, sumsq, flags, _ = _apply_ws(x, m, "full", nan_mode=1)
+    ref = oracle.apply_map(clean, m)
+    assert rel_fro(out, ref) < 1e-12 and flags[0] == 1 and not flags[1]
+    assert abs(sumsq / float((ref ** 2).sum()) - 1) < 1e-12
+    x[7, 3, 0] = np.nan  # under a non-zero column: result would depend on the NaN
+    out, _, flags, _ = _apply_ws(x, m, "full", nan_mode=1)
+    assert flags[0] == 1 and flags[1] == 1
+    plain, _, _, _ = _apply_ws(x, m, "full", nan_mode=0)
+    assert np.isnan(plain[7, :, 0]).all() and np.isnan(plain[5, :, 1]).all()
+    assert np.isfinite(plain[8]).all()
+
+
+@pytest.mark.parametrize("slab_chunks", [1, 2, 1000])
+@pytest.mark.parametrize("drop_last", [True, False])
+def test_gram_feat_ws_matches_fused_kernel_and_oracle(slab_chunks, drop_last):
+    from aggforce_b200 import LinearMap, _engine, _lib
+    from aggforce_b200.qp.featlinearmap import id_feat
+    from aggforce_b200.synth import chignolin_topology, synth_trajectory_host
+
+    topo = chignolin_topology()
+    n_frames, nb, kbt = 21, 5, 0.6955215
+    coords, forces = synth_trajectory_host(topo, n_frames, seed=77)
+    beads = topo.bead_atoms[:3]
+    cmap = LinearMap([[i] for i in beads], n_fg_sites=topo.n_sites)
+    labels = id_feat(None, cmap, topo.xh_constraints, return_ids=True)
+    G = int(labels.max()) + 1
+    n_ch = G - 1 if drop_last else G
+    n_feat = G + nb * n_ch
+    ptr_, sites = _engine.csr_from_labels(labels, G)
+    centers = np.linspace(0.0, 8.0 ** 0.5, nb) ** 2
+    dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device="cuda")  # noqa: E731
+    d_c, d_f = dev(coords, np.float32), dev(forces, np.float32)
+    d_ptr, d_sites = dev(ptr_, np.int32), dev(sites, np.int32)
+    d_bptr, d_bsites = dev(np.arange(len(beads) + 1), np.int32), dev(beads, np.int32)
+    d_bw, d_cent = dev(np.ones(len(beads)), np.float64), dev(centers, np.float64)
+    common = (_p(d_ptr), _p(d_sites), G, n_ch, _p(d_bptr), _p(d_bsites), _p(d_bw), len(beads), _p(d_cent), nb, 1.0,
+              1e-3, kbt)
+    fused = torch.zeros((len(beads), n_feat, n_feat), dtype=torch.float64, device="cuda")
+    _lib.call("agf_gram_feat", _p(d_c), _p(d_f), _lib.F32, n_frames, topo.n_sites, *common, _p(fused), _stream())
+    _lib.call("agf_symmetrize_batch", _p(fused), n_feat, len(beads), _stream())
+    packed = torch.zeros_like(fused)
+    n_blocks = (n_feat + 127) // 128
+    ws = torch.empty(slab_chunks * len(beads) * n_blocks * PANEL_BYTES, dtype=torch.uint8, device="cuda")
+    _lib.call("agf_gram_feat_ws", _p(d_c), _p(d_f), _lib.F32, n_frames, topo.n_sites, *common, _p(packed), _p(ws),
+              C.c_size_t(ws.numel()), _stream())
+    _lib.call("agf_symmetrize_batch", _p(packed), n_feat, len(beads), _stream())
+    a, b = packed.cpu().numpy(), fused.cpu().numpy()
+    assert np.isfinite(a).all()
+    for bead in range(len(beads)):
+        assert rel_fro(a[bead], b[bead]) < 1e-12
+    # id-id block is the linear Gram of the label groups, identical for every bead
+    cons = {frozenset(int(s) for s in np.nonzero(labels == g)[0]) for g in range(G) if (labels == g).sum() > 1}
+    lin = oracle.gram_linear(forces, cons)
+    order = oracle.group_columns(topo.n_sites, cons)
+    perm = np.array([order[np.nonzero(labels == g)[0][0]] for g in range(G)])
+    assert rel_fro(a[0][:G, :G], lin[np.ix_(perm, perm)]) < 1e-9
