@@ -7,12 +7,14 @@ from __future__ import annotations
 from typing import Union
 
 import numpy as np
+import scipy.sparse as ss
+import torch
 
 from .. import _engine
 from ..constraints import Constraints, constraint_lookup_dict, merged_groups
 from ..map import LinearMap, SeperableTMap
 from ..trajectory import ForcesTrajectory
-from .solver import DEFAULT_SOLVER_OPTIONS, SolverOptions, solve
+from .solver import DEFAULT_SOLVER_OPTIONS, SolverOptions, solve, solve_equality_qp_device
 
 
 def reduced_columns(n_sites: int, constraints: Constraints) -> np.ndarray:
@@ -55,6 +57,11 @@ def force_gram(forces, n_sites: int, constraints: Constraints):
     return _engine.to_host(gram), cols
 
 
+# reduced problems at least this large are solved on the device (cuSOLVER through torch.linalg);
+# below it the host solve is faster than the launch + synchronisation overhead
+_DEVICE_SOLVE_MIN = 512
+
+
 def qp_linear_map(
     traj: ForcesTrajectory,
     coord_map: LinearMap,
@@ -73,18 +80,32 @@ def qp_linear_map(
     n_fg = coord_map.n_fg_sites
     if traj.forces.shape[1] != n_fg:
         raise ValueError("coord_map and forces disagree on the number of fine-grained sites.")
-    qp_mat, cols = force_gram(traj.forces, n_fg, constraints)
-    n_red = qp_mat.shape[0]
+    backend = dict(solver_args or {}).get("backend", "exact")
+    cols = reduced_columns(n_fg, constraints)
+    n_red = int(cols.max()) + 1
+    on_device = backend == "exact" and n_red >= _DEVICE_SOLVE_MIN
+    if on_device:
+        qp_mat = _engine.gram_linear(_engine.Frames(traj.forces), cols, n_red)  # stays on the device
+    else:
+        qp_mat, cols = force_gram(traj.forces, n_fg, constraints)
     group_size = np.bincount(cols, minlength=n_red).astype(np.float64)
-    if l2_regularization > 0.0:
-        qp_mat[np.diag_indices(n_red)] += l2_regularization * group_size  # l2 * C'C
+    if l2_regularization > 0.0:  # l2 * C'C
+        if on_device:
+            qp_mat.diagonal().add_(torch.as_tensor(l2_regularization * group_size, device=qp_mat.device))
+        else:
+            qp_mat[np.diag_indices(n_red)] += l2_regularization * group_size
     # A = coord_map @ C : sum the coordinate-map columns of every group
     cmat = np.asarray(coord_map.standard_matrix, dtype=np.float64)
-    a_mat = np.zeros((coord_map.n_cg_sites, n_red))
-    np.add.at(a_mat.T, cols, cmat.T)
-    backend = dict(solver_args or {}).get("backend", "exact")
+    onehot = ss.csr_matrix((np.ones(n_fg), (np.arange(n_fg), cols)), shape=(n_fg, n_red))
+    a_mat = np.asarray((onehot.T @ cmat.T).T)
     if backend == "exact":
-        sol = solve(qp_mat, a_mat, np.eye(coord_map.n_cg_sites), solver_args)
+        sol = None
+        if on_device:
+            sol = solve_equality_qp_device(qp_mat, a_mat, np.eye(coord_map.n_cg_sites))
+            if sol is None:  # not numerically positive definite: host path with its null-space fallback
+                qp_mat = _engine.to_host(qp_mat)
+        if sol is None:
+            sol = solve(qp_mat, a_mat, np.eye(coord_map.n_cg_sites), solver_args)
         if sol is None:
             raise ValueError("Map optimization failed.")
         reduced = sol.T

@@ -66,6 +66,34 @@ def solve_equality_qp(P, A, b) -> Optional[np.ndarray]:
     return x
 
 
+def solve_equality_qp_device(P, A, b) -> Optional[np.ndarray]:
+    """Same closed form on the GPU for large problems: ``P`` is a float64 CUDA tensor
+    (the Gram never leaves the device), one cuSOLVER Cholesky + multi-right-hand-side solves through
+    ``torch.linalg``.  Returns ``None`` when ``P`` or the Schur complement is not numerically
+    positive definite -- the caller then falls back to :func:`solve_equality_qp` on the host."""
+    import torch
+
+    a = torch.as_tensor(np.asarray(A, dtype=np.float64), device=P.device)
+    rhs = torch.as_tensor(np.asarray(b, dtype=np.float64), device=P.device)
+    vec = rhs.ndim == 1
+    if vec:
+        rhs = rhs[:, None]
+    chol, info = torch.linalg.cholesky_ex(P)
+    if int(info.item()) != 0:
+        return None
+    pia = torch.cholesky_solve(a.T.contiguous(), chol)  # P^-1 A'
+    schur = a @ pia
+    chol_s, info_s = torch.linalg.cholesky_ex(schur)
+    if int(info_s.item()) != 0:
+        return None
+    x = pia @ torch.cholesky_solve(rhs, chol_s)
+    resid = float((a @ x - rhs).abs().max().item()) if x.numel() else 0.0
+    if not bool(torch.isfinite(x).all().item()) or resid > 1e-6 * max(1.0, float(rhs.abs().max().item())):
+        return None
+    out = x.cpu().numpy()
+    return out[:, 0] if vec else out
+
+
 def solve(P, A, b, solver_args: Optional[SolverOptions] = None) -> Optional[np.ndarray]:
     """Dispatch: exact solve by default, ``qpsolvers`` on request (vector ``b`` only)."""
     opts = dict(solver_args or {})

@@ -183,3 +183,29 @@ def test_gram_feat_ws_matches_fused_kernel_and_oracle(slab_chunks, drop_last):
     order = oracle.group_columns(topo.n_sites, cons)
     perm = np.array([order[np.nonzero(labels == g)[0][0]] for g in range(G)])
     assert rel_fro(a[0][:G, :G], lin[np.ix_(perm, perm)]) < 1e-9
+
+
+def test_large_fit_uses_device_solve_and_matches_oracle():
+    """n_red >= 512: Gram stays on the device, exact solve through cuSOLVER; weights vs the oracle's
+    host solve of the same problem (<= 1e-6 relative), and the singular case falls back to the host."""
+    from aggforce_b200 import LinearMap, project_forces
+    from aggforce_b200.synth import protein_like_topology, synth_trajectory_host
+
+    topo = protein_like_topology(120)  # 1200 atoms -> n_red 624
+    coords, forces = synth_trajectory_host(topo, 600, seed=4)
+    cmap = LinearMap([[i] for i in topo.bead_atoms], n_fg_sites=topo.n_sites)
+    cons = topo.xh_constraints
+    res = project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds=cons, l2_regularization=1e2)
+    w = res["tmap"].force_map.standard_matrix
+    ref = oracle.qp_linear_weights(forces, cmap.standard_matrix, cons, 1e2)
+    assert rel_fro(w, ref) < 1e-6
+    assert rel_fro(res["mapped_forces"], oracle.apply_map(forces, ref)) < 1e-6
+    # 3 * 40 rows < n_red and no regularisation: P is singular -> host null-space solve
+    res0 = project_forces(coords=coords[:40], forces=forces[:40], coord_map=cmap, constrained_inds=cons)
+    w0 = res0["tmap"].force_map.standard_matrix
+    assert np.isfinite(w0).all()
+    assert np.abs(w0[:, topo.bead_atoms] @ np.eye(len(topo.bead_atoms)) - 0).shape == (len(topo.bead_atoms),) * 2
+    ref0 = oracle.qp_linear_weights(forces[:40], cmap.standard_matrix, cons, 0.0)
+    f0 = forces[:40]
+    assert abs(np.mean(oracle.apply_map(f0, w0) ** 2) - np.mean(oracle.apply_map(f0, ref0) ** 2)) < 1e-6 * max(
+        1.0, np.mean(oracle.apply_map(f0, ref0) ** 2))

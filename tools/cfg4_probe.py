@@ -62,3 +62,17 @@ print("apply parity rel fro", np.linalg.norm(out - refo) / np.linalg.norm(refo))
 cmap = agf.LinearMap([[i] for i in topo.bead_atoms], n_fg_sites=topo.n_sites)
 ms = timeit(lambda: cmap(coords))
 print(f"slice apply: {ms:.3f} ms  {T/ms*1e3:.3e} frames/s")
+
+# whole path at this shape: constraints + Gram + host QP (n_red 2600, 500 beads) + both applications
+t0 = time.perf_counter()
+res = agf.project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds="auto", l2_regularization=1e3)
+torch.cuda.synchronize(); dt = time.perf_counter() - t0
+print(f"project_forces end to end: {dt*1e3:.0f} ms ({T/dt:.3e} frames/s)")
+pr = cProfile.Profile(); pr.enable()
+res = agf.project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds=cons, l2_regularization=1e3)
+torch.cuda.synchronize(); pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+sub_w = oracle.qp_linear_weights(forces.cpu().numpy(), cmap.standard_matrix, cons, 1e3) if T <= 4096 else None
+if sub_w is not None:
+    w = res["tmap"].force_map.standard_matrix
+    print("weights rel err vs oracle:", np.linalg.norm(w - sub_w) / np.linalg.norm(sub_w))
