@@ -6,7 +6,7 @@ featurised and Gaussian maps under ``aggforce_b200.qp``) and runs every per-fram
 hand-written sm_100a kernels (``csrc/``) behind the C ABI in ``include/agf_b200.h``.
 """
 from .trajectory import Trajectory  # noqa: F401
-from .agg import project_forces  # noqa: F401
+from .agg import project_forces, project_forces_grid_cv  # noqa: F401
 from .constraints import guess_pairwise_constraints  # noqa: F401
 from .qp import qp_linear_map, constraint_aware_uni_map, joptgauss_map  # noqa: F401
 from .map import LinearMap  # noqa: F401

@@ -9,7 +9,9 @@ all-reduces its accumulators and the residual is the global mean.
 """
 from __future__ import annotations
 
-from typing import Any, Callable, Dict, Final, Union
+from gc import collect
+from itertools import product
+from typing import Any, Callable, Collection, Dict, Final, List, Mapping, NamedTuple, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -110,6 +112,119 @@ def project_forces(
         RESIDUAL_KNAME: residual,
         CONSTRAINTS_KNAME: constrained_inds,
     }
+
+
+def project_forces_grid_cv(
+    cv_arg_dict: Mapping[str, List[Any]],
+    coords,
+    forces,
+    n_folds: int = 5,
+    rng: Optional[np.random.Generator] = None,
+    **kwargs,
+) -> Dict[str, Dict[Any, Any]]:
+    """K-fold cross validation of ``project_forces`` over a grid of arguments (reference
+    ``agg.py:142-235``): for every parameter combination, ``scores`` holds the hold-out
+    ``force_smoothness`` averaged over folds, ``sds`` its sample standard deviation and ``n_runs``
+    the number of folds whose optimisation succeeded.  ``rng`` (extension) seeds the fold
+    shuffle, which the reference leaves unseeded (``agg.py:188``).
+
+    Fast path when the method is ``qp_linear_map``, the constraints are given and the
+    grid only varies ``l2_regularization``: ONE pass over the data accumulates a Gram per fold
+    (kernel (a)); the training Gram of a fold is the total minus its own, and the hold-out score
+    is ``trace(W G_fold W') / (3 T_fold n_cg)`` -- no further pass over the frames for any grid
+    point.  Everything else runs ``project_forces`` per fold and grid point as the reference does
+    (it calls ``tmap.from_arrays``, which no TMap defines; ``map_arrays`` is used here).
+    """
+    n_frames = forces.shape[0]
+    frames = np.arange(n_frames)
+    (np.random.default_rng() if rng is None else rng).shuffle(frames)
+    folds = np.array_split(frames, n_folds, axis=0)
+    grid = process_cvargs(cv_arg_dict)
+    results: Dict[str, Dict[Any, Any]] = {SCORES_KNAME: {}, SDS_KNAME: {}, NRUNS_KNAME: {}}
+
+    fast = (kwargs.get("method", qp_linear_map) is qp_linear_map and set(cv_arg_dict) <= {"l2_regularization"}
+            and not isinstance(kwargs.get("constrained_inds", PROJECT_FORCES_CNSTR_AUTO), str)
+            and dict(kwargs.get("solver_args") or {}).get("backend", "exact") == "exact"
+            and isinstance(kwargs.get("coord_map"), LinearMap) and not _engine.sharded())
+    fold_scores: Dict[Any, List[float]] = {label: [] for label, _ in grid}
+    if fast:
+        from .qp.qplinear import reduced_columns
+        from .qp.solver import solve_equality_qp
+
+        coord_map, cons = kwargs["coord_map"], kwargs.get("constrained_inds") or set()
+        n_fg, n_cg = coord_map.n_fg_sites, coord_map.n_cg_sites
+        cols = reduced_columns(n_fg, cons)
+        n_red = int(cols.max()) + 1
+        src = _engine.Frames(forces)
+        grams = [_engine.to_host(_engine.gram_linear(_engine.Frames(src.gather(np.sort(idx))), cols, n_red))
+                 for idx in folds]
+        total = np.sum(grams, axis=0)
+        group_size = np.bincount(cols, minlength=n_red).astype(np.float64)
+        cmat = np.asarray(coord_map.standard_matrix, dtype=np.float64)
+        a_mat = np.zeros((n_cg, n_red))
+        np.add.at(a_mat.T, cols, cmat.T)
+        for label, args in grid:
+            l2 = float(args.get("l2_regularization", kwargs.get("l2_regularization", 0.0)))
+            for fold, g_val in zip(folds, grams):
+                p_train = total - g_val
+                if l2 > 0.0:
+                    p_train[np.diag_indices(n_red)] += l2 * group_size
+                sol = solve_equality_qp(p_train, a_mat, np.eye(n_cg))
+                if sol is None:
+                    print("Map optimization failed.")
+                    continue
+                w = sol.T  # (n_cg, n_red) reduced weights
+                fold_scores[label].append(float(np.einsum("cr,rs,cs->", w, g_val, w) / (3.0 * len(fold) * n_cg)))
+    else:
+        is_dev = isinstance(forces, torch.Tensor)
+        take = (lambda arr, idx: arr[torch.as_tensor(idx, device=arr.device)]) if is_dev else (lambda arr, idx: arr[idx])
+        outside = [np.concatenate([f for j, f in enumerate(folds) if j != i]) for i in range(len(folds))]
+        for label, args in grid:
+            combined = dict(kwargs, **args)
+            for train_inds, val_inds in zip(outside, folds):
+                try:
+                    tmap = project_forces(coords=None if coords is None else take(coords, train_inds),
+                                          forces=take(forces, train_inds), **combined)[TMAP_KNAME]
+                    _, val_forces = tmap.map_arrays(None if coords is None else take(coords, val_inds),
+                                                    take(forces, val_inds))
+                    fold_scores[label].append(force_smoothness(val_forces))
+                    del tmap
+                except ValueError as e:  # failed optimisation: the fold is skipped, as in the reference
+                    print(e)
+                collect()
+    for label, _ in grid:
+        results[SCORES_KNAME][label] = mean(fold_scores[label])
+        results[SDS_KNAME][label] = sample_sd(fold_scores[label])
+        results[NRUNS_KNAME][label] = len(fold_scores[label])
+    return results
+
+
+def process_cvargs(arg_dict: Mapping[str, List[Any]]) -> List[Tuple[Any, Dict[str, Any]]]:
+    """Grid of parameter combinations: ``[(CVArgs(key1=v, key2=w, ...), {key1: v, key2: w, ...}), ...]``
+    for every element of the product of the value lists (reference ``agg.py:238-288``)."""
+    names = list(arg_dict.keys())
+    cv_args = NamedTuple("CVArgs", [(n, Any) for n in names])  # type: ignore[misc]
+    out = []
+    for values in product(*[arg_dict[n] for n in names]):
+        key = cv_args(**dict(zip(names, values)))
+        out.append((key, {n: getattr(key, n) for n in names}))
+    return out
+
+
+def mean(s: Collection[float]) -> Union[float, None]:
+    """Arithmetic mean, ``None`` for an empty collection (reference ``agg.py:300-318``)."""
+    return None if len(s) == 0 else sum(s) / len(s)
+
+
+def sample_sd(s: Collection[float]) -> Union[float, None]:
+    """Sample standard deviation, ``None`` for an empty collection (reference ``agg.py:321-343``;
+    a single element divides by zero there -- NaN here)."""
+    m = mean(s)
+    if m is None:
+        return None
+    if len(s) < 2:
+        return float("nan")
+    return (sum((o - m) ** 2 for o in s) / (len(s) - 1)) ** 0.5
 
 
 class _Shared:

@@ -20,10 +20,15 @@
 #include "frame_pipe.cuh"
 #include "panel.cuh"
 
+#ifndef AGF_TRI_MMA_WARPS
+#define AGF_TRI_MMA_WARPS 8
+#endif
+
 namespace agf {
 
 constexpr int kGramThreads = 256;
 constexpr int kGramWarps = 8;
+constexpr int kTriMmaWarps = AGF_TRI_MMA_WARPS;  // MMA warps of the single-block kernel (tile plans below)
 constexpr int kBlockCols = 128;  // reduced columns per block
 constexpr int kStride = 132;     // panel row stride in doubles (132 % 16 == 4: conflict free)
 
@@ -46,7 +51,7 @@ struct GramParams {
 // the contiguous run [tile_begin(w), tile_begin(w+1)) -- balanced to within one tile.
 __host__ __device__ constexpr int tri_tiles(int nt) { return nt * (nt + 1) / 2; }
 __host__ __device__ constexpr int tile_begin(int nt, int w) {
-  const int total = tri_tiles(nt), base = total / kGramWarps, extra = total % kGramWarps;
+  const int total = tri_tiles(nt), base = total / kTriMmaWarps, extra = total % kTriMmaWarps;
   return w * base + (w < extra ? w : extra);
 }
 // Tile order: two tile rows at a time, column by column -- (r,c), (r+1,c), (r,c+1), (r+1,c+1) ... --
@@ -69,7 +74,7 @@ __host__ __device__ constexpr int tile_rc(int nt, int t, bool want_row) {
 }
 __host__ __device__ constexpr int tile_row(int nt, int t) { return tile_rc(nt, t, true); }
 __host__ __device__ constexpr int tile_col(int nt, int t) { return tile_rc(nt, t, false); }
-constexpr int kMaxTriSlots = (tri_tiles(16) + kGramWarps - 1) / kGramWarps;  // 17
+constexpr int kMaxTriSlots = (tri_tiles(16) + kTriMmaWarps - 1) / kTriMmaWarps;
 
 template <int NT, int W, int T, int END>
 struct TriTiles {
@@ -118,7 +123,15 @@ __device__ __forceinline__ void tri_sweep_warp(int warp, const double* lane_pane
     case 4: tri_sweep<NT, 4, KSTEPS>(lane_panel, acc); break;
     case 5: tri_sweep<NT, 5, KSTEPS>(lane_panel, acc); break;
     case 6: tri_sweep<NT, 6, KSTEPS>(lane_panel, acc); break;
-    default: tri_sweep<NT, 7, KSTEPS>(lane_panel, acc); break;
+    case 7: tri_sweep<NT, 7, KSTEPS>(lane_panel, acc); break;
+    case 8: tri_sweep<NT, 8, KSTEPS>(lane_panel, acc); break;
+    case 9: tri_sweep<NT, 9, KSTEPS>(lane_panel, acc); break;
+    case 10: tri_sweep<NT, 10, KSTEPS>(lane_panel, acc); break;
+    case 11: tri_sweep<NT, 11, KSTEPS>(lane_panel, acc); break;
+    case 12: tri_sweep<NT, 12, KSTEPS>(lane_panel, acc); break;
+    case 13: tri_sweep<NT, 13, KSTEPS>(lane_panel, acc); break;
+    case 14: tri_sweep<NT, 14, KSTEPS>(lane_panel, acc); break;
+    default: tri_sweep<NT, kTriMmaWarps - 1, KSTEPS>(lane_panel, acc); break;
   }
 }
 
@@ -188,7 +201,7 @@ __device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
 //   raw_full[s]   : TMA bulk copy of a chunk landed            (tx-count mbarrier)
 //   panel_full[b] : fill warps finished panel b                (1 arrival, after a named barrier)
 //   panel_empty[b]: all 8 MMA warps finished sweeping panel b  (8 arrivals)
-constexpr int kMmaWarps = 8;
+constexpr int kMmaWarps = kTriMmaWarps;
 constexpr int kFillWarps = 8;
 constexpr int kTriThreads = (kMmaWarps + kFillWarps) * 32;
 constexpr int kFillThreads = kFillWarps * 32;
@@ -400,7 +413,15 @@ __global__ void __launch_bounds__(kTriThreads, 1) gram_tri_kernel(const __grid_c
     case 4: tri_store<NT, 4>(acc, p.gram, p.n_red, g, q); break;
     case 5: tri_store<NT, 5>(acc, p.gram, p.n_red, g, q); break;
     case 6: tri_store<NT, 6>(acc, p.gram, p.n_red, g, q); break;
-    default: tri_store<NT, 7>(acc, p.gram, p.n_red, g, q); break;
+    case 7: tri_store<NT, 7>(acc, p.gram, p.n_red, g, q); break;
+    case 8: tri_store<NT, 8>(acc, p.gram, p.n_red, g, q); break;
+    case 9: tri_store<NT, 9>(acc, p.gram, p.n_red, g, q); break;
+    case 10: tri_store<NT, 10>(acc, p.gram, p.n_red, g, q); break;
+    case 11: tri_store<NT, 11>(acc, p.gram, p.n_red, g, q); break;
+    case 12: tri_store<NT, 12>(acc, p.gram, p.n_red, g, q); break;
+    case 13: tri_store<NT, 13>(acc, p.gram, p.n_red, g, q); break;
+    case 14: tri_store<NT, 14>(acc, p.gram, p.n_red, g, q); break;
+    default: tri_store<NT, kTriMmaWarps - 1>(acc, p.gram, p.n_red, g, q); break;
   }
 }
 

@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=1_000_000, help="frames per GPU")
-    ap.add_argument("--cpu-frames", type=int, default=2000, help="frames of the CPU sample")
+    ap.add_argument("--cpu-frames", type=int, default=4000, help="frames of the CPU sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()

@@ -307,3 +307,39 @@ def test_full_size_properties_1m_frames(topo):
     sub = slice(123_456, 123_456 + 2_000)
     assert rel_fro(mf[sub].cpu().numpy(), oracle.apply_map(forces[sub].cpu().numpy(), w)) < MAP_TOL
     assert rel_fro(LinearMap(3.0 * w)(forces[sub]).cpu().numpy(), 3.0 * mf[sub].cpu().numpy()) < 1e-12
+
+
+# ------------------------------------------------------------------ grid cross-validation
+def test_grid_cv_one_pass_grams_match_per_fold_fits(topo):
+    """Fast path (one Gram per fold, train = total - fold, hold-out score from the fold's Gram)
+    against the reference's procedure (fit on the training frames, apply to the hold-out frames),
+    and against a numpy restatement with the oracle's solver."""
+    from aggforce_b200 import project_forces_grid_cv, qp_linear_map
+    from aggforce_b200.synth import synth_trajectory_host
+
+    coords, forces = synth_trajectory_host(topo, 600, seed=31)
+    cmap, cons = _cmap(topo), topo.xh_constraints
+    grid = {"l2_regularization": [1.0, 1e3]}
+    fast = project_forces_grid_cv(grid, coords, forces, n_folds=4, rng=np.random.default_rng(5), coord_map=cmap,
+                                  constrained_inds=cons)
+    wrapped = lambda **kw: qp_linear_map(**kw)  # noqa: E731  (not `is qp_linear_map` -> generic path)
+    slow = project_forces_grid_cv(grid, coords, forces, n_folds=4, rng=np.random.default_rng(5), coord_map=cmap,
+                                  constrained_inds=cons, method=wrapped)
+    assert list(fast["scores"]) == list(slow["scores"]) and len(fast["scores"]) == 2
+    for key in fast["scores"]:
+        assert key._fields == ("l2_regularization",)
+        assert fast["n_runs"][key] == slow["n_runs"][key] == 4
+        assert abs(fast["scores"][key] / slow["scores"][key] - 1) < 1e-9
+        assert abs(fast["sds"][key] / slow["sds"][key] - 1) < 1e-6
+    # numpy restatement of one grid point
+    frames = np.arange(600)
+    np.random.default_rng(5).shuffle(frames)
+    folds = np.array_split(frames, 4)
+    cm = _slice_matrix(topo)
+    scores = []
+    for i, val in enumerate(folds):
+        train = np.concatenate([f for j, f in enumerate(folds) if j != i])
+        w = oracle.qp_linear_weights(forces[train], cm, cons, 1e3)
+        scores.append(np.mean(oracle.apply_map(forces[val], w) ** 2))
+    key = [k for k in fast["scores"] if k.l2_regularization == 1e3][0]
+    assert abs(fast["scores"][key] / np.mean(scores) - 1) < 1e-6

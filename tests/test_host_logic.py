@@ -259,3 +259,15 @@ def test_fusable_featurizer_recognition():
     assert _fusable(lambda p, c, k: None) is None
     assert _fusable(Multifeaturize([id_feat, id_feat])) is None
     assert _fusable(Curry(gb_feat, 8.0)) is None  # positional args are not introspected
+
+
+def test_cv_helpers_match_reference_semantics():
+    from aggforce_b200.agg import mean, process_cvargs, sample_sd
+
+    grid = process_cvargs({"l2_regularization": [1.0, 10.0], "n_folds_unused": ["a"]})
+    assert [g[1] for g in grid] == [{"l2_regularization": 1.0, "n_folds_unused": "a"},
+                                    {"l2_regularization": 10.0, "n_folds_unused": "a"}]
+    assert grid[0][0]._fields == ("l2_regularization", "n_folds_unused") and grid[1][0].l2_regularization == 10.0
+    assert mean([]) is None and sample_sd([]) is None
+    assert mean([1.0, 2.0, 6.0]) == 3.0
+    assert abs(sample_sd([1.0, 2.0, 6.0]) - np.std([1.0, 2.0, 6.0], ddof=1)) < 1e-15
