@@ -536,13 +536,16 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
         raise ValueError("xyz and cross_xyz must have the same number of frames")
     n, n_o = frames.n_sites, (frames.n_sites if other is None else other.n_sites)
     t_local = frames.n_frames
-    t_total = global_count(t_local)
     empty = (np.zeros((0, 2), dtype=np.int64), np.zeros(0))
-    if t_total == 0 or t_local == 0 and not sharded():
+    # Under frame sharding with a small pair matrix the global frame count travels with the screening
+    # statistics (one MAX all-reduce of [M2 | per-rank counts], no separate count round trip).
+    fused = sharded() and n * n_o <= (1 << 22) and _dist().get_backend(_Sharding.group) == "nccl"
+    t_total = None if fused else global_count(t_local)
+    if not fused and (t_total == 0 or t_local == 0 and not sharded()):
         return empty
     # a pair can only be a constraint if  M2_total <= thr^2 * T  (var = M2 / T < thr^2); partial
     # M2 never exceeds the total, so anything above the (slightly widened) bound is pruned for good.
-    bound = float(threshold) ** 2 * t_total * (1.0 + 1e-6) + 1e-300
+    bound = None if fused else float(threshold) ** 2 * t_total * (1.0 + 1e-6) + 1e-300
     dev = device()
 
     def other_piece(piece_t0: int, count: int) -> Optional[torch.Tensor]:
@@ -559,12 +562,27 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
         if o0 is not None and o0.dtype != x0.dtype:
             o0 = o0.to(x0.dtype)
         _lib.call("agf_pair_screen", ptr(x0), ptr(o0), dtype_code(x0), n0, n, n_o, ptr(m2), stream_ptr())
-        alive = (m2 <= bound).to(torch.uint8)
+    if fused:
+        dist = _dist()
+        world, rank = dist.get_world_size(_Sharding.group), dist.get_rank(_Sharding.group)
+        if n0 == 0:  # a rank without frames constrains nothing
+            m2 = torch.zeros_like(m2)
+            if other is None:
+                m2 = torch.where(torch.triu(torch.ones_like(m2), diagonal=1) > 0, m2, torch.full_like(m2, float("inf")))
+        counts = torch.zeros(world, dtype=torch.float64, device=dev)
+        counts[rank] = float(t_local)
+        buf = torch.cat([m2.reshape(-1), counts])
+        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=_Sharding.group)
+        bound_dev = float(threshold) ** 2 * buf[-world:].sum() * (1.0 + 1e-6) + 1e-300
+        alive = buf[:-world].reshape(n_o, n) <= bound_dev
     else:
-        alive = torch.ones((n_o, n), dtype=torch.uint8, device=dev)
-        if other is None:
-            alive = torch.triu(alive, diagonal=1)
-    allreduce_min_(alive)
+        if n0 > 0:
+            alive = (m2 <= bound).to(torch.uint8)
+        else:
+            alive = torch.ones((n_o, n), dtype=torch.uint8, device=dev)
+            if other is None:
+                alive = torch.triu(alive, diagonal=1)
+        allreduce_min_(alive)
     pairs = torch.nonzero(alive).to(torch.int32).contiguous()  # [P, 2] = (i over other, j over xyz)
     del m2, alive
     n_pairs = int(pairs.shape[0])
@@ -607,13 +625,19 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
         m2_local = acc[:, 1] - acc[:, 0] ** 2 / t_local
     else:
         mean, m2_local = torch.zeros_like(shift), torch.zeros_like(shift)
+    # the surviving pair list rides along (as float64) so that ONE synchronising read returns everything
     rec = torch.cat([torch.tensor([float(t_local)], dtype=torch.float64, device=dev), mean, m2_local])
+    pairs_f = pairs.to(torch.float64).reshape(-1)
     if sharded():
         dist = _dist()
         outs = [torch.empty_like(rec) for _ in range(dist.get_world_size(_Sharding.group))]
         dist.all_gather(outs, rec, group=_Sharding.group)
-        parts = list(to_host(torch.stack(outs)))
+        flat = to_host(torch.cat([torch.stack(outs).reshape(-1), pairs_f]))
+        n_rec = rec.numel()
+        parts = [flat[i * n_rec : (i + 1) * n_rec] for i in range(len(outs))]
+        pairs_host = flat[len(outs) * n_rec :]
     else:
-        parts = [to_host(rec)]
+        flat = to_host(torch.cat([rec, pairs_f]))
+        parts, pairs_host = [flat[: rec.numel()]], flat[rec.numel() :]
     sd = merge_moments(parts, n_pairs)
-    return to_host(pairs).astype(np.int64), sd
+    return pairs_host.reshape(-1, 2).astype(np.int64), sd

@@ -176,6 +176,7 @@ def main() -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     T = args.frames
     topo = chignolin_topology()
@@ -199,7 +200,7 @@ def main() -> None:
     def timed(fn, steps, warmup, sample_clocks=False):
         # the sampler runs across warm-up AND the timed steps: the timed region alone lasts tens of
         # milliseconds, less than one nvidia-smi sampling period
-        sampler = ClockSampler(local) if sample_clocks else None
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None  # one nvidia-smi poller per box
         for _ in range(warmup):
             fn()
         barrier()
