@@ -131,6 +131,38 @@ def workspace(nbytes: int) -> torch.Tensor:
     return buf
 
 
+# --------------------------------------------------------------------------------------
+# deferred launches: work that does not depend on a fit's result (the coordinate-map application
+# of project_forces) is enqueued right after the fit's last kernel, so the GPU runs it while the
+# host solves the QP instead of idling
+# --------------------------------------------------------------------------------------
+_DEFERRED: list = []
+
+
+def defer(fn) -> None:
+    _DEFERRED.append(fn)
+
+
+def run_deferred() -> None:
+    while _DEFERRED:
+        _DEFERRED.pop(0)()
+
+
+def clear_deferred() -> None:
+    _DEFERRED.clear()
+
+
+def to_host_overlapped(t: torch.Tensor) -> np.ndarray:
+    """Like :func:`to_host`, but deferred launches are enqueued behind ``t``'s producer and the
+    host only waits for the copy of ``t`` (dedicated D2H stream)."""
+    if not _DEFERRED:
+        return to_host(t)
+    host = start_d2h(t)
+    run_deferred()
+    finish_d2h()
+    return host.numpy()
+
+
 def dev_i32(values: Sequence[int]) -> torch.Tensor:
     return _dev_cached(np.ascontiguousarray(values, dtype=np.int32))
 

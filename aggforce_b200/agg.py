@@ -75,17 +75,34 @@ def project_forces(
     coords_in, forces_in = _engine.Frames(coords), _engine.Frames(forces)
     if auto:
         constrained_inds = guess_pairwise_constraints(coords_in)
-    traj_map: TMap = method(
-        traj=Trajectory(coords=_Shared(coords, coords_in), forces=_Shared(forces, forces_in)),
-        coord_map=coord_map,
-        constraints=constrained_inds,
-        **kwargs,
-    )
+    # The coordinate map does not depend on the fit: its application is deferred to the moment the
+    # fit has enqueued its last kernel (or launched right here when the fit never asks), so it runs
+    # on the GPU while the host builds / solves the map.
+    early: Dict[str, Any] = {}
+    if isinstance(coord_map, LinearMap) and coords is not None:
+        if method is qp_linear_map:  # [Gram][coordinate map] | host QP
+            _engine.defer(lambda: early.update(launch=coord_map._launch(coords_in)))
+        else:  # runs while the host (or a later kernel of the method) builds the force map
+            early["launch"] = coord_map._launch(coords_in)
+    try:
+        traj_map: TMap = method(
+            traj=Trajectory(coords=_Shared(coords, coords_in), forces=_Shared(forces, forces_in)),
+            coord_map=coord_map,
+            constraints=constrained_inds,
+            **kwargs,
+        )
+    except BaseException:
+        _engine.clear_deferred()
+        raise
     if (isinstance(traj_map, SeperableTMap) and isinstance(traj_map.force_map, LinearMap)
             and isinstance(traj_map.coord_map, LinearMap)):
         # both applications are enqueued back to back; one read returns NaN flags + residual sum
         cm, fm = traj_map.coord_map, traj_map.force_map
-        fc, oc, sc = cm._launch(coords_in)
+        if cm is not coord_map:
+            _engine.clear_deferred()
+            early.clear()
+        _engine.run_deferred()
+        fc, oc, sc = early["launch"] if "launch" in early else cm._launch(coords_in)
         host_c = _engine.start_d2h(oc) if fc.on_host else None  # downloads overlap the force upload
         ff, of, sf = fm._launch(forces_in, want_sumsq=True)
         host_f = _engine.start_d2h(of) if ff.on_host else None
@@ -102,6 +119,7 @@ def project_forces(
         mapped_forces = fm._finish(ff, of, status[3:6], host_f)
         residual = float(status[5] / status[6])
     else:
+        _engine.clear_deferred()
         mapped = traj_map(t)
         mapped_coords, mapped_forces = mapped.coords, mapped.forces
         residual = force_smoothness(mapped_forces)

@@ -54,7 +54,7 @@ def force_gram(forces, n_sites: int, constraints: Constraints):
     cols = reduced_columns(n_sites, constraints)
     n_red = int(cols.max()) + 1
     gram = _engine.gram_linear(_engine.Frames(forces), cols, n_red)
-    return _engine.to_host(gram), cols
+    return _engine.to_host_overlapped(gram), cols
 
 
 # reduced problems at least this large are solved on the device (cuSOLVER through torch.linalg);
@@ -86,6 +86,7 @@ def qp_linear_map(
     on_device = backend == "exact" and n_red >= _DEVICE_SOLVE_MIN
     if on_device:
         qp_mat = _engine.gram_linear(_engine.Frames(traj.forces), cols, n_red)  # stays on the device
+        _engine.run_deferred()
     else:
         qp_mat, cols = force_gram(traj.forces, n_fg, constraints)
     group_size = np.bincount(cols, minlength=n_red).astype(np.float64)
