@@ -497,7 +497,7 @@ extern "C" size_t agf_gram_feat_workspace_bytes(int32_t n_groups, int32_t n_chan
   const int64_t n_feat = (int64_t)n_groups + (int64_t)nb * n_channels;
   const int64_t per_chunk = (int64_t)n_cg * panel_blocks((int)n_feat) * kPanelBytes;
   const int64_t chunks = (n_frames + kPanelKF - 1) / kPanelKF;
-  const int64_t cap = (int64_t)2 << 30;  // slabs of at most 2 GiB
+  const int64_t cap = (int64_t)8 << 30;  // slabs of at most 8 GiB
   int64_t want = chunks * per_chunk;
   if (want > cap) want = cap / per_chunk * per_chunk;
   if (want < per_chunk) want = per_chunk;

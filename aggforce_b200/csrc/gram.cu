@@ -20,6 +20,9 @@
 #include "frame_pipe.cuh"
 #include "panel.cuh"
 
+#ifndef AGF_SYRK_WAVES
+#define AGF_SYRK_WAVES 12
+#endif
 #ifndef AGF_TRI_MMA_WARPS
 #define AGF_TRI_MMA_WARPS 8
 #endif
@@ -620,10 +623,13 @@ int launch_panel_syrk(const double* ws, int64_t n_chunks, int32_t n, int32_t bat
   p.n_pairs = p.n_blocks * (p.n_blocks + 1) / 2;
   p.batch = batch;
   p.gram = gram;
-  // enough CTAs for ~4 waves so that the cheap (diagonal / narrow) items at the end of every
-  // (k-split, batch) group fill in behind the full ones
+  // Work items differ in cost (full / diagonal 17/32 / narrow) and one CTA occupies an SM, so the
+  // launch ends with a tail of about one full item: aim for AGF_SYRK_WAVES waves of CTAs (tail
+  // <= 1/waves of the launch) while keeping >= 32 chunks per CTA to amortise the 16 K-atomic epilogue.
   const int64_t items = (int64_t)p.n_pairs * batch;
-  int64_t ks = (4LL * sm_count() + items - 1) / items;
+  int64_t ks = ((int64_t)AGF_SYRK_WAVES * sm_count() + items - 1) / items;
+  if (ks < n_chunks / 128) ks = n_chunks / 128;  // long slabs: CTAs of ~128 chunks (~0.45 ms) bound the tail
+  if (ks > n_chunks / 32) ks = n_chunks / 32;
   if (ks > n_chunks) ks = n_chunks;
   if (ks < 1) ks = 1;
   p.k_splits = (int32_t)ks;
@@ -742,7 +748,7 @@ extern "C" size_t agf_gram_linear_workspace_bytes(int32_t n_sites, int32_t n_red
   const int64_t n_blocks = (n_red + kBlockCols - 1) / kBlockCols;
   const int64_t per_chunk = n_blocks * kWsPanel * (int64_t)sizeof(double);
   const int64_t chunks = (n_frames + kWsKF - 1) / kWsKF;
-  const int64_t cap = (int64_t)1 << 30;  // slabs of at most 1 GiB
+  const int64_t cap = (int64_t)4 << 30;  // slabs of at most 4 GiB
   int64_t want = chunks * per_chunk;
   if (want > cap) want = cap / per_chunk * per_chunk;
   if (want < per_chunk) want = per_chunk;
