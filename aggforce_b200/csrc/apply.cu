@@ -140,8 +140,13 @@ __device__ __forceinline__ void group_value3(const TI* __restrict__ fr, const in
   }
 }
 
-template <typename TI, typename TO, int NT>
-__global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(const __grid_constant__ DenseSmallParams p) {
+// SPLIT = warps per octet: with SPLIT == 2 the two warps of a team each contract half of the unique
+// columns and the partial accumulators are combined through a double-buffered shared-memory
+// scratch (one 64-thread named barrier per octet).  The per-octet chain LDS -> F2F -> DADD -> DMMA is
+// latency bound; twice the warps per SM hide twice the latency.
+template <typename TI, typename TO, int NT, int SPLIT>
+__global__ void __launch_bounds__((kApplyConsumers * SPLIT + 1) * 32, 1)
+    apply_dense_small_kernel(const __grid_constant__ DenseSmallParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_cg_pad = NT * 8;
   const int su = panel_stride(n_cg_pad);
@@ -160,6 +165,9 @@ __global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(con
   uint64_t* empty = full + kMaxStages;
   off += 2 * kMaxStages * sizeof(uint64_t);
   off = (off + 127) / 128 * 128;
+  constexpr int kAccDoubles = 3 * NT * 2;  // per lane
+  double* s_scratch = reinterpret_cast<double*>(smem + off);  // [team][2][kAccDoubles][32], SPLIT == 2 only
+  if (SPLIT == 2) off += (size_t)kApplyConsumers * 2 * kAccDoubles * 32 * sizeof(double);
   TI* raw = reinterpret_cast<TI*>(smem + off);
   const int64_t frame_elems = (int64_t)p.n_sites * 3;
   const int64_t stage_elems = ((int64_t)kOctet * frame_elems * (int64_t)sizeof(TI) + 15) / 16 * 16 / (int64_t)sizeof(TI);
@@ -197,7 +205,7 @@ __global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(con
   const int64_t first = blockIdx.x, step = gridDim.x;
   const int64_t n_mine = p.sch.n_chunks > first ? (p.sch.n_chunks - first + step - 1) / step : 0;
 
-  if (warp == kApplyConsumers) {
+  if (warp == kApplyConsumers * SPLIT) {
     // ---------------- producer warp
     for (int64_t j = 0; j < n_mine; ++j) {
       const int64_t c = first + j * step;
@@ -242,8 +250,13 @@ __global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(con
   // A waiter can tell the current mbarrier phase from the previous one only, so at most n_stages
   // warps may consume (then the stage a warp waits for is never two phases ahead of its fill).
   const int n_cons = n_stages < kApplyConsumers ? n_stages : kApplyConsumers;
-  if (warp >= n_cons) return;
-  for (int64_t j = warp; j < n_mine; j += n_cons) {
+  const int team = warp / SPLIT, half = warp % SPLIT;
+  if (team >= n_cons) return;
+  // this warp's share of the unique columns
+  const int xmid = SPLIT == 2 ? ((xpad / 4 + 1) / 2) * 4 : xpad;
+  const int x_begin = half == 0 ? 0 : xmid, x_end = (SPLIT == 2 && half == 0) ? xmid : xpad;
+  int it = 0;
+  for (int64_t j = team; j < n_mine; j += n_cons) {
     const int64_t c = first + j * step;
     const int stage = (int)(j % n_stages);
     const uint32_t parity = (uint32_t)((j / n_stages) & 1);
@@ -260,7 +273,7 @@ __global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(con
         for (int n = 0; n < NT; ++n) acc[d][n][0] = acc[d][n][1] = 0.0;
       if (!generic_groups) {
 #pragma unroll 2
-        for (int x0 = 0; x0 < xpad; x0 += 4) {
+        for (int x0 = x_begin; x0 < x_end; x0 += 4) {
           const int4 mem = s_tab[x0 + q];
           double a0 = 0.0, a1 = 0.0, a2 = 0.0;
           if (mem.x >= 0) { a0 = to_f64(fr[mem.x]); a1 = to_f64(fr[mem.x + 1]); a2 = to_f64(fr[mem.x + 2]); }
@@ -278,7 +291,7 @@ __global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(con
           }
         }
       } else {
-        for (int x0 = 0; x0 < xpad; x0 += 4) {
+        for (int x0 = x_begin; x0 < x_end; x0 += 4) {
           double v[3], cnt[3];
           group_value3<TI>(fr, s_ptr, s_sites, x0 + q, p.n_ucol, false, v, cnt);
           if (!valid) v[0] = v[1] = v[2] = 0.0;
@@ -291,6 +304,29 @@ __global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(con
             dmma884(acc[2][n][0], acc[2][n][1], v[2], b);
           }
         }
+      }
+      if (SPLIT == 2) {
+        // combine the two halves: warp 1 of the team publishes, warp 0 adds and finishes the octet
+        double* scr = s_scratch + ((size_t)(team * 2 + (it & 1)) * kAccDoubles) * 32 + lane;
+        ++it;
+        if (half == 1) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              scr[((d * NT + n) * 2) * 32] = acc[d][n][0];
+              scr[((d * NT + n) * 2 + 1) * 32] = acc[d][n][1];
+            }
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + team) : "memory");
+        if (half == 1) continue;  // the raw stage is released by warp 0 (which may still redo it)
+#pragma unroll
+        for (int d = 0; d < 3; ++d)
+#pragma unroll
+          for (int n = 0; n < NT; ++n) {
+            acc[d][n][0] += scr[((d * NT + n) * 2) * 32];
+            acc[d][n][1] += scr[((d * NT + n) * 2 + 1) * 32];
+          }
       }
       if (nan_mode) {
         bool has_nan = false;
@@ -358,7 +394,7 @@ __global__ void __launch_bounds__(kApplyThreads, 1) apply_dense_small_kernel(con
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[stage]);
+    if (lane == 0 && half == 0) mbar_arrive(&empty[stage]);  // one arrival per stage (also for empty chunks)
   }
   if (p.sumsq) {
     sq = warp_sum(sq);
@@ -586,6 +622,8 @@ __global__ void __launch_bounds__(256) apply_dense_big_kernel(const TI* __restri
 }
 
 // Shared-memory footprint of the small dense kernel before its raw ring; 0 = does not apply.
+static int small_split(int ntk) { return ntk <= 2 ? 2 : 1; }  // warps per octet (scratch grows with NT)
+
 static size_t small_fixed_bytes(int n_ucol, int nnz, int n_cg) {
   const int nt = (n_cg + 7) / 8;
   if (n_cg > 64 || nt < 1) return 0;
@@ -594,7 +632,9 @@ static size_t small_fixed_bytes(int n_ucol, int nnz, int n_cg) {
   const int xpad = (n_ucol + 3) & ~3;
   size_t off = (size_t)xpad * su * sizeof(double) + (size_t)xpad * 16 + (size_t)(n_ucol + 1) * 4 + (size_t)nnz * 4;
   off = (off + 15) / 16 * 16 + 2 * kMaxStages * sizeof(uint64_t);
-  return (off + 127) / 128 * 128;
+  off = (off + 127) / 128 * 128;
+  if (small_split(ntk) == 2) off += (size_t)kApplyConsumers * 2 * (3 * ntk * 2) * 32 * sizeof(double);
+  return off;
 }
 static bool small_fits(int n_sites, int n_ucol, int nnz, int n_cg, size_t elem) {
   const size_t off = small_fixed_bytes(n_ucol, nnz, n_cg);
@@ -613,13 +653,14 @@ static int launch_small(DenseSmallParams& p, cudaStream_t stream) {
   if (n_stages > kMaxStages) n_stages = kMaxStages;
   p.n_stages = n_stages;
   size_t smem = off + (size_t)n_stages * stage_bytes;
-  auto kern = apply_dense_small_kernel<TI, TO, NT>;
+  constexpr int SPLIT = NT <= 2 ? 2 : 1;
+  auto kern = apply_dense_small_kernel<TI, TO, NT, SPLIT>;
   AGF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t ctas = sm_count();
   int64_t want = (p.sch.n_chunks + kApplyConsumers - 1) / kApplyConsumers;
   if (ctas > want) ctas = want;
   if (ctas < 1) ctas = 1;
-  kern<<<(int)ctas, kApplyThreads, smem, stream>>>(p);
+  kern<<<(int)ctas, (kApplyConsumers * SPLIT + 1) * 32, smem, stream>>>(p);
   AGF_CUDA_TRY(cudaGetLastError());
   return AGF_OK;
 }
