@@ -254,7 +254,11 @@ class Frames:
     """A ``(n_frames, n_sites, 3)`` array as the kernels see it (see module docstring)."""
 
     def __new__(cls, array=None, *args, **kwargs):
-        # virtual frame sources (subclasses, e.g. the Gaussian-augmented frames) pass through unchanged
+        # virtual frame sources (subclasses: Gaussian-augmented frames, synthetic frames) pass through
+        # unchanged, also when wrapped by agg._Shared; their __init__ must tolerate the second call
+        inner = getattr(array, "frames", None)
+        if isinstance(inner, Frames):
+            array = inner
         if cls is Frames and isinstance(array, Frames) and type(array) is not Frames:
             return array
         return super().__new__(cls)

@@ -124,3 +124,59 @@ def synth_trajectory_device(topo: Topology, n_frames: int, seed: int = 1234, fra
               int(n_frames), C.c_uint64(seed), POS_SIGMA, FORCE_SIGMA, H_COUPLING, _engine.ptr(coords),
               _engine.ptr(forces), _engine.stream_ptr())
     return coords, forces
+
+
+class SynthFrames:
+    """Virtual ``(n_frames, n_sites, 3)`` frame source backed by the counter-based generator: slabs of
+    frames are produced by ``agf_synth_frames`` as a kernel asks for them and never stored, so a
+    rank's share of config 4 (1.25 M frames x 5 000 atoms: 75 GB per array) streams through HBM once
+    per pass.  Behaves like ``_engine.Frames`` (use ``make_synth_frames``)."""
+
+
+def make_synth_frames(topo: Topology, n_frames: int, which: str, seed: int = 1234, frame0: int = 0,
+                      slab_bytes: int = 1 << 30):
+    """``which``: ``"coords"`` or ``"forces"``.  Global frames ``[frame0, frame0 + n_frames)``."""
+    import numpy as _np
+    import torch
+
+    from . import _engine
+
+    assert which in ("coords", "forces")
+
+    class _SynthFrames(_engine.Frames, SynthFrames):
+        def __init__(self, source=None) -> None:
+            if "n_frames" in self.__dict__:  # _engine.Frames(x) passes an existing instance through
+                return
+            self._dev, self._host = None, None
+            self.n_frames, self.n_sites = int(n_frames), int(topo.n_sites)
+
+        @property
+        def on_host(self) -> bool:
+            return False
+
+        @property
+        def np_dtype(self):
+            return _np.float32
+
+        def pieces(self, start: int = 0, stop=None):
+            stop = self.n_frames if stop is None else min(stop, self.n_frames)
+            per = max(4, (slab_bytes // (self.n_sites * 12)) // 4 * 4)
+            for a in range(start, stop, per):
+                b = min(a + per, stop)
+                c, f = synth_trajectory_device(topo, b - a, seed=seed, frame0=frame0 + a,
+                                               want_coords=which == "coords", want_forces=which == "forces")
+                yield a, (c if which == "coords" else f)
+
+        def resident(self) -> "torch.Tensor":
+            return torch.cat([p for _, p in self.pieces()])
+
+        def prefix(self, n: int) -> "torch.Tensor":
+            return torch.cat([p for _, p in self.pieces(0, min(n, self.n_frames))])
+
+        def gather(self, frame_indices) -> "torch.Tensor":
+            idx = _np.asarray(frame_indices, dtype=_np.int64)
+            rows = [synth_trajectory_device(topo, 1, seed=seed, frame0=frame0 + int(i), want_coords=which == "coords",
+                                            want_forces=which == "forces")[0 if which == "coords" else 1] for i in idx]
+            return torch.cat(rows)
+
+    return _SynthFrames()

@@ -193,7 +193,7 @@ class AugmentedFrames(_engine.Frames):
 
     def __init__(self, source, augmenter: Optional[CondNormal] = None, kbt: float = 0.0,
                  draw: Optional[NoiseDraw] = None, which: str = "coords") -> None:
-        if source is self:  # _engine.Frames(aug) passes an existing instance through
+        if "_src" in self.__dict__:  # _engine.Frames(aug) passes an existing instance through
             return
         assert augmenter is not None and draw is not None and which in ("coords", "forces")
         self._src = _engine.Frames(source)

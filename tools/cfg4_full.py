@@ -1,0 +1,33 @@
+"""Config 4 at one rank's full share (default 1.25 M frames x 5000 atoms, n_red 2600, 500 beads):
+the trajectory (75 GB per array) is never materialised -- SynthFrames regenerate slabs of frames
+from the counter-based generator for every pass (constraint detection, Gram, two applications)."""
+import sys, time
+sys.path.insert(0, '/root/repo')
+import numpy as np, torch
+import aggforce_b200 as agf
+from aggforce_b200 import _lib
+from aggforce_b200.synth import make_synth_frames, protein_like_topology
+
+T = int(sys.argv[1]) if len(sys.argv) > 1 else 1_250_000
+topo = protein_like_topology(500)
+coords = make_synth_frames(topo, T, "coords", seed=3, slab_bytes=4 << 30)
+forces = make_synth_frames(topo, T, "forces", seed=3, slab_bytes=4 << 30)
+cmap = agf.LinearMap([[i] for i in topo.bead_atoms], n_fg_sites=topo.n_sites)
+print(f"n_sites {topo.n_sites} beads {len(topo.bead_atoms)} frames {T}  ({T * topo.n_sites * 12 / 1e9:.1f} GB per array, virtual)")
+torch.cuda.synchronize()
+_lib.timing(True)
+t0 = time.perf_counter()
+res = agf.project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds="auto", l2_regularization=1e3)
+torch.cuda.synchronize()
+dt = time.perf_counter() - t0
+recs = _lib.timing_records(); _lib.timing(False)
+agg = {}
+for n, ms in recs: agg[n] = agg.get(n, 0.0) + ms
+print(f"project_forces(auto constraints, qp_linear_map): {dt:.2f} s = {T/dt:.3e} frames/s")
+print("  entry points [ms]:", ", ".join(f"{n} {ms:.0f}" for n, ms in sorted(agg.items(), key=lambda kv: -kv[1])))
+print("  constraints", len(res["constraints"]), "== topology:", res["constraints"] == topo.xh_constraints,
+      " residual", res["residual"], " mapped forces", tuple(res["mapped_forces"].shape), res["mapped_forces"].dtype)
+flop = (3 * 2600 * 2601 + 3 * 5000) * T
+g = agg.get("agf_gram_linear_ws", 0.0)
+if g: print(f"  Gram: {g:.0f} ms = {flop / g / 1e9:.1f} TFLOP/s ({flop / g / 1e9 / 37.15 * 100:.1f}% of DMMA peak)")
+print("  peak memory allocated: %.1f GB" % (torch.cuda.max_memory_allocated() / 1e9))
