@@ -642,12 +642,25 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
             _lib.call("agf_pair_moments", ptr(piece), ptr(o), dtype_code(piece), piece.shape[0], n, n_o,
                       ptr(pairs), int(pairs.shape[0]), ptr(shift), ptr(acc), stream_ptr())
 
+    # second pruning point after a few thousand frames: bounds the survivor count for flexible
+    # molecules (at n = 5000 the 32-frame screen leaves ~10^5 pairs, 4096 frames leave the bonded
+    # ones).  Under sharding every rank holds the same pair list and a pair dead on any rank is dead
+    # globally (M2_global >= M2_rank), so the keep masks are combined with one MIN all-reduce; the
+    # branch depends on the (global) pair count only, so all ranks take it together.
     done = 0
-    if t_local > 4 * _RESCREEN_FRAMES and n_pairs > 4 * max(n, n_o) and not sharded():
-        run(0, _RESCREEN_FRAMES)
-        done = _RESCREEN_FRAMES
-        m2p = acc[:, 1] - acc[:, 0] ** 2 / done
-        keep = torch.nonzero(m2p <= bound).reshape(-1)
+    if n_pairs > 4 * max(n, n_o) and (sharded() or t_local > 4 * _RESCREEN_FRAMES):
+        done = min(_RESCREEN_FRAMES, t_local)
+        run(0, done)
+        if done > 0:
+            m2p = acc[:, 1] - acc[:, 0] ** 2 / done
+            keep_mask = m2p <= (bound_dev if fused else bound)
+        else:
+            keep_mask = torch.ones(n_pairs, dtype=torch.bool, device=dev)
+        if sharded():
+            km = keep_mask.to(torch.uint8)
+            allreduce_min_(km)
+            keep_mask = km > 0
+        keep = torch.nonzero(keep_mask).reshape(-1)
         pairs, shift, acc = pairs[keep].contiguous(), shift[keep].contiguous(), acc[keep].contiguous()
         n_pairs = int(pairs.shape[0])
         if n_pairs == 0:
