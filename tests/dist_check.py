@@ -44,6 +44,15 @@ def main() -> None:
     rel_f = float((mf - ref["mapped_forces"][lo:hi]).norm() / ref["mapped_forces"][lo:hi].norm())
     ok = (res["constraints"] == ref["constraints"] == topo.xh_constraints and rel_w < 1e-9 and rel_f < 1e-9
           and abs(res["residual"] / ref["residual"] - 1) < 1e-9)
+    # second pruning point under sharding: a deliberately weak first screen (2 frames) leaves far more
+    # than 4 n pairs, which the 256-frame rescreen prunes with one MIN all-reduce of the keep masks
+    from aggforce_b200 import _engine
+
+    _engine._SCREEN_FRAMES, _engine._RESCREEN_FRAMES = 2, 256
+    with agf.frame_sharding():
+        cons2 = agf.guess_pairwise_constraints(coords)
+    _engine._SCREEN_FRAMES, _engine._RESCREEN_FRAMES = 32, 4096
+    ok = ok and cons2 == topo.xh_constraints
     flag = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -94,3 +94,17 @@ def test_device_and_host_paths_agree_bitwise():
     g_host, _ = force_gram(f, 33, set())
     g_dev, _ = force_gram(torch.as_tensor(f, device="cuda"), 33, set())
     assert rel_fro(g_host, g_dev) < 1e-14  # atomics: order may differ in the last bits
+
+
+def test_constraints_second_pruning_point(monkeypatch):
+    """A weak first screen (2 frames) leaves more than 4 n candidate pairs; the rescreen after a
+    few hundred frames prunes them exactly (partial M2 never exceeds the total)."""
+    from aggforce_b200 import _engine, guess_pairwise_constraints
+    from aggforce_b200.synth import protein_like_topology, synth_trajectory_host
+
+    topo = protein_like_topology(30)
+    coords, _ = synth_trajectory_host(topo, 3000, seed=8)
+    monkeypatch.setattr(_engine, "_SCREEN_FRAMES", 2)
+    monkeypatch.setattr(_engine, "_RESCREEN_FRAMES", 256)
+    got = guess_pairwise_constraints(coords)
+    assert got == topo.xh_constraints == oracle.guess_pairwise_constraints(coords[:, :, :].astype(np.float64))
