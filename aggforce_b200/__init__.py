@@ -8,6 +8,13 @@ hand-written sm_100a kernels (``csrc/``) behind the C ABI in ``include/agf_b200.
 from .trajectory import Trajectory  # noqa: F401
 from .agg import project_forces, project_forces_grid_cv  # noqa: F401
 from .constraints import guess_pairwise_constraints  # noqa: F401
-from .qp import qp_linear_map, constraint_aware_uni_map, joptgauss_map  # noqa: F401
+from .qp import (  # noqa: F401
+    qp_linear_map,
+    constraint_aware_uni_map,
+    joptgauss_map,
+    stagedjoptgauss_map,
+    stagedjslicegauss_map,
+    stagedjforcegauss_map,
+)
 from .map import LinearMap  # noqa: F401
 from ._engine import frame_sharding, Frames  # noqa: F401

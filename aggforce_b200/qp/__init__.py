@@ -12,4 +12,9 @@ from .featlinearmap import (  # noqa: F401
     id_feat,
 )
 from .gbfeat import gb_feat, GbSpec  # noqa: F401
-from .jgauss import joptgauss_map  # noqa: F401
+from .jgauss import (  # noqa: F401
+    joptgauss_map,
+    stagedjforcegauss_map,
+    stagedjoptgauss_map,
+    stagedjslicegauss_map,
+)

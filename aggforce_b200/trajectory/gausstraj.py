@@ -54,12 +54,15 @@ class CondNormal(Augmenter):
 
     def __init__(self, cov: float, premap=None, source_postmap=None, seed: Optional[int] = None,
                  dtype: Any = None, noise=None) -> None:
-        if source_postmap is not None:
-            raise NotImplementedError("source_postmap is not supported by the B200 augmenter")
         if not np.isscalar(cov):
             raise NotImplementedError("only scalar (isotropic) covariances are supported")
         owner = getattr(premap, "__self__", None)
         self.premap = owner if owner is not None else premap
+        # linear map applied to the log-gradient w.r.t. the source sites (jaxgausstraj.py:263-284):
+        # the staged maps pass (force_map @ coord_map.T) so that the noise force on an ALREADY mapped
+        # trajectory is the mapped back-projected noise force
+        post_owner = getattr(source_postmap, "__self__", None)
+        self.source_postmap = post_owner if post_owner is not None else source_postmap
         self.cov = float(cov)
         self.seed = int(np.random.default_rng().integers(0, 10**6)) if seed is None else int(seed)
         self.dtype = np.dtype(np.float32 if dtype is None else dtype)
@@ -73,10 +76,9 @@ class CondNormal(Augmenter):
         return source if self.premap is None else self.premap(source)
 
     def _back(self, eps: torch.Tensor):
-        """A^T eps for the pre-map (identity when premap is None)."""
-        if self.premap is None:
-            return eps
-        return self.premap.T(eps)
+        """[source_postmap] A^T eps for the pre-map A (identity when premap is None)."""
+        out = eps if self.premap is None else self.premap.T(eps)
+        return out if self.source_postmap is None else self.source_postmap(out)
 
     # -- Augmenter interface
     def sample(self, source):
@@ -129,7 +131,13 @@ class CondNormal(Augmenter):
                 return _engine.dev_i32(ptr_), _engine.dev_i32([0]), _engine.dev_f64([0.0])
             return _engine.dev_i32(ptr_), _engine.dev_i32(cols), _engine.dev_f64(mat[rows, cols])
 
-        arrays = (*csr(m), *csr(np.ascontiguousarray(m.T)), m.shape[0])
+        corr = np.ascontiguousarray(m.T)  # (n_sites, n_new): back-projection of the noise force
+        if self.source_postmap is not None:
+            post = np.asarray(self.source_postmap.standard_matrix, dtype=np.float64)
+            if post.shape != (n_sites, n_sites):
+                raise ValueError(f"source_postmap must map {n_sites} sites to {n_sites} sites; got {post.shape}")
+            corr = post @ corr
+        arrays = (*csr(m), *csr(corr), m.shape[0])
         self._csr = (n_sites, arrays)
         return arrays
 
@@ -171,7 +179,8 @@ class CondNormal(Augmenter):
         return full_coords, full_forces
 
     def astype(self, dtype, *args, **kwargs) -> "CondNormal":  # noqa: ARG002
-        return self.__class__(cov=self.cov, premap=self.premap, seed=self.seed, dtype=dtype)
+        return self.__class__(cov=self.cov, premap=self.premap, source_postmap=self.source_postmap, seed=self.seed,
+                              dtype=dtype)
 
 
 class NoiseDraw:

@@ -245,3 +245,54 @@ def test_joptgauss_slabs_reproduce_the_same_noise(topo, data, monkeypatch):
     got_f = torch.cat([p for _, p in gausstraj.AugmentedFrames(df, aug, KBT, draw, "forces").pieces()]).cpu().numpy()
     rc, rf = oracle.gauss_augment(coords, forces, cmap.standard_matrix, 0.3, KBT, noise)
     assert rel_fro(got_c, rc) < 1e-6 and rel_fro(got_f, rf) < 1e-6
+
+
+def test_staged_gauss_maps(topo, data):
+    """Staged Gaussian maps (reference jgauss.py:143-650) against a numpy restatement of their
+    composition (parity with the JAX reference itself is unpinned)."""
+    import warnings
+
+    from aggforce_b200 import Trajectory, stagedjforcegauss_map, stagedjoptgauss_map, stagedjslicegauss_map
+    from aggforce_b200.trajectory import CoordsTrajectory
+
+    coords, forces = data
+    cmap, cons = _cmap(topo), topo.xh_constraints
+    cm = np.asarray(cmap.standard_matrix)
+    T, n_cg, var, kbt = len(coords), 10, 0.25, KBT
+    z = np.random.default_rng(3).standard_normal((T, n_cg, 3)).astype(np.float32)
+    traj = Trajectory(coords=coords, forces=forces)
+    staged = stagedjoptgauss_map(traj, cmap, var=var, kbt=kbt, constraints=cons, seed=1, premap_l2_regularization=1e2,
+                                 noise=z, l2_regularization=1e1)
+    pre, post = staged[1], staged[0]
+    w0 = oracle.qp_linear_weights(forces, cm, cons, 1e2)
+    assert rel_fro(pre.force_map.standard_matrix, w0) < 1e-6
+    full_c, full_f = oracle.gauss_augment(coords, forces, cm, var, kbt, z)
+    pm_f = np.concatenate([oracle.apply_map(full_f[:, :175], w0), full_f[:, 175:]], axis=1).astype(np.float32)
+    sl = np.zeros((n_cg, 2 * n_cg))
+    sl[np.arange(n_cg), n_cg + np.arange(n_cg)] = 1
+    w1 = oracle.qp_linear_weights(pm_f, sl, set(), 1e1)
+    got_w1 = post.tmap.force_map.standard_matrix
+    assert got_w1.shape == (n_cg, 2 * n_cg) and rel_fro(got_w1, w1) < 1e-4
+    # application with an injected draw: Y_final = W1 [W0 F + kbt/var P eps ; -kbt/var eps],  P = W0 A^T
+    z2 = np.random.default_rng(4).standard_normal((T, n_cg, 3)).astype(np.float32)
+    post.augmenter._noise = z2
+    out = staged(traj)
+    eps = np.sqrt(var) * z2.astype(np.float64)
+    x_cg, y_cg = oracle.apply_map(coords, cm), oracle.apply_map(forces, w0)
+    p = w0 @ cm.T
+    f_aug = np.concatenate([y_cg + kbt / var * oracle.apply_map(eps, p), -kbt / var * eps], axis=1)
+    assert rel_fro(out.coords, x_cg + eps) < 1e-5
+    assert rel_fro(out.forces, oracle.apply_map(f_aug, w1)) < 1e-4
+    # slice map: forces are the noise-site forces -kbt (y - A x) / var, also for force-free input
+    sliced = stagedjslicegauss_map(CoordsTrajectory(coords=coords), cmap, var=var, kbt=kbt, seed=2)
+    o = sliced(CoordsTrajectory(coords=coords))
+    assert np.allclose(o.forces, -kbt * (o.coords - x_cg) / var, rtol=1e-3, atol=1e-3)
+    assert abs((o.coords - x_cg).var() / var - 1) < 0.2
+    # force map: W0 A^T = I, so the noise contributions cancel exactly with W1 = [I | I]
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        fmap = stagedjforcegauss_map(traj, cmap, var=var, kbt=kbt, constraints=cons, seed=5,
+                                     premap_l2_regularization=1e2)
+    assert np.allclose(fmap[0].tmap.force_map.standard_matrix, np.hstack([np.eye(n_cg), np.eye(n_cg)]), atol=1e-4)
+    of = fmap(traj)
+    assert rel_fro(of.forces, y_cg) < 1e-4  # real mapped forces, noise forces cancelled
