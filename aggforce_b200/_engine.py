@@ -428,6 +428,10 @@ def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Te
     # 3- and 4-member columns is then also the one holding pairs, and the ragged last group holds
     # singles -- the number of (warp-wide) f64 additions per frame drops from 33 to 12 at cln025
     order = np.argsort(-sizes, kind="stable")  # internal position -> caller's column
+    if n_red > 128:
+        # packed-panel path: no per-lane member walk to balance; keep the caller's order (columns follow
+        # their first site), so the pack kernel's gathers of neighbouring columns hit neighbouring sites
+        order = np.arange(n_red)
     rank = np.empty(n_red, dtype=np.int64)
     rank[order] = np.arange(n_red)
     internal = np.where(col_of_site >= 0, rank[np.maximum(col_of_site, 0)], -1)
@@ -497,6 +501,13 @@ class CompiledMap:
         # length (f32->f64 conversions issue per warp instruction, divergent lists would serialise)
         sizes = np.bincount(inverse[inverse >= 0], minlength=uniq.shape[0])
         order = np.argsort(sizes, kind="stable")
+        if self.n_cg > 64:
+            # packed-panel GEMM path: order the unique columns by their first site instead, so the pack
+            # kernel's gathers for neighbouring columns hit neighbouring sites of a frame
+            live = np.nonzero(inverse >= 0)[0]
+            first = np.full(uniq.shape[0], self.n_fg, dtype=np.int64)
+            np.minimum.at(first, inverse[live], live)
+            order = np.argsort(first, kind="stable")
         rank = np.empty_like(order)
         rank[order] = np.arange(order.size)
         inverse = np.where(inverse >= 0, rank[np.maximum(inverse, 0)], -1)
