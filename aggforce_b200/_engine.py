@@ -479,6 +479,7 @@ class CompiledMap:
             else:
                 weights = m64[rows, cols]
             self.row_ptr, self.row_sites, self.row_w = dev_i32(ptr_), dev_i32(cols), dev_f64(weights)
+            self.slice = nnz == self.n_cg and bool((nz_per_row == 1).all())  # one site per bead
             return
         if column_labels is not None:
             inverse = np.asarray(column_labels, dtype=np.int64)
@@ -532,7 +533,11 @@ def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float,
     flags = torch.zeros(2, dtype=torch.int32, device=device())
     for t0, piece in frames.pieces(start, stop):
         o = out[t0 - start : t0 - start + piece.shape[0]]
-        if cmap.sparse:
+        if cmap.sparse and cmap.slice:
+            _lib.call("agf_map_apply_slice", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites,
+                      ptr(cmap.row_sites), ptr(cmap.row_w), cmap.n_cg, ptr(o), dtype_code(o), ptr(sumsq), nan_mode,
+                      float(nan_atol), ptr(flags), stream_ptr())
+        elif cmap.sparse:
             _lib.call("agf_map_apply_sparse", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites,
                       ptr(cmap.row_ptr), ptr(cmap.row_sites), ptr(cmap.row_w), cmap.n_cg, ptr(o), dtype_code(o),
                       ptr(sumsq), nan_mode, float(nan_atol), ptr(flags), stream_ptr())

@@ -99,6 +99,72 @@ __global__ void __launch_bounds__(256) apply_sparse_kernel(const TI* __restrict_
   }
 }
 
+// Slice maps (exactly one site per bead, the usual coordinate map): the loads of four (frame, bead)
+// items are issued before any of them is used -- the generic kernel above is bound by the latency of
+// its one dependent gather per thread (ncu: long-scoreboard stalls, DRAM traffic already at the
+// 64-byte minimum), not by bandwidth.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) apply_slice_kernel(const TI* __restrict__ x, int64_t n_frames, int n_sites,
+                                                          const int32_t* __restrict__ row_sites,
+                                                          const double* __restrict__ row_w, int n_cg,
+                                                          TO* __restrict__ out, double* sumsq, int nan_mode,
+                                                          double nan_atol, int32_t* nan_flags) {
+  constexpr int U = 4;
+  const int64_t total = n_frames * n_cg;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double sq = 0.0;
+  bool saw_nan = false, bad = false;
+  for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < total; base += stride * U) {
+    double v[U][3], w[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t idx = base + u * stride;
+      v[u][0] = v[u][1] = v[u][2] = 0.0;
+      w[u] = 0.0;
+      if (idx < total) {
+        const int64_t t = idx / n_cg;
+        const int c = (int)(idx - t * n_cg);
+        const TI* p = x + t * (int64_t)n_sites * 3 + 3 * __ldg(row_sites + c);
+        w[u] = __ldg(row_w + c);
+        v[u][0] = ldg_sparse(p);
+        v[u][1] = ldg_sparse(p + 1);
+        v[u][2] = ldg_sparse(p + 2);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t idx = base + u * stride;
+      if (idx >= total) continue;
+      double a[3];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        double f = v[u][d];
+        if (nan_mode && f != f) {  // NaN counts as 0; the result depends on it unless its weight is ~0
+          saw_nan = true;
+          bad |= fabs(w[u]) > nan_atol + kNanRtol * fabs(w[u]);
+          f = 0.0;
+        }
+        a[d] = w[u] * f;
+      }
+      TO* o = out + idx * 3;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        store_out(o + d, a[d]);
+        const double r = (double)static_cast<TO>(a[d]);
+        sq += r * r;
+      }
+    }
+  }
+  if (sumsq) {
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sumsq, sq);
+  }
+  if (nan_mode) {
+    if (saw_nan) atomicOr(nan_flags, 1);
+    if (bad) atomicOr(nan_flags + 1, 1);
+  }
+}
+
 // ------------------------------------------------------------------------------------ dense small
 // Work item = 8 consecutive frames ("octet").  A producer warp streams octets through a ring
 // of shared-memory stages with 1-D TMA bulk copies; each of the 8 consumer warps owns whole
@@ -860,6 +926,34 @@ extern "C" int agf_map_apply_sparse(const void* points, int in_dtype, int64_t n_
   else if (in_dtype == AGF_F64 && out_dtype == AGF_F64) AGF_SP(double, double);
   else AGF_SP(double, float);
 #undef AGF_SP
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}
+
+extern "C" int agf_map_apply_slice(const void* points, int in_dtype, int64_t n_frames, int32_t n_sites,
+                                   const int32_t* row_sites, const double* row_weights, int32_t n_cg, void* out,
+                                   int out_dtype, double* sumsq, int nan_mode, double nan_atol, int32_t* nan_flags,
+                                   void* stream) {
+  using namespace agf;
+  AGF_REQUIRE(points && row_sites && row_weights && out, "agf_map_apply_slice: null pointer");
+  AGF_REQUIRE(n_frames >= 0 && n_sites > 0 && n_cg > 0, "agf_map_apply_slice: bad sizes");
+  AGF_REQUIRE(nan_mode == 0 || nan_flags != nullptr, "agf_map_apply_slice: nan_mode 1 needs nan_flags");
+  AGF_REQUIRE((in_dtype == AGF_F32 || in_dtype == AGF_F64) && (out_dtype == AGF_F32 || out_dtype == AGF_F64),
+              "agf_map_apply_slice: bad dtype");
+  if (n_frames == 0) return AGF_OK;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t total = n_frames * n_cg;
+  const int64_t want = (total + 256 * 4 - 1) / (256 * 4);
+  const int blocks = (int)(want < (int64_t)sm_count() * 8 ? (want < 1 ? 1 : want) : (int64_t)sm_count() * 8);
+#define AGF_SL(TI, TO)                                                                                        \
+  apply_slice_kernel<TI, TO><<<blocks, 256, 0, s>>>(reinterpret_cast<const TI*>(points), n_frames, n_sites,   \
+                                                    row_sites, row_weights, n_cg, reinterpret_cast<TO*>(out), \
+                                                    sumsq, nan_mode, nan_atol, nan_flags)
+  if (in_dtype == AGF_F32 && out_dtype == AGF_F64) AGF_SL(float, double);
+  else if (in_dtype == AGF_F32 && out_dtype == AGF_F32) AGF_SL(float, float);
+  else if (in_dtype == AGF_F64 && out_dtype == AGF_F64) AGF_SL(double, double);
+  else AGF_SL(double, float);
+#undef AGF_SL
   AGF_CUDA_TRY(cudaGetLastError());
   return AGF_OK;
 }

@@ -247,7 +247,7 @@ def main() -> None:
                 _, r1, r2 = step(c, f)
                 d2h["n"] = sum(r[k].nbytes for r in (r1, r2) for k in ("mapped_coords", "mapped_forces"))
 
-            ms_e2e, _, _ = timed(host_step, max(1, min(args.steps, 3)), 1)
+            ms_e2e, _, _ = timed(host_step, max(1, min(args.steps, 5)), 3)
             e2e = {"value": world * T / (ms_e2e * 1e-3), "unit": UNIT,
                    "h2d_bytes_per_step": int(nc.nbytes + nf.nbytes), "d2h_bytes_per_step": int(d2h["n"]),
                    "ms_per_step": ms_e2e}
@@ -282,10 +282,11 @@ def main() -> None:
             else:
                 entry.update(bound="hbm", achieved=per / 1e9, peak=hbm_peak, unit="GB/s")
             entry["frac"] = entry["achieved"] / entry["peak"]
-        elif name == "agf_map_apply_sparse":
-            # three launches: coords slice map x2 (10 nnz) and the uniform force map (21 nnz); algorithmic
-            # bytes = referenced sites (12 B each) + f64 outputs
-            amount = ((2 * 10 + uni_nnz) * 12 + 3 * 24 * n_cg) * T
+        elif name in ("agf_map_apply_sparse", "agf_map_apply_slice"):
+            # slice: the coordinate map of both project_forces calls (10 sites); sparse: the uniform force
+            # map (21 nnz).  Algorithmic bytes = referenced sites (12 B each) + f64 outputs, per launch
+            nnz = n_cg if name == "agf_map_apply_slice" else uni_nnz
+            amount = (nnz * 12 + 24 * n_cg) * T * len(times)
             entry.update(bound="hbm", achieved=amount / (tot * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s")
             entry["frac"] = entry["achieved"] / entry["peak"]
         if name in traffic_per_frame:

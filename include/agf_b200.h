@@ -130,6 +130,14 @@ int agf_map_apply_sparse(const void* points, int in_dtype, int64_t n_frames, int
                          int32_t n_cg, void* out, int out_dtype, double* sumsq, int nan_mode,
                          double nan_atol, int32_t* nan_flags, void* stream);
 
+/* Slice maps: exactly one site per bead (row_sites int32 [n_cg], row_weights f64 [n_cg]) -- the
+ * usual coordinate map.  Same outputs / NaN semantics; four gathers in flight per thread.
+ */
+int agf_map_apply_slice(const void* points, int in_dtype, int64_t n_frames, int32_t n_sites,
+                        const int32_t* row_sites, const double* row_weights, int32_t n_cg,
+                        void* out, int out_dtype, double* sumsq, int nan_mode, double nan_atol,
+                        int32_t* nan_flags, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (c) pair-distance moments for constraint detection.
  * Replaces  src/aggforce/util.py:64-70 (all-pairs displacement + norm) and
