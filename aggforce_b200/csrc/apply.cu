@@ -17,6 +17,10 @@
 #include "frame_pipe.cuh"
 #include "panel.cuh"
 
+#ifndef AGF_APPLY_TEAMS
+#define AGF_APPLY_TEAMS 8
+#endif
+
 namespace agf {
 
 constexpr double kNanRtol = 1e-5;  // numpy.allclose default used at map/core.py:230
@@ -193,7 +197,7 @@ struct DenseSmallParams {
   int32_t n_stages;
 };
 
-constexpr int kApplyConsumers = 8;
+constexpr int kApplyConsumers = AGF_APPLY_TEAMS;
 constexpr int kApplyThreads = (kApplyConsumers + 1) * 32;
 constexpr int kOctet = 8;
 constexpr int kMaxStages = 16;
