@@ -450,7 +450,7 @@ def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Te
     allreduce_sum_(gram)
     _lib.call("agf_symmetrize", ptr(gram), n_red, stream_ptr())
     if not np.array_equal(order, np.arange(n_red)):
-        back = torch.as_tensor(rank, device=gram.device)
+        back = _dev_cached(np.ascontiguousarray(rank, dtype=np.int64))  # cached: no pageable upload per call
         gram = gram[back][:, back]
     return gram
 
@@ -691,7 +691,7 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
     else:
         mean, m2_local = torch.zeros_like(shift), torch.zeros_like(shift)
     # the surviving pair list rides along (as float64) so that ONE synchronising read returns everything
-    rec = torch.cat([torch.tensor([float(t_local)], dtype=torch.float64, device=dev), mean, m2_local])
+    rec = torch.cat([torch.full((1,), float(t_local), dtype=torch.float64, device=dev), mean, m2_local])
     pairs_f = pairs.to(torch.float64).reshape(-1)
     if sharded():
         dist = _dist()

@@ -108,7 +108,7 @@ def project_forces(
         host_f = _engine.start_d2h(of) if ff.on_host else None
         # [flags_c(2), sumsq_c, flags_f(2), sumsq_f, n_elements]; under frame sharding the residual
         # numerator / denominator are summed over ranks on the device before the single read
-        count = torch.tensor([float(np.prod(of.shape))], dtype=torch.float64, device=of.device)
+        count = torch.full((1,), float(np.prod(of.shape)), dtype=torch.float64, device=of.device)  # fill kernel, no upload
         packed = torch.cat([sc, sf, count])
         if _engine.sharded():
             tail = packed[5:7].clone()

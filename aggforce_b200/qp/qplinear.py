@@ -4,6 +4,7 @@ Drop-in for the reference's ``src/aggforce/qp/qplinear.py``.
 """
 from __future__ import annotations
 
+import functools
 from typing import Union
 
 import numpy as np
@@ -23,8 +24,24 @@ def reduced_columns(n_sites: int, constraints: Constraints) -> np.ndarray:
     Sites constrained together share one coefficient.  Column order follows the reference
     (``qplinear.py:157-163``): walking the sites in increasing order, every site that is not a
     dependent member of a merged constraint group opens the next column; dependents reuse
-    their anchor's (the smallest index of their group).
+    their anchor's (the smallest index of their group).  Pure index bookkeeping: memoised on the
+    constraint set (a fit, the uniform map and the CV folds all ask for the same table).
     """
+    try:
+        key = frozenset(constraints)
+    except TypeError:  # unhashable members: compute directly
+        return _reduced_columns(n_sites, constraints)
+    return _reduced_columns_cached(n_sites, key).copy()
+
+
+@functools.lru_cache(maxsize=16)
+def _reduced_columns_cached(n_sites: int, constraints: frozenset) -> np.ndarray:
+    cols = _reduced_columns(n_sites, constraints)
+    cols.setflags(write=False)
+    return cols
+
+
+def _reduced_columns(n_sites: int, constraints: Constraints) -> np.ndarray:
     anchor_of = constraint_lookup_dict(merged_groups(constraints))
     cols = np.full(n_sites, -1, dtype=np.int64)
     free = [s for s in range(n_sites) if s not in anchor_of]
@@ -97,8 +114,12 @@ def qp_linear_map(
             qp_mat[np.diag_indices(n_red)] += l2_regularization * group_size
     # A = coord_map @ C : sum the coordinate-map columns of every group
     cmat = np.asarray(coord_map.standard_matrix, dtype=np.float64)
-    onehot = ss.csr_matrix((np.ones(n_fg), (np.arange(n_fg), cols)), shape=(n_fg, n_red))
-    a_mat = np.asarray((onehot.T @ cmat.T).T)
+    if n_fg * coord_map.n_cg_sites <= (1 << 16):  # small: a scatter-add beats building a sparse one-hot
+        a_mat = np.zeros((coord_map.n_cg_sites, n_red))
+        np.add.at(a_mat.T, cols, cmat.T)
+    else:
+        onehot = ss.csr_matrix((np.ones(n_fg), (np.arange(n_fg), cols)), shape=(n_fg, n_red))
+        a_mat = np.asarray((onehot.T @ cmat.T).T)
     if backend == "exact":
         sol = None
         if on_device:
