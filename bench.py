@@ -96,7 +96,7 @@ def reference_arm(args) -> None:
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _emit(line)
 
 
 def workload_config(frames_per_gpu: int) -> dict:
@@ -158,8 +158,30 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- GPU arm
+_REAL_STDOUT = None
+
+
+def _quiet_stdout() -> None:
+    """The contract is ONE JSON line on stdout: route everything libraries print to fd 1 (NCCL's
+    version banner, ...) to stderr and keep the real stdout for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main() -> None:
     args = parse()
+    _quiet_stdout()
     if args.impl == "reference":
         reference_arm(args)
         return
@@ -317,7 +339,7 @@ def main() -> None:
             "config": workload_config(T), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
