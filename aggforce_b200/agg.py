@@ -19,7 +19,7 @@ import torch
 from . import _engine
 from .constraints import Constraints, guess_pairwise_constraints
 from .map import LinearMap, SeperableTMap, TMap
-from .qp import qp_linear_map
+from .qp import constraint_aware_uni_map, qp_linear_map
 from .trajectory import Trajectory
 
 PROJECT_FORCES_CNSTR_AUTO: Final = "auto"
@@ -82,8 +82,9 @@ def project_forces(
     if isinstance(coord_map, LinearMap) and coords is not None:
         if method is qp_linear_map:  # [Gram][coordinate map] | host QP
             _engine.defer(lambda: early.update(launch=coord_map._launch(coords_in)))
-        else:  # runs while the host (or a later kernel of the method) builds the force map
+        elif method is constraint_aware_uni_map:  # runs while the host builds the uniform map
             early["launch"] = coord_map._launch(coords_in)
+        # other methods return maps that are applied as a whole (featurised / augmented): nothing to hoist
     try:
         traj_map: TMap = method(
             traj=Trajectory(coords=_Shared(coords, coords_in), forces=_Shared(forces, forces_in)),
