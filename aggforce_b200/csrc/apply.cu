@@ -198,7 +198,6 @@ struct DenseSmallParams {
 };
 
 constexpr int kApplyConsumers = AGF_APPLY_TEAMS;
-constexpr int kApplyThreads = (kApplyConsumers + 1) * 32;
 constexpr int kOctet = 8;
 constexpr int kMaxStages = 16;
 

@@ -24,7 +24,6 @@
 namespace agf {
 
 constexpr int kFgThreads = 256;
-constexpr int kFgWarps = 8;
 constexpr int kFgBlock = 128;   // feature columns per block
 constexpr int kFgStride = 132;  // panel stride (conflict-free DMMA fragment loads)
 constexpr int kFgKF = 8;        // frames per chunk -> 24 panel rows, 6 k-steps
