@@ -7,13 +7,14 @@ raises.  Build the library with ``python -m aggforce_b200.csrc.build`` (or
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 from typing import Optional
 
 F32, F64 = 0, 1
 
 _LIB: Optional[C.CDLL] = None
-LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libagf_b200.so"
+LIB_PATH = Path(os.environ.get("AGF_B200_LIB") or Path(__file__).resolve().parent / "csrc" / "libagf_b200.so")
 
 _vp, _i32, _i64, _u64, _dbl, _flt = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_double, C.c_float
 

@@ -20,6 +20,9 @@
 #include "frame_pipe.cuh"
 #include "panel.cuh"
 
+#ifndef AGF_TRI_UNROLL
+#define AGF_TRI_UNROLL 3
+#endif
 #ifndef AGF_SYRK_WAVES
 #define AGF_SYRK_WAVES 12
 #endif
@@ -31,6 +34,7 @@ namespace agf {
 
 constexpr int kGramThreads = 256;
 constexpr int kGramWarps = 8;
+constexpr int kTriUnroll = AGF_TRI_UNROLL;  // k-steps of the triangular sweep unrolled together
 constexpr int kTriMmaWarps = AGF_TRI_MMA_WARPS;  // MMA warps of the single-block kernel (tile plans below)
 constexpr int kBlockCols = 128;  // reduced columns per block
 constexpr int kStride = 132;     // panel row stride in doubles (132 % 16 == 4: conflict free)
@@ -106,7 +110,7 @@ struct TriTiles {
 // One chunk: every k-step loads the NT fragments once and feeds this warp's tiles.
 template <int NT, int W, int KSTEPS>
 __device__ __forceinline__ void tri_sweep(const double* __restrict__ lane_panel, double (&acc)[kMaxTriSlots][2]) {
-#pragma unroll 3
+#pragma unroll kTriUnroll
   for (int kk = 0; kk < KSTEPS; ++kk) {
     const double* pk = lane_panel + kk * 4 * kStride;
     double frag[NT];
