@@ -140,8 +140,8 @@ def test_map_apply_ws_nan_protocol():
 
 
 @pytest.mark.parametrize("slab_chunks", [1, 2, 1000])
-@pytest.mark.parametrize("drop_last", [True, False])
-def test_gram_feat_ws_matches_fused_kernel_and_oracle(slab_chunks, drop_last):
+@pytest.mark.parametrize("drop_last,in_dtype", [(True, np.float32), (False, np.float32), (True, np.float64)])
+def test_gram_feat_ws_matches_fused_kernel_and_oracle(slab_chunks, drop_last, in_dtype):
     from aggforce_b200 import LinearMap, _engine, _lib
     from aggforce_b200.qp.featlinearmap import id_feat
     from aggforce_b200.synth import chignolin_topology, synth_trajectory_host
@@ -158,19 +158,20 @@ def test_gram_feat_ws_matches_fused_kernel_and_oracle(slab_chunks, drop_last):
     ptr_, sites = _engine.csr_from_labels(labels, G)
     centers = np.linspace(0.0, 8.0 ** 0.5, nb) ** 2
     dev = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a, dtype=dt), device="cuda")  # noqa: E731
-    d_c, d_f = dev(coords, np.float32), dev(forces, np.float32)
+    d_c, d_f = dev(coords, in_dtype), dev(forces, in_dtype)
+    code = _lib.F32 if in_dtype == np.float32 else _lib.F64
     d_ptr, d_sites = dev(ptr_, np.int32), dev(sites, np.int32)
     d_bptr, d_bsites = dev(np.arange(len(beads) + 1), np.int32), dev(beads, np.int32)
     d_bw, d_cent = dev(np.ones(len(beads)), np.float64), dev(centers, np.float64)
     common = (_p(d_ptr), _p(d_sites), G, n_ch, _p(d_bptr), _p(d_bsites), _p(d_bw), len(beads), _p(d_cent), nb, 1.0,
               1e-3, kbt)
     fused = torch.zeros((len(beads), n_feat, n_feat), dtype=torch.float64, device="cuda")
-    _lib.call("agf_gram_feat", _p(d_c), _p(d_f), _lib.F32, n_frames, topo.n_sites, *common, _p(fused), _stream())
+    _lib.call("agf_gram_feat", _p(d_c), _p(d_f), code, n_frames, topo.n_sites, *common, _p(fused), _stream())
     _lib.call("agf_symmetrize_batch", _p(fused), n_feat, len(beads), _stream())
     packed = torch.zeros_like(fused)
     n_blocks = (n_feat + 127) // 128
     ws = torch.empty(slab_chunks * len(beads) * n_blocks * PANEL_BYTES, dtype=torch.uint8, device="cuda")
-    _lib.call("agf_gram_feat_ws", _p(d_c), _p(d_f), _lib.F32, n_frames, topo.n_sites, *common, _p(packed), _p(ws),
+    _lib.call("agf_gram_feat_ws", _p(d_c), _p(d_f), code, n_frames, topo.n_sites, *common, _p(packed), _p(ws),
               C.c_size_t(ws.numel()), _stream())
     _lib.call("agf_symmetrize_batch", _p(packed), n_feat, len(beads), _stream())
     a, b = packed.cpu().numpy(), fused.cpu().numpy()
@@ -209,3 +210,34 @@ def test_large_fit_uses_device_solve_and_matches_oracle():
     f0 = forces[:40]
     assert abs(np.mean(oracle.apply_map(f0, w0) ** 2) - np.mean(oracle.apply_map(f0, ref0) ** 2)) < 1e-6 * max(
         1.0, np.mean(oracle.apply_map(f0, ref0) ** 2))
+
+
+@pytest.mark.parametrize("in_dtype", [np.float32, np.float64])
+def test_slice_map_kernel(in_dtype):
+    """agf_map_apply_slice (one site per bead): values, f32 maps, residual sum, NaN protocol."""
+    from aggforce_b200 import LinearMap
+
+    rng = np.random.default_rng(11)
+    n_fg, beads = 60, [3, 17, 18, 59, 0]
+    x = rng.normal(0, 20, size=(1031, n_fg, 3)).astype(in_dtype)
+    lm = LinearMap([[b] for b in beads], n_fg_sites=n_fg)
+    out, sumsq = lm.apply_with_sumsq(x)
+    assert out.dtype == np.float64 and np.array_equal(out, x[:, beads, :].astype(np.float64))
+    assert abs(sumsq / float((out ** 2).sum()) - 1) < 1e-12
+    w = np.zeros((len(beads), n_fg))
+    w[np.arange(len(beads)), beads] = [0.5, -2.0, 1.0, 3.0, 1e-9]
+    scaled = LinearMap(w)(x)
+    assert rel_fro(scaled, oracle.apply_map(x, w)) < 1e-14
+    if in_dtype == np.float32:
+        out32 = LinearMap(w.astype(np.float32))(x)
+        assert out32.dtype == np.float32 and rel_fro(out32, oracle.apply_map(x, w)) < 1e-6
+    xn = x.copy()
+    xn[5, 7, :] = np.nan  # unreferenced site: ignored
+    xn[9, 0, 1] = np.nan  # referenced with weight 1e-9 < atol: counts as 0
+    clean = np.nan_to_num(xn, nan=0.0)
+    assert rel_fro(LinearMap(w)(xn), oracle.apply_map(clean, w)) < 1e-14
+    xn[11, 17, 2] = np.nan  # referenced with weight -2: the result depends on the NaN
+    with pytest.raises(ValueError):
+        LinearMap(w)(xn)
+    plain = LinearMap(w, handle_nans=False)(xn)
+    assert np.isnan(plain[11, :, 2]).all()  # numpy semantics: 0 * NaN = NaN in every bead
