@@ -33,7 +33,9 @@ from ..map import CLAFTMap, CLAMap, LinearMap
 from ..trajectory import Trajectory
 from ..util import Curry
 from .gbfeat import GbSpec, gb_feat
-from .solver import DEFAULT_SOLVER_OPTIONS, SolverOptions, solve
+from .solver import DEFAULT_SOLVER_OPTIONS, SolverOptions, solve, solve_equality_qp_device
+
+_DEVICE_SOLVE_MIN = 512  # feature counts from which the per-bead QP is solved on the device
 
 KNAME_FEATS: Final = "feats"
 KNAME_DIVS: Final = "divs"
@@ -265,8 +267,9 @@ class _FusedContext:
         return (p(self.d_grp_ptr), p(self.d_grp_sites), self.n_groups, self.n_channels, p(self.d_bead_ptr),
                 p(self.d_bead_sites), p(self.d_bead_w), self.n_cg, p(self.d_centers), self.nb, self.width, self.clip)
 
-    def grams(self, coords: _engine.Frames, forces: _engine.Frames, kbt: float) -> np.ndarray:
-        """All-reduced per-bead Grams in the user's feature order, ``(n_cg, n_feat, n_feat)`` float64."""
+    def grams(self, coords: _engine.Frames, forces: _engine.Frames, kbt: float, on_device: bool = False):
+        """All-reduced per-bead Grams in the user's feature order, ``(n_cg, n_feat, n_feat)`` float64
+        (numpy, or a CUDA tensor with ``on_device``)."""
         nf = self.n_feat_kernel
         gram = torch.zeros((self.n_cg, nf, nf), dtype=torch.float64, device=_engine.device())
         pc, pf = coords.pieces(), forces.pieces()
@@ -282,6 +285,11 @@ class _FusedContext:
                       _engine.stream_ptr())
         _engine.allreduce_sum_(gram)
         _lib.call("agf_symmetrize_batch", _engine.ptr(gram), nf, self.n_cg, _engine.stream_ptr())
+        if on_device:
+            if np.array_equal(self.columns, np.arange(nf)):
+                return gram
+            sel = torch.as_tensor(self.columns, device=gram.device)
+            return gram[:, sel][:, :, sel].contiguous()
         host = _engine.to_host(gram)
         return host[:, self.columns][:, :, self.columns]
 
@@ -375,7 +383,9 @@ def _fit_fused(traj, coord_map, featurizer, plan, kbt, n_constraint_frames, cons
                l2_regularization, constraint_frames) -> CLAFTMap:
     ctx = _FusedContext(coord_map, constraints, plan)
     coords, forces = _engine.Frames(traj.coords), _engine.Frames(traj.forces)
-    grams = ctx.grams(coords, forces, kbt)
+    backend = dict(solver_args or {}).get("backend", "exact")
+    on_device = backend == "exact" and ctx.columns.size >= _DEVICE_SOLVE_MIN
+    grams = ctx.grams(coords, forces, kbt, on_device=on_device)  # large problems never leave the device
     n_feat = grams.shape[1]
     coefs = []
     for bead in range(coord_map.n_cg_sites):
@@ -383,10 +393,19 @@ def _fit_fused(traj, coord_map, featurizer, plan, kbt, n_constraint_frames, cons
         a_mat = ctx.constraint_rows(coords, bead, frames)
         target = np.zeros((len(frames), coord_map.n_cg_sites))
         target[:, bead] = 1
-        qp_mat = grams[bead]
-        if l2_regularization > 0:
-            qp_mat = qp_mat + l2_regularization * np.eye(n_feat)
-        params = solve(qp_mat, a_mat, target.reshape(-1), solver_args)
+        params = None
+        if on_device:
+            qp_dev = grams[bead].clone()
+            if l2_regularization > 0:
+                qp_dev.diagonal().add_(l2_regularization)
+            params = solve_equality_qp_device(qp_dev, a_mat, target.reshape(-1))
+            qp_mat = None if params is not None else _engine.to_host(qp_dev)
+        else:
+            qp_mat = grams[bead]
+            if l2_regularization > 0:
+                qp_mat = qp_mat + l2_regularization * np.eye(n_feat)
+        if params is None:
+            params = solve(qp_mat, a_mat, target.reshape(-1), solver_args)
         if params is None:
             raise ValueError("Map optimization failed.")
         coefs.append(params)

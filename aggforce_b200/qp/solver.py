@@ -70,7 +70,9 @@ def solve_equality_qp_device(P, A, b) -> Optional[np.ndarray]:
     """Same closed form on the GPU for large problems: ``P`` is a float64 CUDA tensor
     (the Gram never leaves the device), one cuSOLVER Cholesky + multi-right-hand-side solves through
     ``torch.linalg``.  Returns ``None`` when ``P`` or the Schur complement is not numerically
-    positive definite -- the caller then falls back to :func:`solve_equality_qp` on the host."""
+    positive definite (or the solution misses the equality constraints) -- the caller then falls back
+    to :func:`solve_equality_qp` on the host.  A singular Schur complement (redundant equality rows, as
+    the featurised fit produces) is handled like the host path: least squares on the small system."""
     import torch
 
     a = torch.as_tensor(np.asarray(A, dtype=np.float64), device=P.device)
@@ -84,9 +86,12 @@ def solve_equality_qp_device(P, A, b) -> Optional[np.ndarray]:
     pia = torch.cholesky_solve(a.T.contiguous(), chol)  # P^-1 A'
     schur = a @ pia
     chol_s, info_s = torch.linalg.cholesky_ex(schur)
-    if int(info_s.item()) != 0:
-        return None
-    x = pia @ torch.cholesky_solve(rhs, chol_s)
+    if int(info_s.item()) == 0:
+        lam = torch.cholesky_solve(rhs, chol_s)
+    else:  # redundant equality rows: the small (n_rows x n_rows) system goes to the host's least squares
+        lam_h = np.linalg.lstsq(schur.cpu().numpy(), rhs.cpu().numpy(), rcond=None)[0]
+        lam = torch.as_tensor(lam_h, device=P.device)
+    x = pia @ lam
     resid = float((a @ x - rhs).abs().max().item()) if x.numel() else 0.0
     if not bool(torch.isfinite(x).all().item()) or resid > 1e-6 * max(1.0, float(rhs.abs().max().item())):
         return None
