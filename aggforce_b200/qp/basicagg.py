@@ -22,11 +22,11 @@ def constraint_aware_uni_map(
     (transitively) to one of them.  ``traj`` is ignored."""
     matrix = np.asarray(coord_map.standard_matrix)
     groups = merged_groups(set() if constraints is None else constraints)
+    group_of = {site: gi for gi, g in enumerate(groups) for site in g}  # merged groups are disjoint
     out = np.zeros_like(matrix)
     for bead, row in enumerate(matrix):
         members = set(np.nonzero(row)[0].tolist())
-        for g in groups:
-            if members.intersection(g):
-                members.update(g)
+        for gi in {group_of[m] for m in members if m in group_of}:
+            members.update(groups[gi])
         out[bead, sorted(members)] = 1.0
     return SeperableTMap(coord_map=coord_map, force_map=LinearMap(out))
