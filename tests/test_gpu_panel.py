@@ -241,3 +241,34 @@ def test_slice_map_kernel(in_dtype):
         LinearMap(w)(xn)
     plain = LinearMap(w, handle_nans=False)(xn)
     assert np.isnan(plain[11, :, 2]).all()  # numpy semantics: 0 * NaN = NaN in every bead
+
+
+def test_config4_shape_properties():
+    """BASELINE config 4 shape (5 000 atoms, 500 beads, n_red 2 600): oracle parity on a sub-sample
+    and size-independent properties on more frames -- Gram additivity over frame shards, linearity
+    of the packed-panel application, constraints recovered exactly."""
+    from aggforce_b200 import LinearMap, _engine, guess_pairwise_constraints
+    from aggforce_b200.qp.qplinear import force_gram, reduced_columns
+    from aggforce_b200.synth import protein_like_topology, synth_trajectory_device
+
+    topo = protein_like_topology(500)
+    coords, forces = synth_trajectory_device(topo, 3000, seed=17)
+    cons = topo.xh_constraints
+    cols = reduced_columns(topo.n_sites, cons)
+    n_red = int(cols.max()) + 1
+    assert (topo.n_sites, n_red) == (5000, 2600)
+    sub = forces[:48].cpu().numpy()
+    g_sub, _ = force_gram(forces[:48], topo.n_sites, cons)
+    assert rel_fro(g_sub, oracle.gram_linear(sub, cons)) < 1e-9
+    whole, _ = force_gram(forces, topo.n_sites, cons)
+    parts = sum(force_gram(forces[a:b], topo.n_sites, cons)[0] for a, b in [(0, 1001), (1001, 2050), (2050, 3000)])
+    assert rel_fro(whole, parts) < 1e-12 and np.array_equal(whole, whole.T)
+    rng = np.random.default_rng(2)
+    w = rng.normal(size=(500, n_red))[:, cols]
+    lm = LinearMap(w)
+    out = lm(forces)
+    assert rel_fro(out[:16].cpu().numpy(), oracle.apply_map(forces[:16].cpu().numpy(), w)) < 1e-12
+    assert rel_fro((-1.5 * lm)(forces).cpu().numpy(), -1.5 * out.cpu().numpy()) < 1e-12
+    mapped, sumsq = lm.apply_with_sumsq(forces)
+    assert abs(sumsq / float((mapped.double() ** 2).sum().item()) - 1) < 1e-12
+    assert guess_pairwise_constraints(coords) == cons
