@@ -38,18 +38,37 @@ def _fingerprint() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile every source to an object file (in parallel) and link the shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+
     fp = _fingerprint()
     if not force and LIB.exists() and STAMP.exists() and STAMP.read_text() == fp:
         return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", str(LIB), *[str(CSRC / s) for s in SOURCES], "-lcudart"]
+    nvcc = _nvcc()
+    objdir = CSRC / "_build"
+    objdir.mkdir(exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "--shared"]
+
+    def compile_one(name: str):
+        obj = objdir / (Path(name).stem + ".o")
+        cmd = [nvcc, *compile_flags, "-c", "-o", str(obj), str(CSRC / name)]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        return name, obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    failed = [(n, r) for n, _, r in results if r.returncode != 0]
+    if failed:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(f"[{n}]\n{r.stdout}{r.stderr}" for n, r in failed))
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
+        for _, _, r in results:
+            print(r.stderr)
+    link = subprocess.run([nvcc, "--shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+                           "-o", str(LIB), *[str(o) for _, o, _ in results], "-lcudart"],
+                          capture_output=True, text=True)
+    if link.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + link.stdout + link.stderr)
     STAMP.write_text(fp)
     return LIB
 
