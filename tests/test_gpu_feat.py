@@ -296,3 +296,19 @@ def test_staged_gauss_maps(topo, data):
     assert np.allclose(fmap[0].tmap.force_map.standard_matrix, np.hstack([np.eye(n_cg), np.eye(n_cg)]), atol=1e-4)
     of = fmap(traj)
     assert rel_fro(of.forces, y_cg) < 1e-4  # real mapped forces, noise forces cancelled
+
+
+def test_project_forces_with_gaussian_methods(topo, data):
+    """project_forces drives the noised maps like any other method (reference agg.py:120-128)."""
+    from aggforce_b200 import joptgauss_map, project_forces, stagedjoptgauss_map
+
+    coords, forces = data
+    cmap, cons = _cmap(topo), topo.xh_constraints
+    x_cg = oracle.apply_map(coords, cmap.standard_matrix)
+    for method in (joptgauss_map, stagedjoptgauss_map):
+        res = project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds=cons, method=method,
+                             var=0.2, kbt=KBT, seed=3, l2_regularization=1e2)
+        assert res["mapped_coords"].shape == (len(coords), 10, 3) and np.isfinite(res["mapped_forces"]).all()
+        assert abs((res["mapped_coords"] - x_cg).var() / 0.2 - 1) < 0.2
+        assert abs(res["residual"] - np.mean(res["mapped_forces"] ** 2)) < 1e-9 * res["residual"]
+        assert res["constraints"] == cons
