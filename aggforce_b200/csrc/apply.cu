@@ -18,7 +18,10 @@
 #include "panel.cuh"
 
 #ifndef AGF_APPLY_TEAMS
-#define AGF_APPLY_TEAMS 8
+#define AGF_APPLY_TEAMS 7
+#endif
+#ifndef AGF_APPLY_SCRATCH_BUFS
+#define AGF_APPLY_SCRATCH_BUFS 1  // 1: two named barriers per octet; 2: one barrier, 21 KB less for the ring
 #endif
 
 namespace agf {
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__((kApplyConsumers * SPLIT + 1) * 32, 1)
   off = (off + 127) / 128 * 128;
   constexpr int kAccDoubles = 3 * NT * 2;  // per lane
   double* s_scratch = reinterpret_cast<double*>(smem + off);  // [team][2][kAccDoubles][32], SPLIT == 2 only
-  if (SPLIT == 2) off += (size_t)kApplyConsumers * 2 * kAccDoubles * 32 * sizeof(double);
+  if (SPLIT == 2) off += (size_t)kApplyConsumers * AGF_APPLY_SCRATCH_BUFS * kAccDoubles * 32 * sizeof(double);
   TI* raw = reinterpret_cast<TI*>(smem + off);
   const int64_t frame_elems = (int64_t)p.n_sites * 3;
   const int64_t stage_elems = ((int64_t)kOctet * frame_elems * (int64_t)sizeof(TI) + 15) / 16 * 16 / (int64_t)sizeof(TI);
@@ -389,7 +392,8 @@ __global__ void __launch_bounds__((kApplyConsumers * SPLIT + 1) * 32, 1)
       }
       if (SPLIT == 2) {
         // combine the two halves: warp 1 of the team publishes, warp 0 adds and finishes the octet
-        double* scr = s_scratch + ((size_t)(team * 2 + (it & 1)) * kAccDoubles) * 32 + lane;
+        double* scr = s_scratch + ((size_t)(team * AGF_APPLY_SCRATCH_BUFS + (it & (AGF_APPLY_SCRATCH_BUFS - 1))) *
+                                   kAccDoubles) * 32 + lane;
         ++it;
         if (half == 1) {
 #pragma unroll
@@ -401,14 +405,18 @@ __global__ void __launch_bounds__((kApplyConsumers * SPLIT + 1) * 32, 1)
             }
         }
         asm volatile("bar.sync %0, 64;" ::"r"(1 + team) : "memory");
+        if (half == 0) {
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+              acc[d][n][0] += scr[((d * NT + n) * 2) * 32];
+              acc[d][n][1] += scr[((d * NT + n) * 2 + 1) * 32];
+            }
+        }
+        if (AGF_APPLY_SCRATCH_BUFS == 1)  // single buffer: warp 1 may not overwrite it before warp 0 has read it
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + team) : "memory");
         if (half == 1) continue;  // the raw stage is released by warp 0 (which may still redo it)
-#pragma unroll
-        for (int d = 0; d < 3; ++d)
-#pragma unroll
-          for (int n = 0; n < NT; ++n) {
-            acc[d][n][0] += scr[((d * NT + n) * 2) * 32];
-            acc[d][n][1] += scr[((d * NT + n) * 2 + 1) * 32];
-          }
       }
       if (nan_mode) {
         bool has_nan = false;
@@ -715,7 +723,7 @@ static size_t small_fixed_bytes(int n_ucol, int nnz, int n_cg) {
   size_t off = (size_t)xpad * su * sizeof(double) + (size_t)xpad * 16 + (size_t)(n_ucol + 1) * 4 + (size_t)nnz * 4;
   off = (off + 15) / 16 * 16 + 2 * kMaxStages * sizeof(uint64_t);
   off = (off + 127) / 128 * 128;
-  if (small_split(ntk) == 2) off += (size_t)kApplyConsumers * 2 * (3 * ntk * 2) * 32 * sizeof(double);
+  if (small_split(ntk) == 2) off += (size_t)kApplyConsumers * AGF_APPLY_SCRATCH_BUFS * (3 * ntk * 2) * 32 * sizeof(double);
   return off;
 }
 static bool small_fits(int n_sites, int n_ucol, int nnz, int n_cg, size_t elem) {
