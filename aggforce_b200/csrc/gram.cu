@@ -20,6 +20,9 @@
 #include "frame_pipe.cuh"
 #include "panel.cuh"
 
+#ifndef AGF_TRI_FILL_WARPS
+#define AGF_TRI_FILL_WARPS 16
+#endif
 #ifndef AGF_TRI_UNROLL
 #define AGF_TRI_UNROLL 3
 #endif
@@ -209,7 +212,7 @@ __device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
 //   panel_full[b] : fill warps finished panel b                (1 arrival, after a named barrier)
 //   panel_empty[b]: all 8 MMA warps finished sweeping panel b  (8 arrivals)
 constexpr int kMmaWarps = kTriMmaWarps;
-constexpr int kFillWarps = 8;
+constexpr int kFillWarps = AGF_TRI_FILL_WARPS;
 constexpr int kTriThreads = (kMmaWarps + kFillWarps) * 32;
 constexpr int kFillThreads = kFillWarps * 32;
 constexpr int kRawStages = 3;
