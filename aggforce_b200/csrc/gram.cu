@@ -24,7 +24,7 @@
 #define AGF_TRI_FILL_WARPS 16
 #endif
 #ifndef AGF_TRI_UNROLL
-#define AGF_TRI_UNROLL 3
+#define AGF_TRI_UNROLL 2
 #endif
 #ifndef AGF_SYRK_WAVES
 #define AGF_SYRK_WAVES 12
