@@ -9,8 +9,11 @@ Parity status (see DESIGN.md "Oracle"):
     id-feature Gram and the equality-QP solve are PINNED: ``tests/golden/make_golden.py``
     ran the unmodified reference (``/root/reference/src`` behind a ``qpsolvers`` shim)
     and the committed fixtures under ``tests/golden/`` hold its outputs.
-  * ``gb_feat`` (JAX) and ``joptgauss_map`` (JAX) could not be executed in the build
-    container (no jax): for those two the oracle is a line-by-line restatement whose
-    derivative is checked against finite differences -- **parity unpinned**.
+  * ``gb_feat``, ``JCondNormal`` / ``joptgauss_map`` and the ``jaxmapval`` projections (the JAX half)
+    are PINNED to the reference's own modules executed unmodified behind a torch-backed ``jax``
+    stand-in (``tests/golden/make_golden_jax.py``, ``tests/golden/jax_shim``; real jax/jaxlib are
+    not installable here): fixtures ``ref_gbfeat.npz``, ``ref_jcondnormal.npz``, ``ref_mapval.npz``.
+    The stand-in runs float32 on torch CPU, so those comparisons carry a float32 tolerance, and the
+    reference's threefry noise stream is replaced by recorded draws.
 """
 from .ref_numpy import *  # noqa: F401,F403

@@ -36,6 +36,11 @@ __all__ = [
     "feat_constraint_rows",
     "feat_map_apply",
     "gauss_augment",
+    "gauss_log_gradient",
+    "sq_gaussian_forces",
+    "mscg_ip",
+    "random_force_proj",
+    "random_residual_shift",
 ]
 
 
@@ -335,6 +340,7 @@ def gb_features(
     dist_power: float = 0.5,
     clip: float = 1e-3,
     drop_last_channel: bool = True,
+    div_method: str = "basic",
 ) -> Tuple[np.ndarray, np.ndarray]:
     """Literal float64 restatement of ``gb_feat`` for ONE bead.
 
@@ -353,6 +359,14 @@ def gb_features(
         ``sum_a g_k(d_a)`` w.r.t. every site with the bead held fixed (Q6), placed in the
         differentiated site's channel and summed over sites.  Because the smear rows sum
         to one this is ``m_ch * g_k'(d_ch) * (p_ch - R)/d_ch``.
+
+    A smeared site that coincides with the bead (``d = 0``: a bead atom in no constraint group
+    under a slice map) has an undefined direction.  Pinned against the reference run behind the
+    jax shim (``tests/golden/ref_gbfeat.npz``): with ``div_method="basic"`` (forward mode, :525-543)
+    the NaN stays in the coincident site's own channel -- and vanishes when that channel is the
+    dropped one; with ``div_method="reorder"`` (reverse mode, :544-565, the reference default) the
+    NaN cotangent of the coincident site is multiplied by the zeros of the smear matrix in the
+    transposed contraction, ``0 * NaN = NaN``, and the whole frame's divergence is NaN.
     """
     x = np.asarray(points, dtype=np.float64)
     cm = np.asarray(cmap_matrix, dtype=np.float64)
@@ -386,6 +400,10 @@ def gb_features(
             continue
         feats[:, a, ch * n_basis : (ch + 1) * n_basis] = g[:, a, :]
         divs[:, ch * n_basis : (ch + 1) * n_basis, :] += site_grad[:, a, :, :]
+    if div_method == "reorder":
+        divs[(dist == 0.0).any(axis=1)] = np.nan
+    elif div_method != "basic":
+        raise ValueError("Unknown method for jacobian calculation.")
     return feats, divs
 
 
@@ -528,3 +546,79 @@ def gauss_augment(
     full_coords = np.concatenate([x, y], axis=1)
     full_forces = np.concatenate([f + kbt * grad_x, kbt * grad_y], axis=1)
     return full_coords, full_forces
+
+
+def gauss_log_gradient(
+    source: np.ndarray, generated: np.ndarray, premap_matrix: Optional[np.ndarray], var: float
+) -> Tuple[np.ndarray, np.ndarray]:
+    """Log-gradients of ``g(y|x) = N(y; A x, var I)`` w.r.t. ``x`` and ``y``.
+
+    Closed form of what ``JCondNormal.log_gradient`` obtains by autodiff
+    (src/aggforce/trajectory/jaxgausstraj.py:77-96, 263-284): ``grad_y = -(y - A x)/var``,
+    ``grad_x = A'(y - A x)/var``; ``premap_matrix=None`` is the identity premap
+    (src/aggforce/trajectory/simplegausstraj.py:108-110).  Returns ``(grad_x, grad_y)`` in the
+    reference's order (source first).
+    """
+    x = np.asarray(source, dtype=np.float64)
+    y = np.asarray(generated, dtype=np.float64)
+    if premap_matrix is None:
+        resid = y - x
+        return resid / var, -resid / var
+    a = np.asarray(premap_matrix, dtype=np.float64)
+    resid = y - np.einsum("cf,tfd->tcd", a, x)
+    return np.einsum("cf,tcd->tfd", a, resid) / var, -resid / var
+
+
+# --------------------------------------------------------------------------------------
+# validation projections (SURVEY 8f-4; src/aggforce/jaxmapval.py)
+# --------------------------------------------------------------------------------------
+def sq_gaussian_forces(positions: np.ndarray, offset: float, width: float) -> np.ndarray:
+    """Forces of the potential ``E = sum_{i,j} exp(-((|x_j - x_i|^2 - offset)/width)^2)``.
+
+    jaxmapval.py:365-401: one unclipped Gaussian of every entry of the full SQUARED distance matrix
+    (both orders of each pair and the zero diagonal, jaxutil.py:168-176), summed per frame, and
+    ``-dE/dx`` by autodiff.  Closed form: each unordered pair appears twice, so
+    ``F_i = -4 sum_j G'(s_ij) (x_i - x_j)`` with ``G'(s) = -2 (s - offset)/width^2 * G(s)``.
+    """
+    x = np.asarray(positions, dtype=np.float64)
+    disp = x[:, :, None, :] - x[:, None, :, :]  # [t, i, j] = x_i - x_j
+    s = (disp * disp).sum(-1)
+    z = (s - offset) / width
+    gprime = -2.0 * z / width * np.exp(-(z * z))
+    return -4.0 * np.einsum("tij,tijd->tid", gprime, disp)
+
+
+def rsqpg_offset(inner: float, outer: float, width: float, randg, sq_args: bool = True) -> Tuple[float, float]:
+    """``(offset, width)`` as ``rsqpg_forces`` draws / squares them (jaxmapval.py:131-139)."""
+    if sq_args:
+        outer, inner, width = outer**2, inner**2, width**2
+    return randg.random() * (outer - inner) + inner, width
+
+
+__all__.append("rsqpg_offset")
+
+
+def mscg_ip(forces: np.ndarray, funcs: np.ndarray) -> float:
+    """``sum(funcs * forces) / n_steps`` (jaxmapval.py:359-360)."""
+    f = np.asarray(forces, dtype=np.float64)
+    return float((np.asarray(funcs, dtype=np.float64) * f).sum() / f.shape[0])
+
+
+def random_force_proj(coords, forces, n_samples, randg, inner, outer, width, sq_args=True) -> List[float]:
+    """Projections of ``forces`` on ``n_samples`` random Gaussian force fields (jaxmapval.py:309-319)."""
+    vals = []
+    for _ in range(n_samples):
+        off, w = rsqpg_offset(inner, outer, width, randg, sq_args)
+        vals.append(mscg_ip(forces, sq_gaussian_forces(coords, off, w)))
+    return vals
+
+
+def random_residual_shift(coords, forces, n_samples, randg, inner, outer, width, sq_args=True) -> List[float]:
+    """``mean((F - G_s)^2) - mean(F^2)`` per random force field ``G_s`` (jaxmapval.py:227-237)."""
+    f = np.asarray(forces, dtype=np.float64)
+    base = float(np.mean(f**2))
+    vals = []
+    for _ in range(n_samples):
+        off, w = rsqpg_offset(inner, outer, width, randg, sq_args)
+        vals.append(float(np.mean((f - sq_gaussian_forces(coords, off, w)) ** 2)) - base)
+    return vals

@@ -186,3 +186,178 @@ def test_apply_nan_protocol(golden):
     with pytest.raises(ValueError):
         oracle.apply_map_nan_protocol(ref["pos_nan"], dense)
     assert np.allclose(oracle.apply_map(ref["pos"], dense), ref["mapped"], rtol=1e-13)
+
+
+# --------------------------------------------------------------------------------------
+# the JAX half: fixtures from the reference's own jaxfeat / jaxgausstraj / jgauss / jaxmapval run
+# behind tests/golden/jax_shim (tests/golden/make_golden_jax.py).  float32 reference -> float32 bars.
+# --------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gbfix(golden):
+    return dict(np.load(golden / "ref_gbfeat.npz"))
+
+
+@pytest.fixture(scope="module")
+def jcn(golden):
+    return dict(np.load(golden / "ref_jcondnormal.npz"))
+
+
+F32_ABS = 5e-6  # float32 features are O(1); divergences O(1)
+
+
+@pytest.mark.parametrize("nb", [4, 7])
+@pytest.mark.parametrize("dm", ["reorder", "basic"])
+def test_gb_features_match_reference_small(gbfix, nb, dm):
+    """Slice map on the 12-site system: bead 1 sits on site 4, the only site of the LARGEST label
+    (its feature block is dropped, Q5) and coincides with its own smeared position (Q6)."""
+    x, ids = gbfix["small_x"], gbfix["small_ids"]
+    cons = [tuple(p) for p in gbfix["small_cons"]]
+    cm = gbfix["small_cmap_slice"]
+    assert ids[4] == ids.max() and (ids == ids.max()).sum() == 1
+    feats, divs = gbfix[f"small_slice_nb{nb}_{dm}_feats"], gbfix[f"small_slice_nb{nb}_{dm}_divs"]
+    assert feats.shape == (3, 6, 12, nb * ids.max()) and divs.shape == (3, 6, nb * ids.max(), 3)
+    for bead in range(3):
+        of, od = oracle.gb_features(x, cm, cons, ids, bead, outer=8, inner=0, n_basis=nb, width=1.0, div_method=dm)
+        assert np.abs(feats[bead] - of).max() < F32_ABS
+        assert np.abs(feats[bead][:, 4]).max() == 0.0  # top-label site: all-zero feature row in the reference
+        assert np.array_equal(np.isnan(divs[bead]), np.isnan(od))
+        ok = ~np.isnan(od)
+        assert not ok.any() or np.abs(divs[bead][ok] - od[ok]).max() < F32_ABS
+    # the two readings of Q6 for the coincident bead: reverse mode poisons the frame, forward mode does not
+    assert np.isnan(gbfix[f"small_slice_nb{nb}_reorder_divs"][1]).all()
+    assert not np.isnan(gbfix[f"small_slice_nb{nb}_basic_divs"][1]).any()
+    # keeping the last channel (our switch) only APPENDS a block: the reference part is unchanged
+    of_keep, _ = oracle.gb_features(x, cm, cons, ids, 0, outer=8, inner=0, n_basis=nb, width=1.0,
+                                    drop_last_channel=False)
+    of_drop, _ = oracle.gb_features(x, cm, cons, ids, 0, outer=8, inner=0, n_basis=nb, width=1.0)
+    assert np.array_equal(of_keep[..., : of_drop.shape[-1]], of_drop) and np.abs(of_keep[:, 4, -nb:]).max() > 0
+
+
+def test_gb_features_match_reference_com_and_alt_parameters(gbfix):
+    x, ids = gbfix["small_x"], gbfix["small_ids"]
+    cons = [tuple(p) for p in gbfix["small_cons"]]
+    cm = gbfix["small_cmap_com"]
+    feats, divs = gbfix["small_com_nb7_basic_feats"], gbfix["small_com_nb7_basic_divs"]
+    for bead in range(3):
+        of, od = oracle.gb_features(x, cm, cons, ids, bead, outer=8, inner=0, n_basis=7, width=1.0)
+        assert np.abs(feats[bead] - of).max() < F32_ABS
+        # a centre-of-group bead coincides with its group's smeared position up to float32 rounding: the
+        # direction of that channel's divergence is rounding noise in the reference -- compare the others
+        ch = int(ids[np.argmax(cm[bead] > 0)])
+        keep = np.ones(od.shape[1], dtype=bool)
+        if ch < ids.max():
+            keep[ch * 7 : (ch + 1) * 7] = False
+        assert np.abs(divs[bead][:, keep] - od[:, keep]).max() < F32_ABS
+    cm = gbfix["small_cmap_slice"]
+    for bead in (0, 2):
+        of, od = oracle.gb_features(x, cm, cons, ids, bead, outer=6.5, inner=0.5, n_basis=5, width=0.7, dist_power=1.0)
+        assert np.abs(gbfix["small_alt_feats"][bead] - of).max() < F32_ABS
+        assert np.abs(gbfix["small_alt_divs"][bead] - od).max() < 2e-5
+
+
+def test_gb_features_match_reference_cln025(gbfix, small_cln):
+    from aggforce_b200.synth import chignolin_topology
+
+    topo = chignolin_topology()
+    coords = small_cln["coords"][:4]
+    cons = pairs_to_set(small_cln["cons10"])
+    cm = np.zeros((10, 175))
+    cm[np.arange(10), topo.bead_atoms] = 1
+    ids = gbfix["cln_ids"]
+    assert ids.max() == 96
+    for bead in (0, 7):
+        of, od = oracle.gb_features(coords, cm, cons, ids, bead, outer=8, inner=0, n_basis=7, width=1.0,
+                                    div_method="reorder")
+        assert gbfix[f"cln_feats_b{bead}"].shape == (4, 175, 672)
+        assert np.abs(gbfix[f"cln_feats_b{bead}"] - of).max() < F32_ABS
+        assert np.abs(gbfix[f"cln_divs_b{bead}"] - od).max() < 2e-5
+
+
+def test_featurised_fit_matches_reference(gbfix):
+    """qp_feat_linear_map(Multifeaturize([id_feat, Curry(gb_feat, n_basis=4)])) of the reference on a
+    40-site sub-system: Gram (float32 in the reference), equality rows, coefficients, mapped forces."""
+    c, f, ids = gbfix["fit_coords"], gbfix["fit_forces"], gbfix["fit_ids"]
+    cons = pairs_to_set(gbfix["fit_cons"])
+    beads = gbfix["fit_beads"]
+    cm = np.zeros((len(beads), c.shape[1]))
+    cm[np.arange(len(beads)), beads] = 1
+    kbt, l2 = float(gbfix["fit_kbt"]), float(gbfix["fit_l2"])
+    idf, idd = oracle.id_features(len(c), ids)
+    feats, divs, coefs = [], [], []
+    for bead in range(len(beads)):
+        gf, gd = oracle.gb_features(c, cm, cons, ids, bead, outer=8.0, inner=0.0, n_basis=4, width=1.0)
+        ph, dv = np.concatenate([idf, gf], axis=2), np.concatenate([idd, gd], axis=1)
+        p = oracle.feat_gram(f, ph, dv, kbt, l2)
+        assert p.shape == gbfix["fit_P"][bead].shape
+        assert rel_fro(p, gbfix["fit_P"][bead]) < 2e-6  # the reference accumulates this Gram in float32
+        a, b = oracle.feat_constraint_rows(ph, cm, bead, gbfix["fit_frame_choice"])
+        assert np.abs(a - gbfix["fit_A"][bead]).max() < F32_ABS and np.array_equal(b, gbfix["fit_b"][bead])
+        # the fitted coefficients amplify the Gram's float32 error: check through the solver on the
+        # reference's own (P, A, b), and the mapped forces with the reference's coefficients
+        sol = oracle.solve_equality_qp(gbfix["fit_P"][bead], gbfix["fit_A"][bead], gbfix["fit_b"][bead])
+        assert rel_fro(sol, gbfix["fit_coefs"][bead]) < 1e-6
+        feats.append(ph), divs.append(dv), coefs.append(gbfix["fit_coefs"][bead])
+    mapped = oracle.feat_map_apply(f, feats, divs, coefs)
+    assert rel_fro(mapped, gbfix["fit_mapped_forces"]) < 5e-6
+
+
+@pytest.mark.parametrize("name", ["slice", "avg"])
+def test_jcondnormal_matches_reference(jcn, name):
+    src, var, a = jcn["source"], float(jcn["var"]), jcn[f"{name}_matrix"]
+    gen, z = jcn[f"{name}_generated"], jcn[f"{name}_z"]
+    # sample: y = A x + sqrt(var) z with the recorded standard-normal draw
+    y = np.einsum("cf,tfd->tcd", a, src.astype(np.float64)) + np.sqrt(var) * z
+    assert np.abs(gen - y).max() < 1e-5
+    gx, gy = oracle.gauss_log_gradient(src, gen, a, var)
+    assert np.abs(jcn[f"{name}_lg_source"] - gx).max() < 2e-5 * max(1.0, np.abs(gx).max())
+    assert np.abs(jcn[f"{name}_lg_generated"] - gy).max() < 2e-5 * max(1.0, np.abs(gy).max())
+
+
+def test_jcondnormal_identity_premap(jcn):
+    gx, gy = oracle.gauss_log_gradient(jcn["source"][:, :6], jcn["ident_generated"], None, float(jcn["var"]))
+    assert np.abs(jcn["ident_lg_source"] - gx).max() < 2e-5 and np.abs(jcn["ident_lg_generated"] - gy).max() < 2e-5
+
+
+def test_joptgauss_matches_reference(jcn, gbfix):
+    """joptgauss_map of the reference end to end (jgauss.py:114-138), with the noise it drew."""
+    c, f = gbfix["fit_coords"], gbfix["fit_forces"]
+    cons = pairs_to_set(jcn["jopt_cons"])
+    beads = jcn["jopt_beads"]
+    n_fg, n_cg = c.shape[1], len(beads)
+    cm = np.zeros((n_cg, n_fg))
+    cm[np.arange(n_cg), beads] = 1
+    var, kbt, l2 = float(jcn["jopt_var"]), float(jcn["jopt_kbt"]), float(jcn["jopt_l2"])
+    xa, fa = oracle.gauss_augment(c, f, cm, var, kbt, jcn["jopt_z_fit"])
+    p = oracle.gram_linear(fa, cons) + l2 * oracle.l2_linear_term(n_fg + n_cg, cons)
+    assert rel_fro(p, jcn["jopt_P"]) < 5e-6  # float32 augmented forces in the reference
+    aug_cm = np.zeros((n_cg, n_fg + n_cg))
+    aug_cm[np.arange(n_cg), n_fg + np.arange(n_cg)] = 1
+    assert np.array_equal(aug_cm, jcn["jopt_coord_matrix"])
+    w = oracle.qp_linear_weights(fa, aug_cm, cons, l2)
+    assert rel_fro(w, jcn["jopt_W"]) < 1e-4
+    xa2, fa2 = oracle.gauss_augment(c, f, cm, var, kbt, jcn["jopt_z_apply"])
+    assert rel_fro(oracle.apply_map(xa2, aug_cm), jcn["jopt_mapped_coords"]) < 1e-6
+    assert rel_fro(oracle.apply_map(fa2, jcn["jopt_W"]), jcn["jopt_mapped_forces"]) < 1e-5
+
+
+def test_validation_projections_match_reference(golden):
+    mvf = dict(np.load(golden / "ref_mapval.npz"))
+    c, f = mvf["cg_coords"], mvf["cg_forces"]
+    for s in range(3):
+        off, w = oracle.rsqpg_offset(6.0, 12.0, 0.5, np.random.default_rng(s))
+        assert abs(off - mvf["rsqpg_offsets"][s]) < 1e-12
+        ref = mvf["rsqpg_forces"][s]
+        assert np.abs(oracle.sq_gaussian_forces(c, off, w) - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+    off, w = oracle.rsqpg_offset(30.0, 80.0, 9.0, np.random.default_rng(1), sq_args=False)
+    ref = mvf["rsqpg_forces_nosq"]
+    assert np.abs(oracle.sq_gaussian_forces(c, off, w) - ref).max() < 1e-4 * max(1.0, np.abs(ref).max())
+    kw = dict(inner=6.0, outer=12.0, width=0.5)
+    proj = oracle.random_force_proj(c, f, 16, np.random.default_rng(42100), **kw)
+    scale = np.abs(mvf["proj"]).max()
+    assert np.abs(np.asarray(proj) - mvf["proj"]).max() < 1e-4 * scale
+    assert abs(np.mean(proj) - mvf["proj_avg"]) < 1e-4 * scale
+    shift = oracle.random_residual_shift(c, f, 16, np.random.default_rng(42100), **kw)
+    # the reference subtracts two O(mean F^2) float numbers: absolute bar at that scale
+    bar = 1e-5 * float(np.mean(f.astype(np.float64) ** 2)) + 1e-4 * np.abs(mvf["shift"]).max()
+    assert np.abs(np.asarray(shift) - mvf["shift"]).max() < bar
+    assert abs(np.mean(shift) - mvf["shift_avg"]) < bar
