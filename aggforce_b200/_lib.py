@@ -44,6 +44,10 @@ SIGNATURES = {
                        _vp, _vp, C.c_int, _vp, _vp],
     "agf_gauss_augment": [_vp, _vp, C.c_int, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _dbl, _dbl, _vp, _u64,
                           C.c_uint32, _i64, _vp, _vp, _vp],
+    "agf_gauss_field_moments": [_vp, _vp, C.c_int, _i64, _i32, _vp, _i32, _dbl, _vp, _vp],
+    "agf_sq_gaussian_forces": [_vp, C.c_int, _i64, _i32, _dbl, _dbl, _vp, C.c_int, _vp],
+    "agf_probe_dmma": [_i32, _vp, _vp, _vp],
+    "agf_probe_read": [_vp, _i64, _vp, _vp],
     "agf_synth_frames": [_vp, _vp, _vp, _i32, _i64, _i64, _u64, _flt, _flt, _flt, _vp, _vp, _vp],
 }
 PLAIN = {"agf_version": (C.c_int, []), "agf_last_error": (C.c_char_p, []), "agf_device_sm_count": (C.c_int, []),

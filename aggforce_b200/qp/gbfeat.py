@@ -53,7 +53,8 @@ class GbSpec:
         return n_labels - 1 if self.drop_last_channel else n_labels
 
 
-def _materialise(points: torch.Tensor, cmap_row: torch.Tensor, labels: torch.Tensor, n_labels: int, spec: GbSpec):
+def _materialise(points: torch.Tensor, cmap_row: torch.Tensor, labels: torch.Tensor, n_labels: int, spec: GbSpec,
+                 div_method: str = DIVMETHOD_BASIC):
     """(feats (T, n, n_ch*nb), divs (T, n_ch*nb, 3)) in float64 on the device for one bead."""
     T, n, _ = points.shape
     nb, n_ch = spec.n_basis, spec.n_channels(n_labels)
@@ -77,6 +78,12 @@ def _materialise(points: torch.Tensor, cmap_row: torch.Tensor, labels: torch.Ten
         feats[:, site[keep], labels[keep] * nb + k] = g[:, labels[keep], k]
     unit = disp / dist[..., None]
     divs = (size[None, :n_ch, None, None] * gp[:, :n_ch, :, None] * unit[:, :n_ch, None, :]).reshape(T, n_ch * nb, 3)
+    if div_method == DIVMETHOD_REORDER:
+        # reverse-mode autodiff of the reference (jaxfeat.py:544-565): the NaN cotangent of a group that
+        # coincides with the bead (d = 0) meets the zeros of the smear matrix, 0 * NaN = NaN, and the
+        # whole frame's divergence is NaN (pinned by tests/golden/ref_gbfeat.npz); forward mode ("basic")
+        # confines it to the coincident group's own channel
+        divs[(dist == 0.0).any(dim=1)] = float("nan")
     return feats, divs
 
 
@@ -99,7 +106,12 @@ def gb_feat(
     Signature and return value as the reference's (``jaxfeat.py:20-184``): ``{"feats": per-bead
     (n_frames, n_fg, n_feat) arrays, "divs": per-bead (n_frames, n_feat, 3) arrays, "names": None}``,
     generators when ``lazy``.  ``batch_size`` is accepted for compatibility (frames are processed
-    on the device in one pass); both ``div_method`` values give the same closed form.
+    on the device in one pass); both ``div_method`` values give the same closed form and differ only
+    in how far the NaN of a group coinciding with the bead spreads (see ``_materialise``).
+
+    ``drop_last_channel=True`` is the reference's behaviour (Q5): ``channel_allocate`` scatters the
+    block of the largest label into an empty slice, which JAX's scatter ignores; it is pinned by the
+    reference run behind the jax stand-in (``tests/golden/ref_gbfeat.npz``), not by real jaxlib.
     """
     if div_method not in (DIVMETHOD_REORDER, DIVMETHOD_BASIC):
         raise ValueError("Unknown method for jacobian calculation.")
@@ -116,7 +128,7 @@ def gb_feat(
     cm = torch.as_tensor(np.asarray(cmap.standard_matrix, dtype=np.float64), device=dev)
 
     def one(bead: int, which: int):
-        out = _materialise(pts, cm[bead], labels, n_labels, spec)[which].to(torch.float32)
+        out = _materialise(pts, cm[bead], labels, n_labels, spec, div_method)[which].to(torch.float32)
         return _engine.to_host(out) if host else out
 
     feats = (one(c, 0) for c in range(cmap.n_cg_sites))

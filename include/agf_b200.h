@@ -257,6 +257,29 @@ int agf_feat_apply(const void* coords, const void* forces, int dtype, int64_t n_
                    const double* coefs, void* out, int out_dtype, double* sumsq, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Validation projections on random Gaussian force fields.
+ * Replaces  src/aggforce/jaxmapval.py:365-401 (sq_gaussian_energies / sq_gaussian_forces: JAX
+ * autodiff of  E = sum_{i,j} exp(-((|x_j - x_i|^2 - offset)/width)^2)  over the full squared
+ * distance matrix) and the per-sample loops of random_force_proj (:309-319, mscg_ip :359-360) and
+ * random_residual_shift (:227-237).  All samples are evaluated in ONE pass over the frames:
+ *   out[s, 0] += sum_{t,i} F[t,i,:] . G_s[t,i,:]        out[s, 1] += sum_{t,i} |G_s[t,i,:]|^2
+ * with G_s the force field of offset offsets[s]  (projection = out[s,0] / n_frames;
+ * residual shift = (out[s,1] - 2 out[s,0]) / (3 n_frames n_sites)).
+ *   coords, forces  device [n_frames, n_sites, 3] (the MAPPED arrays), dtype f32 or f64
+ *   offsets         device f64 [n_samples];  width: the (already squared, if sq_args) width
+ *   out             device f64 [n_samples, 2], accumulated into (zero it first)
+ */
+int agf_gauss_field_moments(const void* coords, const void* forces, int dtype, int64_t n_frames,
+                            int32_t n_sites, const double* offsets, int32_t n_samples,
+                            double width, double* out, void* stream);
+
+/* One force field written out: out[t, i, :] = -dE/dx_i for a single (offset, width)
+ * (src/aggforce/jaxmapval.py:396-401 as called by rsqpg_forces :139).  out [n_frames, n_sites, 3].
+ */
+int agf_sq_gaussian_forces(const void* coords, int dtype, int64_t n_frames, int32_t n_sites,
+                           double offset, double width, void* out, int out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Synthetic trajectory generator for benchmarks and tests (counter-based, so any
  * frame range of any sharding reproduces the same data):  frame0 = global index of the
  * first generated frame.  See aggforce_b200/synth.py for the model.
@@ -268,6 +291,15 @@ int agf_synth_frames(const float* ref_pos, const int32_t* parent, const float* b
                      int32_t n_sites, int64_t frame0, int64_t n_frames, uint64_t seed,
                      float pos_sigma, float force_sigma, float h_coupling, float* coords,
                      float* forces, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Roofline probes (bench.py measures its denominators in the run that quotes them; no reference
+ * counterpart).  agf_probe_dmma: every SM streams independent DMMA.8x8x4 tiles for `iters`
+ * iterations; *flop_out = flops issued; sink: device f64 [sm_count * 8 * 256].
+ * agf_probe_read: one streaming read of `bytes` bytes (16-byte aligned device buffer).
+ */
+int agf_probe_dmma(int32_t iters, double* sink, int64_t* flop_out, void* stream);
+int agf_probe_read(const void* src, int64_t bytes, float* sink, void* stream);
 
 #ifdef __cplusplus
 }
