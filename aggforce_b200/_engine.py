@@ -210,9 +210,20 @@ def sharded() -> bool:
     return dist.is_available() and dist.is_initialized() and dist.get_world_size(_Sharding.group) > 1
 
 
+def shard_rank() -> int:
+    return _dist().get_rank(_Sharding.group) if sharded() else 0
+
+
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if sharded():
         _dist().all_reduce(t, group=_Sharding.group)
+    return t
+
+
+def allreduce_max_(t: torch.Tensor) -> torch.Tensor:
+    if sharded():
+        dist = _dist()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_Sharding.group)
     return t
 
 
@@ -250,15 +261,33 @@ def global_count(local: int) -> int:
 # --------------------------------------------------------------------------------------
 # trajectory arrays
 # --------------------------------------------------------------------------------------
+_SHARED_UPLOADS: dict = {}
+
+
+@contextlib.contextmanager
+def shared_uploads(*arrays):
+    """While the context is open, ``Frames(a)`` of any of ``arrays`` (matched by identity) shares ONE
+    upload: ``project_forces`` opens it around constraint detection, the fit and the application, so
+    the caller's own arrays -- not a proxy -- can be handed to every ``method`` / featurizer."""
+    added = []
+    for a in arrays:
+        if a is None or isinstance(a, Frames) or id(a) in _SHARED_UPLOADS:
+            continue
+        _SHARED_UPLOADS[id(a)] = (a, Frames(a))  # the array is kept alive: its id cannot be recycled
+        added.append(id(a))
+    try:
+        yield
+    finally:
+        for key in added:
+            _SHARED_UPLOADS.pop(key, None)
+
+
 class Frames:
     """A ``(n_frames, n_sites, 3)`` array as the kernels see it (see module docstring)."""
 
     def __new__(cls, array=None, *args, **kwargs):
         # virtual frame sources (subclasses: Gaussian-augmented frames, synthetic frames) pass through
-        # unchanged, also when wrapped by agg._Shared; their __init__ must tolerate the second call
-        inner = getattr(array, "frames", None)
-        if isinstance(inner, Frames):
-            array = inner
+        # unchanged; their __init__ must tolerate the second call
         if cls is Frames and isinstance(array, Frames) and type(array) is not Frames:
             return array
         return super().__new__(cls)
@@ -266,9 +295,9 @@ class Frames:
     def __init__(self, array) -> None:
         if array is self:
             return
-        inner = getattr(array, "frames", None)
-        if isinstance(inner, Frames):  # agg._Shared: reuse the upload made by project_forces
-            array = inner
+        shared = _SHARED_UPLOADS.get(id(array))
+        if shared is not None and shared[0] is array:  # upload made once per project_forces call
+            array = shared[1]
         if isinstance(array, Frames):
             self.__dict__ = array.__dict__  # share state (and the cached device copy)
             return
@@ -319,11 +348,18 @@ class Frames:
         free, _ = torch.cuda.mem_get_info()
         return self.nbytes() <= _RESIDENT_FRACTION * free
 
-    def pieces(self, start: int = 0, stop: Optional[int] = None) -> Iterator[Tuple[int, torch.Tensor]]:
+    def piece_frames(self) -> int:
+        """Frames per upload piece of a host array (a multiple of 4: 16-byte aligned piece starts)."""
+        frame_bytes = max(1, self.n_sites * 3 * np.dtype(self.np_dtype).itemsize)
+        return max(4, (_PIECE_BYTES // frame_bytes) // 4 * 4)
+
+    def pieces(self, start: int = 0, stop: Optional[int] = None, per: Optional[int] = None
+               ) -> Iterator[Tuple[int, torch.Tensor]]:
         """Yield ``(first_frame, device_tensor)`` pieces covering frames [start, stop).
 
         Every yielded tensor is safe to use on the current stream.  Host arrays are uploaded
-        on a side stream one piece ahead of the consumer.
+        on a side stream one piece ahead of the consumer, ``per`` frames at a time (default:
+        ``piece_frames()``).
         """
         stop = self.n_frames if stop is None else min(stop, self.n_frames)
         if start >= stop:
@@ -332,8 +368,7 @@ class Frames:
             yield start, self._dev[start:stop]
             return
         device()
-        frame_bytes = max(1, self.n_sites * 3 * np.dtype(self.np_dtype).itemsize)
-        per = max(4, (_PIECE_BYTES // frame_bytes) // 4 * 4)
+        per = self.piece_frames() if per is None else max(4, int(per) // 4 * 4)
         whole = start == 0 and stop == self.n_frames and self._fits()
         cs, cur = _copy_stream(), torch.cuda.current_stream()
         with warnings.catch_warnings():
@@ -349,6 +384,12 @@ class Frames:
             a, b = bounds[i], bounds[i + 1]
             dst = full[a:b] if whole else torch.empty((b - a, self.n_sites, 3), dtype=self.torch_dtype,
                                                       device=device())
+            if not whole:
+                # a fresh staging block may reuse the memory of piece i-2, already released on the host
+                # but possibly still being read by a kernel on the compute stream: order the copy after
+                # everything enqueued there so far (kernel i-1 is enqueued after this call, so the
+                # upload still overlaps it)
+                cs.wait_stream(cur)
             with torch.cuda.stream(cs):
                 dst.copy_(src[a:b], non_blocking=True)
                 ev = torch.cuda.Event()
@@ -368,6 +409,13 @@ class Frames:
             views[i] = None  # type: ignore[call-overload]
         if whole:
             self._dev = full
+
+    def frame_range(self, t0: int, count: int) -> torch.Tensor:
+        """Frames ``[t0, t0 + count)`` as ONE device tensor usable on the current stream."""
+        if self._dev is not None:
+            return self._dev[t0 : t0 + count]
+        parts = [p for _, p in self.pieces(t0, t0 + count)]
+        return parts[0] if len(parts) == 1 else torch.cat(parts)
 
     def resident(self) -> torch.Tensor:
         """The whole array on the device (uploaded once and cached)."""
@@ -395,6 +443,51 @@ class Frames:
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             return torch.from_numpy(self._host[:n]).to(device())
+
+
+def paired_pieces(a: Frames, b: Frames) -> Iterator[Tuple[int, torch.Tensor, torch.Tensor]]:
+    """``(first_frame, piece_of_a, piece_of_b)`` over ONE frame schedule shared by both arrays.
+
+    Each array on its own would be cut by its own rule (a device tensor is one piece, a host array
+    is cut by bytes per frame, virtual sources by their slab size), so zipping two ``pieces()``
+    generators pairs different frame ranges.  Two plain host arrays are cut with the smaller of
+    their piece lengths (uploads of both stay one piece ahead); otherwise ``a`` drives and ``b``
+    supplies the matching range."""
+    if a.n_frames != b.n_frames:
+        raise ValueError(f"paired arrays have {a.n_frames} and {b.n_frames} frames")
+    plain = type(a) is Frames and type(b) is Frames
+    if plain and a._dev is None and b._dev is None:
+        per = min(a.piece_frames(), b.piece_frames())
+        ga, gb = a.pieces(per=per), b.pieces(per=per)
+        for (t0, pa), (t1, pb) in zip(ga, gb):
+            if t0 != t1 or pa.shape[0] != pb.shape[0]:
+                raise AgfError(f"paired upload schedules diverged at frames {t0} / {t1}")
+            yield t0, pa, pb
+        for _ in ga:  # run both generators to their end: that is where the resident copy is kept
+            pass
+        for _ in gb:
+            pass
+        return
+    if plain and a._dev is not None and b._dev is None:  # let the host array drive its own uploads
+        for t0, pb in b.pieces():
+            yield t0, a._dev[t0 : t0 + pb.shape[0]], pb
+        return
+    for t0, pa in a.pieces():
+        yield t0, pa, b.frame_range(t0, pa.shape[0])
+
+
+def allreduce_host_sum(arr: np.ndarray) -> np.ndarray:
+    """Sum of one float64 host array over the ranks of the sharding group (same shape everywhere)."""
+    if not sharded():
+        return arr
+    return np.sum(allgather_host(np.ascontiguousarray(arr, dtype=np.float64).reshape(-1)), axis=0).reshape(arr.shape)
+
+
+def broadcast_host(arr: np.ndarray, src: int = 0) -> np.ndarray:
+    """Rank ``src``'s copy of a float64 host array (same shape everywhere)."""
+    if not sharded():
+        return arr
+    return allgather_host(np.ascontiguousarray(arr, dtype=np.float64).reshape(-1))[src].reshape(arr.shape)
 
 
 # --------------------------------------------------------------------------------------

@@ -71,7 +71,14 @@ def project_forces(
     if auto and coords is None:
         raise ValueError(f"If constrained_inds is {PROJECT_FORCES_CNSTR_AUTO}, coords cannot be None.")
     t = Trajectory(coords=coords, forces=forces)
-    # one device upload per array, shared by constraint detection, the fit and the application
+    # one device upload per array, shared by constraint detection, the fit and the application: while
+    # this context is open Frames(coords) / Frames(forces) anywhere below resolve to the same upload,
+    # and every method (also user callables and generic featurizers) receives the caller's own arrays
+    with _engine.shared_uploads(coords, forces):
+        return _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method, kwargs)
+
+
+def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method, kwargs) -> Dict[str, Any]:
     coords_in, forces_in = _engine.Frames(coords), _engine.Frames(forces)
     if auto:
         constrained_inds = guess_pairwise_constraints(coords_in)
@@ -87,7 +94,7 @@ def project_forces(
         # other methods return maps that are applied as a whole (featurised / augmented): nothing to hoist
     try:
         traj_map: TMap = method(
-            traj=Trajectory(coords=_Shared(coords, coords_in), forces=_Shared(forces, forces_in)),
+            traj=t,
             coord_map=coord_map,
             constraints=constrained_inds,
             **kwargs,
@@ -112,9 +119,10 @@ def project_forces(
         count = torch.full((1,), float(np.prod(of.shape)), dtype=torch.float64, device=of.device)  # fill kernel, no upload
         packed = torch.cat([sc, sf, count])
         if _engine.sharded():
-            tail = packed[5:7].clone()
-            _engine.allreduce_sum_(tail)
-            packed = torch.cat([packed[:5], tail])
+            # residual sums are added over ranks, and so are the NaN flags, so that a violated NaN
+            # protocol raises on every rank (a lone raiser would leave the others in the next collective)
+            # (flags are >= 0, so their sum is non-zero exactly when any rank's is: ONE collective)
+            _engine.allreduce_sum_(packed)
         status = packed.cpu().numpy()
         mapped_coords = cm._finish(fc, oc, status[0:3], host_c)
         mapped_forces = fm._finish(ff, of, status[3:6], host_f)
@@ -244,28 +252,3 @@ def sample_sd(s: Collection[float]) -> Union[float, None]:
     if len(s) < 2:
         return float("nan")
     return (sum((o - m) ** 2 for o in s) / (len(s) - 1)) ** 0.5
-
-
-class _Shared:
-    """Array stand-in handed to fit methods: exposes ``shape`` like the original array and
-    carries the already-uploaded ``Frames`` so kernels do not upload it a second time."""
-
-    def __init__(self, original, frames) -> None:
-        self.original = original
-        self.frames = frames
-
-    @property
-    def shape(self):
-        return self.original.shape
-
-    def __len__(self) -> int:
-        return len(self.original)
-
-    def __getattr__(self, name):
-        return getattr(self.original, name)
-
-    def __getitem__(self, idx):
-        return self.original[idx]
-
-    def __array__(self, *args, **kwargs):
-        return np.asarray(self.original, *args, **kwargs)

@@ -67,6 +67,7 @@ class LinearMap:
             raise ValueError("NaN checking can only be performed if standard_matrix is itself finite.")
         self.nan_check_threshold = nan_check_threshold
         self._compiled: Optional[Tuple[bytes, _engine.CompiledMap]] = None
+        self._frozen_digest: Optional[bytes] = None
         self._column_labels: Optional[np.ndarray] = None  # set by fits that know the column structure
 
     # ------------------------------------------------------------------ descriptors
@@ -99,14 +100,16 @@ class LinearMap:
     # ------------------------------------------------------------------ application
     def _compile(self) -> _engine.CompiledMap:
         m = self._standard_matrix
-        # change detection for in-place edits of the matrix: full digest when small, strided sample
-        # (at most 64 Ki elements) plus the array identity when large (hashing 20 MB costs 20 ms)
-        # (strided 2-D sampling: no copy whatever the memory layout of the matrix)
-        rs, cs = max(1, m.shape[0] // 256), max(1, m.shape[1] // 256)
-        sampled = rs > 1 or cs > 1
-        digest = hashlib.blake2b(np.ascontiguousarray(m[::rs, ::cs]).tobytes(), digest_size=16).digest()
-        digest += repr((m.shape, str(m.dtype), rs, cs, m.ctypes.data if sampled else 0,
-                        bool(self.handle_nans))).encode()
+        # ``standard_matrix`` hands out the live array and the reference re-reads it on every call
+        # (core.py:240), so in-place edits must be seen: digest of the WHOLE matrix (microseconds at
+        # cln025, 20 ms for a 500 x 5000 map), taken once only for arrays nobody can write to
+        if m.flags.writeable or self._frozen_digest is None:
+            digest = hashlib.blake2b(np.ascontiguousarray(m).tobytes(), digest_size=16).digest()
+            if not m.flags.writeable:
+                self._frozen_digest = digest
+        else:
+            digest = self._frozen_digest
+        digest += repr((m.shape, str(m.dtype), bool(self.handle_nans))).encode()
         if self._compiled is not None and self._compiled[0] != digest:
             self._column_labels = None  # matrix was edited in place: the fit's column structure is stale
         if self._compiled is None or self._compiled[0] != digest:
@@ -143,6 +146,8 @@ class LinearMap:
 
     def _apply(self, points, want_sumsq: bool = False):
         frames, out, status = self._launch(points, want_sumsq)
+        if _engine.sharded():  # every rank must raise (or not) together: the next collective would hang
+            _engine.allreduce_max_(status[:2])
         host = status.cpu().numpy()  # one synchronising read: NaN flags and the residual sum together
         return self._finish(frames, out, host), float(host[2])
 

@@ -272,9 +272,7 @@ class _FusedContext:
         (numpy, or a CUDA tensor with ``on_device``)."""
         nf = self.n_feat_kernel
         gram = torch.zeros((self.n_cg, nf, nf), dtype=torch.float64, device=_engine.device())
-        pc, pf = coords.pieces(), forces.pieces()
-        for (t0, c), (t1, f) in zip(pc, pf):
-            assert t0 == t1 and c.shape == f.shape
+        for _, c, f in _engine.paired_pieces(coords, forces):
             if c.dtype != f.dtype:
                 c, f = c.to(torch.float64), f.to(torch.float64)
             need = int(_lib.lib().agf_gram_feat_workspace_bytes(self.n_groups, self.n_channels, self.nb, self.n_cg,
@@ -311,7 +309,7 @@ class _FusedContext:
         d_coef = _engine.dev_f64(full)
         out = torch.empty((coords.n_frames, self.n_cg, 3), dtype=torch.float64, device=_engine.device())
         sumsq = torch.zeros(1, dtype=torch.float64, device=_engine.device()) if want_sumsq else None
-        for (t0, c), (_, f) in zip(coords.pieces(), forces.pieces()):
+        for t0, c, f in _engine.paired_pieces(coords, forces):
             if c.dtype != f.dtype:
                 c, f = c.to(torch.float64), f.to(torch.float64)
             o = out[t0 : t0 + c.shape[0]]
@@ -347,6 +345,40 @@ def _pick_frames(n_total: int, n_frames: int, constraint_frames) -> np.ndarray:
     if callable(constraint_frames):
         return np.asarray(constraint_frames(n_total, n_frames))
     return np.asarray(constraint_frames)
+
+
+class _ConstraintFrames:
+    """Per-bead choice of the frames that carry the equality rows, made ONCE for all ranks.
+
+    Under ``frame_sharding`` every rank holds a slice of the frames; the frame indices are GLOBAL
+    (rank r's frames follow those of ranks < r).  Rank 0 draws (or takes the caller's indices), the
+    choice is broadcast, every rank evaluates the rows of the frames it owns and the rows are summed
+    across ranks -- so all ranks solve the same QP.  Without sharding this is ``_pick_frames``."""
+
+    def __init__(self, n_local: int, n_beads: int, n_frames: int, constraint_frames) -> None:
+        self.n_local = int(n_local)
+        counts = np.asarray([c[0] for c in _engine.allgather_host(np.asarray([float(n_local)]))], dtype=np.int64)
+        rank = _engine.shard_rank()
+        self.offset = int(counts[:rank].sum())
+        n_total = int(counts.sum())
+        picks = np.stack([np.asarray(_pick_frames(n_total, n_frames, constraint_frames), dtype=np.int64)
+                          for _ in range(n_beads)])
+        self.picks = _engine.broadcast_host(picks.astype(np.float64)).astype(np.int64)
+
+    def rows(self, bead: int, evaluate: Callable[[np.ndarray], np.ndarray], n_cg: int) -> np.ndarray:
+        """``evaluate(local frame indices) -> (n_sel_local * n_cg, n_feat)``; returns the rows of all
+        chosen frames in the order of the choice."""
+        glob = self.picks[bead]
+        if not _engine.sharded():
+            return evaluate(glob)
+        mine = np.nonzero((glob >= self.offset) & (glob < self.offset + self.n_local))[0]
+        local = evaluate(glob[mine] - self.offset) if mine.size else None
+        n_feat = np.asarray([float(local.shape[1]) if local is not None else 0.0])
+        n_feat = int(max(v[0] for v in _engine.allgather_host(n_feat)))
+        full = np.zeros((glob.size, n_cg, n_feat))
+        if local is not None:
+            full[mine] = local.reshape(mine.size, n_cg, n_feat)
+        return _engine.allreduce_host_sum(full).reshape(glob.size * n_cg, n_feat)
 
 
 def qp_feat_linear_map(
@@ -388,9 +420,10 @@ def _fit_fused(traj, coord_map, featurizer, plan, kbt, n_constraint_frames, cons
     grams = ctx.grams(coords, forces, kbt, on_device=on_device)  # large problems never leave the device
     n_feat = grams.shape[1]
     coefs = []
+    chosen = _ConstraintFrames(coords.n_frames, coord_map.n_cg_sites, n_constraint_frames, constraint_frames)
     for bead in range(coord_map.n_cg_sites):
-        frames = _pick_frames(coords.n_frames, n_constraint_frames, constraint_frames)
-        a_mat = ctx.constraint_rows(coords, bead, frames)
+        frames = chosen.picks[bead]
+        a_mat = chosen.rows(bead, lambda idx, b=bead: ctx.constraint_rows(coords, b, idx), coord_map.n_cg_sites)
         target = np.zeros((len(frames), coord_map.n_cg_sites))
         target[:, bead] = 1
         params = None
@@ -423,12 +456,17 @@ def _fit_generic(traj, coord_map, featurizer, kbt, n_constraint_frames, constrai
     forces = _engine.Frames(traj.forces).resident().to(torch.float64)
     cm = torch.as_tensor(np.asarray(coord_map.standard_matrix, dtype=np.float64), device=dev)
     coefs = []
+    chosen = _ConstraintFrames(forces.shape[0], coord_map.n_cg_sites, n_constraint_frames, constraint_frames)
     for bead, (feat, div) in enumerate(zip(feats, divs)):
         phi = torch.as_tensor(feat).to(device=dev, dtype=torch.float64)
         dv = torch.as_tensor(div).to(device=dev, dtype=torch.float64)
-        frames = _pick_frames(phi.shape[0], n_constraint_frames, constraint_frames)
-        mult = torch.einsum("ca,saf->scf", cm, phi[torch.as_tensor(np.asarray(frames), device=dev)])
-        a_mat = _engine.to_host(mult.reshape(-1, mult.shape[-1]))
+        frames = chosen.picks[bead]
+
+        def rows_of(idx, phi=phi):
+            mult = torch.einsum("ca,saf->scf", cm, phi[torch.as_tensor(np.asarray(idx), device=dev)])
+            return _engine.to_host(mult.reshape(-1, mult.shape[-1]))
+
+        a_mat = chosen.rows(bead, rows_of, coord_map.n_cg_sites)
         target = np.zeros((len(frames), coord_map.n_cg_sites))
         target[:, bead] = 1
         rows = torch.einsum("tad,taf->tdf", forces, phi) + kbt * dv.transpose(1, 2)

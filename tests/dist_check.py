@@ -53,11 +53,40 @@ def main() -> None:
         cons2 = agf.guess_pairwise_constraints(coords)
     _engine._SCREEN_FRAMES, _engine._RESCREEN_FRAMES = 32, 4096
     ok = ok and cons2 == topo.xh_constraints
+    # featurised fit under sharding: the equality-row frames are drawn once, globally, so
+    # every rank fits the map a single GPU fits on all frames with the same frame choice
+    from aggforce_b200.qp import Multifeaturize, gb_feat, id_feat, qp_feat_linear_map
+    from aggforce_b200.util import Curry
+
+    feat = Multifeaturize([id_feat, Curry(gb_feat, inner=0.0, outer=8.0, width=1.0, n_basis=4)])
+    Tf = 3_000
+    fb = np.linspace(0, Tf, world + 1).astype(int)
+    fb[1:-1] += 1
+    flo, fhi = int(fb[rank]), int(fb[rank + 1])
+    choice = np.random.default_rng(42100).choice(Tf, size=20, replace=False)
+    kw = dict(coord_map=cmap, constrained_inds=topo.xh_constraints, method=qp_feat_linear_map, featurizer=feat,
+              kbt=0.6955215, l2_regularization=1e3, constraint_frames=choice)
+    with agf.frame_sharding():
+        fres = agf.project_forces(coords=ac[flo:fhi].contiguous(), forces=af[flo:fhi].contiguous(), **kw)
+    fref = agf.project_forces(coords=ac[:Tf].contiguous(), forces=af[:Tf].contiguous(), **kw)
+    c0 = np.stack(fres["tmap"].force_map.tags["coef_list"])
+    c1 = np.stack(fref["tmap"].force_map.tags["coef_list"])
+    rel_c = np.linalg.norm(c0 - c1) / np.linalg.norm(c1)
+    rel_ff = float((fres["mapped_forces"] - fref["mapped_forces"][flo:fhi]).norm() / fref["mapped_forces"][flo:fhi].norm())
+    ok = ok and rel_c < 1e-8 and rel_ff < 1e-8
+    with agf.frame_sharding():  # unseeded choice: still one choice for all ranks
+        fres2 = agf.project_forces(coords=ac[flo:fhi].contiguous(), forces=af[flo:fhi].contiguous(),
+                                   **dict(kw, constraint_frames=None))
+    c2 = torch.as_tensor(np.stack(fres2["tmap"].force_map.tags["coef_list"]), device="cuda")
+    c2_all = [torch.empty_like(c2) for _ in range(world)]
+    dist.all_gather(c2_all, c2)
+    ok = ok and all(torch.equal(c2_all[0], c) for c in c2_all)
     flag = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"dist_check world={world}: constraints={len(res['constraints'])} rel_w={rel_w:.2e} rel_f={rel_f:.2e} "
-              f"residual={res['residual']:.6g} -> {'OK' if flag.item() else 'FAILED'}")
+              f"residual={res['residual']:.6g} feat rel_coef={rel_c:.2e} rel_mapped={rel_ff:.2e} "
+              f"-> {'OK' if flag.item() else 'FAILED'}")
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
 

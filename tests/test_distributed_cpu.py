@@ -56,6 +56,27 @@ def _worker(rank: int, world: int, port: int, out_dir: str) -> None:
         # residual: global mean of squares from per-rank sums
         local = f[lo:hi]
         assert abs(_global_mean_sq(float((local**2).sum()), local.shape) - float((f**2).mean())) < 1e-12
+        # host helpers: sum / broadcast / rank
+        assert _engine.shard_rank() == rank
+        assert np.array_equal(_engine.allreduce_host_sum(np.full((2, 3), rank + 1.0)), np.full((2, 3), 3.0))
+        assert np.array_equal(_engine.broadcast_host(np.arange(4.0) + 10 * rank), np.arange(4.0))
+        # equality-row frames of a featurised fit are chosen ONCE for all ranks, in global frame
+        # indices, and every rank assembles the same rows from the frames it owns
+        from aggforce_b200.qp.featlinearmap import _ConstraintFrames
+
+        chosen = _ConstraintFrames(hi - lo, n_beads=3, n_frames=20, constraint_frames=None)
+        assert chosen.picks.shape == (3, 20) and chosen.offset == lo
+        both = _engine.allgather_host(chosen.picks.astype(np.float64).reshape(-1))
+        assert np.array_equal(both[0], both[1])  # unseeded draw, still identical on both ranks
+        feat = rng.normal(size=(T, 2, 5))  # "features" (frame, bead', feature), known to both ranks
+
+        def local_rows(idx):
+            return feat[lo:hi][idx].reshape(-1, 5)
+
+        rows = chosen.rows(1, local_rows, n_cg=2)
+        assert np.allclose(rows, feat[chosen.picks[1]].reshape(-1, 5), rtol=0, atol=0)
+        fixed = _ConstraintFrames(hi - lo, 1, 4, np.array([0, 36, 37, 89]))  # straddles the shard boundary
+        assert np.array_equal(fixed.rows(0, local_rows, 2), feat[[0, 36, 37, 89]].reshape(-1, 5))
     assert not _engine.sharded()
     Path(out_dir, f"ok{rank}").write_text("ok")
     dist.destroy_process_group()
