@@ -35,9 +35,14 @@ _RESIDENT_FRACTION = 0.45  # keep a host array resident on the device if it fits
 # --------------------------------------------------------------------------------------
 # device / stream helpers
 # --------------------------------------------------------------------------------------
+_CUDA_OK = [False]
+
+
 def device() -> torch.device:
-    if not torch.cuda.is_available():
-        raise AgfError("aggforce_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+    if not _CUDA_OK[0]:  # asked once: torch.cuda.is_available() costs microseconds on every call
+        if not torch.cuda.is_available():
+            raise AgfError("aggforce_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback.")
+        _CUDA_OK[0] = True
     return torch.device("cuda", torch.cuda.current_device())
 
 
@@ -73,6 +78,17 @@ def to_host(t: torch.Tensor) -> np.ndarray:
     host.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return host.numpy()
+
+
+def read_many(tensors: Sequence[torch.Tensor]) -> List[np.ndarray]:
+    """Several device tensors -> pinned host arrays with ONE synchronisation."""
+    hosts = []
+    for t in tensors:
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        hosts.append(host)
+    torch.cuda.current_stream().synchronize()
+    return [h.numpy() for h in hosts]
 
 
 _DEV_CACHE: "dict[tuple, torch.Tensor]" = {}
@@ -150,6 +166,25 @@ def run_deferred() -> None:
 
 def clear_deferred() -> None:
     _DEFERRED.clear()
+
+
+_FITS_DEFERRED = [False]
+
+
+@contextlib.contextmanager
+def deferred_fits():
+    """Inside this context a device-side fit may return before its status has been read: the caller
+    (``project_forces``) reads it together with the application's status."""
+    prev = _FITS_DEFERRED[0]
+    _FITS_DEFERRED[0] = True
+    try:
+        yield
+    finally:
+        _FITS_DEFERRED[0] = prev
+
+
+def fits_deferred() -> bool:
+    return _FITS_DEFERRED[0]
 
 
 def to_host_overlapped(t: torch.Tensor) -> np.ndarray:
@@ -508,12 +543,13 @@ def csr_from_labels(labels: np.ndarray, n_groups: int) -> Tuple[np.ndarray, np.n
 # --------------------------------------------------------------------------------------
 # kernel wrappers
 # --------------------------------------------------------------------------------------
-def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Tensor:
-    """Kernel (a): all-reduced, symmetrised second-moment matrix (device f64 [n_red, n_red]).
+def gram_linear_raw(frames: Frames, col_of_site: np.ndarray, n_red: int) -> Tuple[torch.Tensor, np.ndarray]:
+    """Kernel (a): accumulated and all-reduced second-moment matrix as the kernels leave it --
+    ``(gram f64 [n_red, n_red] with the element-wise UPPER triangle valid, order)`` where
+    ``order[p]`` is the caller's column held at internal position ``p``.
 
     Internally the reduced columns are ordered by group size (largest first) so that the lanes of a
-    warp walk member lists of similar length while they build the f64 panel; the result is
-    permuted back to the caller's column order.
+    warp walk member lists of similar length while they build the f64 panel.
     """
     col_of_site = np.asarray(col_of_site, dtype=np.int64)
     sizes = np.bincount(col_of_site[col_of_site >= 0], minlength=n_red)
@@ -541,8 +577,17 @@ def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Te
             _lib.call("agf_gram_linear", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites, ptr(d_ptr),
                       ptr(d_sites), n_red, ptr(gram), stream_ptr())
     allreduce_sum_(gram)
+    return gram, order
+
+
+def gram_linear(frames: Frames, col_of_site: np.ndarray, n_red: int) -> torch.Tensor:
+    """Kernel (a): all-reduced, symmetrised second-moment matrix (device f64 [n_red, n_red]) in the
+    caller's column order."""
+    gram, order = gram_linear_raw(frames, col_of_site, n_red)
     _lib.call("agf_symmetrize", ptr(gram), n_red, stream_ptr())
     if not np.array_equal(order, np.arange(n_red)):
+        rank = np.empty(n_red, dtype=np.int64)
+        rank[order] = np.arange(n_red)
         back = _dev_cached(np.ascontiguousarray(rank, dtype=np.int64))  # cached: no pageable upload per call
         gram = gram[back][:, back]
     return gram
@@ -611,10 +656,31 @@ class CompiledMap:
         self.ucol_ptr, self.ucol_sites = dev_i32(ptr_), dev_i32(sites)
         self.umat_t = dev_f64(uniq)  # [n_ucol, n_cg]
 
+    @classmethod
+    def from_labels(cls, column_labels: np.ndarray, n_cg: int, n_labels: int) -> Tuple["CompiledMap", np.ndarray]:
+        """Dense-small map whose unique columns are KNOWN to be the labels (the reduced columns of a
+        fit) and whose values are filled in on the device (``agf_qp_equality_small`` writes ``umat_t``).
+        Returns ``(map, ucol_of_label)``; same unique-column order as the value-based constructor."""
+        self = cls.__new__(cls)
+        labels = np.asarray(column_labels, dtype=np.int64)
+        self.n_cg, self.n_fg = int(n_cg), int(labels.size)
+        self.out_f32, self.sparse, self.slice = False, False, False
+        sizes = np.bincount(labels, minlength=n_labels)
+        order = np.argsort(sizes, kind="stable")
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        ptr_, sites = csr_from_labels(rank[labels], n_labels)
+        self.n_ucol, self.nnz = int(n_labels), int(sites.size)
+        self.ucol_ptr, self.ucol_sites = dev_i32(ptr_), dev_i32(sites)
+        self.umat_t = torch.empty((n_labels, n_cg), dtype=torch.float64, device=device())
+        return self, rank
+
 
 def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float, want_sumsq: bool = False,
-              start: int = 0, stop: Optional[int] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
-    """Kernel (d).  Returns ``(out [T, n_cg, 3] device, sumsq device f64[1] | None, nan_flags int32[2])``."""
+              start: int = 0, stop: Optional[int] = None, sumsq: Optional[torch.Tensor] = None,
+              flags: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+    """Kernel (d).  Returns ``(out [T, n_cg, 3] device, sumsq device f64[1] | None, nan_flags int32[2])``.
+    ``sumsq`` / ``flags``: zeroed slots of a caller-owned status buffer to accumulate into."""
     if frames.n_sites != cmap.n_fg:
         raise ValueError(
             f"map expects {cmap.n_fg} fine-grained sites but the array has {frames.n_sites}"
@@ -622,8 +688,10 @@ def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float,
     stop = frames.n_frames if stop is None else stop
     out_dtype = torch.float32 if (cmap.out_f32 and frames.np_dtype == np.float32) else torch.float64
     out = torch.empty((stop - start, cmap.n_cg, 3), dtype=out_dtype, device=device())
-    sumsq = torch.zeros(1, dtype=torch.float64, device=device()) if want_sumsq else None
-    flags = torch.zeros(2, dtype=torch.int32, device=device())
+    if sumsq is None:
+        sumsq = torch.zeros(1, dtype=torch.float64, device=device()) if want_sumsq else None
+    if flags is None:
+        flags = torch.zeros(2, dtype=torch.int32, device=device())
     for t0, piece in frames.pieces(start, stop):
         o = out[t0 - start : t0 - start + piece.shape[0]]
         if cmap.sparse and cmap.slice:
@@ -672,6 +740,7 @@ def merge_moments(parts: Sequence[np.ndarray], n_pairs: int) -> np.ndarray:
 
 _SCREEN_FRAMES = 32
 _RESCREEN_FRAMES = 4096
+_SELECT_CAP = 8192  # survivor capacity of the one-kernel compaction (small systems)
 
 
 def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
@@ -700,13 +769,17 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
 
     # ---- stage 0: literal all-pairs pass over a short prefix
     n0 = min(t_local, _SCREEN_FRAMES)
-    m2 = torch.full((n_o, n), float("inf"), dtype=torch.float64, device=dev)
+    x0 = o0 = None
     if n0 > 0:
         x0 = frames.prefix(n0)
         o0 = None if other is None else other.prefix(n0)
         if o0 is not None and o0.dtype != x0.dtype:
             o0 = o0.to(x0.dtype)
+        m2 = torch.empty((n_o, n), dtype=torch.float64, device=dev)
         _lib.call("agf_pair_screen", ptr(x0), ptr(o0), dtype_code(x0), n0, n, n_o, ptr(m2), stream_ptr())
+    else:
+        m2 = torch.full((n_o, n), float("inf"), dtype=torch.float64, device=dev)
+    bound_dev = None
     if fused:
         dist = _dist()
         world, rank = dist.get_world_size(_Sharding.group), dist.get_rank(_Sharding.group)
@@ -718,31 +791,52 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
         counts[rank] = float(t_local)
         buf = torch.cat([m2.reshape(-1), counts])
         dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=_Sharding.group)
-        bound_dev = float(threshold) ** 2 * buf[-world:].sum() * (1.0 + 1e-6) + 1e-300
-        alive = buf[:-world].reshape(n_o, n) <= bound_dev
-    else:
-        if n0 > 0:
-            alive = (m2 <= bound).to(torch.uint8)
+        bound_dev = (float(threshold) ** 2 * buf[-world:].sum() * (1.0 + 1e-6) + 1e-300).reshape(1)
+        m2 = buf[:-world].reshape(n_o, n)
+    pairs = shift = acc = None
+    if n0 > 0 and n * n_o <= (1 << 18) and (fused or not sharded()):
+        # small systems: ONE kernel turns the screened matrix into the ordered survivor list, their
+        # frame-0 distances and zeroed accumulators; one small read returns the count and the list
+        cap = min(n * n_o, _SELECT_CAP)
+        ints = torch.empty(1 + 2 * cap, dtype=torch.int32, device=dev)
+        fl = torch.empty(3 * cap, dtype=torch.float64, device=dev)
+        _lib.call("agf_pair_select", ptr(m2), 0.0 if bound is None else bound, ptr(bound_dev), ptr(x0), ptr(o0),
+                  dtype_code(x0), n, n_o, cap, ptr(ints[1:]), ptr(fl), ptr(fl[cap:]), ptr(ints), stream_ptr())
+        host_ints = to_host(ints)
+        n_pairs = int(host_ints[0])
+        if n_pairs == 0:
+            return empty
+        if n_pairs > 0:
+            pairs_host = host_ints[1 : 1 + 2 * n_pairs].reshape(-1, 2).astype(np.int64)
+            pairs = ints[1 : 1 + 2 * n_pairs].view(n_pairs, 2)
+            shift, acc = fl[:n_pairs], fl[cap : cap + 2 * n_pairs].view(n_pairs, 2)
+    if pairs is None:  # general path (large systems, or more survivors than the capacity)
+        if fused:
+            alive = m2 <= bound_dev
         else:
-            alive = torch.ones((n_o, n), dtype=torch.uint8, device=dev)
-            if other is None:
-                alive = torch.triu(alive, diagonal=1)
-        allreduce_min_(alive)
-    pairs = torch.nonzero(alive).to(torch.int32).contiguous()  # [P, 2] = (i over other, j over xyz)
-    del m2, alive
-    n_pairs = int(pairs.shape[0])
-    if n_pairs == 0:
-        return empty
+            if n0 > 0:
+                alive = (m2 <= bound).to(torch.uint8)
+            else:
+                alive = torch.ones((n_o, n), dtype=torch.uint8, device=dev)
+                if other is None:
+                    alive = torch.triu(alive, diagonal=1)
+            allreduce_min_(alive)
+        pairs = torch.nonzero(alive).to(torch.int32).contiguous()  # [P, 2] = (i over other, j over xyz)
+        del alive
+        pairs_host = None
+        n_pairs = int(pairs.shape[0])
+        if n_pairs == 0:
+            return empty
+        shift = torch.zeros(n_pairs, dtype=torch.float64, device=dev)
+        if t_local > 0:
+            xf = frames.prefix(1)
+            of_ = None if other is None else other.prefix(1).to(xf.dtype)
+            _lib.call("agf_pair_first", ptr(xf), ptr(of_), dtype_code(xf), n, n_o, ptr(pairs), n_pairs, ptr(shift),
+                      stream_ptr())
+        acc = torch.zeros((n_pairs, 2), dtype=torch.float64, device=dev)
+    del m2
 
     # ---- stage 1..: stream all frames for the survivors
-    shift = torch.zeros(n_pairs, dtype=torch.float64, device=dev)
-    if t_local > 0:
-        x0 = frames.prefix(1)
-        o0 = None if other is None else other.prefix(1).to(x0.dtype)
-        _lib.call("agf_pair_first", ptr(x0), ptr(o0), dtype_code(x0), n, n_o, ptr(pairs), n_pairs, ptr(shift),
-                  stream_ptr())
-    acc = torch.zeros((n_pairs, 2), dtype=torch.float64, device=dev)
-
     def run(a: int, b: int) -> None:
         for t0, piece in frames.pieces(a, b):
             o = other_piece(t0, piece.shape[0])
@@ -771,31 +865,40 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
             keep_mask = km > 0
         keep = torch.nonzero(keep_mask).reshape(-1)
         pairs, shift, acc = pairs[keep].contiguous(), shift[keep].contiguous(), acc[keep].contiguous()
+        pairs_host = None
         n_pairs = int(pairs.shape[0])
         if n_pairs == 0:
             return empty
     run(done, t_local)
 
-    # ---- per-rank (count, mean, M2) on the device, gathered across ranks, merged (Chan) in
-    #      float64 on the host; P is O(n).  One synchronising read.
+    # ---- per-rank (count, mean, M2), gathered across ranks, merged (Chan) in float64 on the host;
+    #      P is O(n).  One synchronising read.
+    if not sharded():
+        # shift and the two running sums come back as they are; the moments are formed on the host
+        want = [shift, acc] if pairs_host is not None else [shift, acc, pairs]
+        got = read_many(want)
+        sh, ac = got[0], got[1]
+        if pairs_host is None:
+            pairs_host = got[2].astype(np.int64)
+        with np.errstate(invalid="ignore", over="ignore"):
+            rec = np.concatenate([[float(t_local)], sh + ac[:, 0] / max(t_local, 1),
+                                  ac[:, 1] - ac[:, 0] ** 2 / max(t_local, 1)])
+        return pairs_host.reshape(-1, 2), merge_moments([rec], n_pairs)
     if t_local > 0:
         mean = shift + acc[:, 0] / t_local
         m2_local = acc[:, 1] - acc[:, 0] ** 2 / t_local
     else:
         mean, m2_local = torch.zeros_like(shift), torch.zeros_like(shift)
-    # the surviving pair list rides along (as float64) so that ONE synchronising read returns everything
     rec = torch.cat([torch.full((1,), float(t_local), dtype=torch.float64, device=dev), mean, m2_local])
-    pairs_f = pairs.to(torch.float64).reshape(-1)
-    if sharded():
-        dist = _dist()
-        outs = [torch.empty_like(rec) for _ in range(dist.get_world_size(_Sharding.group))]
-        dist.all_gather(outs, rec, group=_Sharding.group)
-        flat = to_host(torch.cat([torch.stack(outs).reshape(-1), pairs_f]))
-        n_rec = rec.numel()
-        parts = [flat[i * n_rec : (i + 1) * n_rec] for i in range(len(outs))]
-        pairs_host = flat[len(outs) * n_rec :]
-    else:
-        flat = to_host(torch.cat([rec, pairs_f]))
-        parts, pairs_host = [flat[: rec.numel()]], flat[rec.numel() :]
+    dist = _dist()
+    outs = [torch.empty_like(rec) for _ in range(dist.get_world_size(_Sharding.group))]
+    dist.all_gather(outs, rec, group=_Sharding.group)
+    # the surviving pair list rides along (as float64) so that ONE synchronising read returns everything
+    extra = [] if pairs_host is not None else [pairs.to(torch.float64).reshape(-1)]
+    flat = to_host(torch.cat([torch.stack(outs).reshape(-1), *extra]))
+    n_rec = rec.numel()
+    parts = [flat[i * n_rec : (i + 1) * n_rec] for i in range(len(outs))]
+    if pairs_host is None:
+        pairs_host = flat[len(outs) * n_rec :].astype(np.int64)
     sd = merge_moments(parts, n_pairs)
-    return pairs_host.reshape(-1, 2).astype(np.int64), sd
+    return pairs_host.reshape(-1, 2), sd

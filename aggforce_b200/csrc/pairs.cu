@@ -154,6 +154,68 @@ __global__ void __launch_bounds__(256) pair_screen_kernel(const T* __restrict__ 
   *dst = s2 - s1 * s1 / (double)n_frames;
 }
 
+// Ordered compaction of the screened pair matrix by ONE CTA (small systems: n_other * n_sites <= 2^18):
+// pairs with m2 <= bound, in row-major order (what a host-side nonzero() returns, so every rank of a
+// sharded run builds the same list), their frame-0 distance (the shift of the streaming pass) and
+// zeroed accumulators.  count[0] = number of survivors, or -(number) when it exceeds `cap` (nothing
+// beyond cap is written; the caller takes the general path).
+constexpr int kSelectThreads = 1024;
+
+template <typename T>
+__global__ void __launch_bounds__(kSelectThreads) pair_select_kernel(const double* __restrict__ m2, double bound,
+                                                                     const double* __restrict__ bound_dev,
+                                                                     const T* __restrict__ xyz0,
+                                                                     const T* __restrict__ other0, int n_sites,
+                                                                     int n_other, int cap, int32_t* __restrict__ pairs,
+                                                                     double* __restrict__ shift,
+                                                                     double* __restrict__ acc,
+                                                                     int32_t* __restrict__ count) {
+  __shared__ int warp_tot[kSelectThreads / 32];
+  __shared__ int total_s;
+  const int total = n_sites * n_other;
+  const int per = (total + kSelectThreads - 1) / kSelectThreads;
+  const int lo = min(total, (int)threadIdx.x * per), hi = min(total, lo + per);
+  const double b = bound_dev ? __ldg(bound_dev) : bound;
+  int mine = 0;
+  for (int e = lo; e < hi; ++e) mine += (__ldg(m2 + e) <= b) ? 1 : 0;
+  // block-wide exclusive scan of `mine`
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_tot[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += v;
+    }
+    warp_tot[lane] = w;  // inclusive totals of warps 0..lane
+    if (lane == 31) total_s = w;
+  }
+  __syncthreads();
+  int pos = incl - mine + (warp ? warp_tot[warp - 1] : 0);
+  const int n_found = total_s;
+  if (threadIdx.x == 0) *count = n_found <= cap ? n_found : -n_found;
+  if (n_found > cap) return;
+  for (int e = lo; e < hi; ++e) {
+    if (__ldg(m2 + e) <= b) {
+      const int i = e / n_sites, j = e - i * n_sites;
+      pairs[2 * pos] = i;
+      pairs[2 * pos + 1] = j;
+      shift[pos] = pair_dist<T>(other0 + (int64_t)i * 3, xyz0 + (int64_t)j * 3);
+      acc[2 * pos] = 0.0;
+      acc[2 * pos + 1] = 0.0;
+      ++pos;
+    }
+  }
+}
+
 template <typename T>
 static int pair_moments_typed(const void* xyz, const void* other, int64_t n_frames, int32_t n_sites, int32_t n_other,
                               const int32_t* pairs, int64_t n_pairs, const double* shift, double* acc,
@@ -257,6 +319,29 @@ extern "C" int agf_pair_screen(const void* xyz, const void* other, int dtype, in
     pair_screen_kernel<double><<<grid, 256, 0, s>>>(reinterpret_cast<const double*>(xyz),
                                                     reinterpret_cast<const double*>(self ? xyz : other), n_frames,
                                                     n_sites, n_o, self, m2);
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}
+
+extern "C" int agf_pair_select(const double* m2, double bound, const double* bound_dev, const void* xyz,
+                               const void* other, int dtype, int32_t n_sites, int32_t n_other, int32_t cap,
+                               int32_t* pairs, double* shift, double* acc, int32_t* count, void* stream) {
+  using namespace agf;
+  AGF_REQUIRE(m2 && xyz && pairs && shift && acc && count, "agf_pair_select: null pointer");
+  AGF_REQUIRE(dtype == AGF_F32 || dtype == AGF_F64, "agf_pair_select: bad dtype");
+  const bool self = (other == nullptr || other == xyz);
+  const int n_o = self ? n_sites : n_other;
+  AGF_REQUIRE(n_sites > 0 && n_o > 0 && cap > 0 && (int64_t)n_sites * n_o <= (1 << 18),
+              "agf_pair_select: at most 2^18 candidate pairs (got %d x %d)", n_o, n_sites);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == AGF_F32)
+    pair_select_kernel<float><<<1, kSelectThreads, 0, s>>>(m2, bound, bound_dev, reinterpret_cast<const float*>(xyz),
+                                                           reinterpret_cast<const float*>(self ? xyz : other),
+                                                           n_sites, n_o, cap, pairs, shift, acc, count);
+  else
+    pair_select_kernel<double><<<1, kSelectThreads, 0, s>>>(m2, bound, bound_dev, reinterpret_cast<const double*>(xyz),
+                                                            reinterpret_cast<const double*>(self ? xyz : other),
+                                                            n_sites, n_o, cap, pairs, shift, acc, count);
   AGF_CUDA_TRY(cudaGetLastError());
   return AGF_OK;
 }

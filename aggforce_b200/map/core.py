@@ -61,7 +61,9 @@ class LinearMap:
                 matrix[bead, :] = row
         else:
             raise ValueError(f"Cannot understand mapping {mapping}.")
-        self._standard_matrix = matrix
+        self._matrix: Optional[np.ndarray] = matrix
+        self._shape: Tuple[int, int] = tuple(matrix.shape)  # type: ignore[assignment]
+        self._pending = None  # a fit whose result still lives on the device (see from_device_fit)
         self.handle_nans = handle_nans
         if self.handle_nans and not np.all(np.isfinite(matrix)):
             raise ValueError("NaN checking can only be performed if standard_matrix is itself finite.")
@@ -70,18 +72,47 @@ class LinearMap:
         self._frozen_digest: Optional[bytes] = None
         self._column_labels: Optional[np.ndarray] = None  # set by fits that know the column structure
 
+    @classmethod
+    def from_device_fit(cls, pending, n_cg: int, column_labels: np.ndarray, compiled: "_engine.CompiledMap",
+                        handle_nans: Union[bool, Literal["safe"]] = True,
+                        nan_check_threshold: float = 1e-6) -> "LinearMap":
+        """Map fitted ON THE DEVICE (``agf_qp_equality_small``): ``compiled`` already holds the
+        coefficients kernel (d) reads, so the map can be applied without the host ever seeing them;
+        ``standard_matrix`` is downloaded (and the solver's status checked) on first access through
+        ``pending.matrix()``."""
+        self = cls.__new__(cls)
+        self._matrix = None
+        self._shape = (int(n_cg), int(np.asarray(column_labels).size))
+        self._pending = pending
+        self.handle_nans = handle_nans
+        self.nan_check_threshold = nan_check_threshold
+        self._compiled = (b"device-fit", compiled)
+        self._frozen_digest = None
+        self._column_labels = np.asarray(column_labels)
+        return self
+
     # ------------------------------------------------------------------ descriptors
+    @property
+    def _standard_matrix(self) -> np.ndarray:
+        if self._matrix is None:  # first host access to a device fit: one synchronising read
+            self._matrix = self._pending.matrix()
+        return self._matrix
+
+    @_standard_matrix.setter
+    def _standard_matrix(self, value: np.ndarray) -> None:
+        self._matrix = value
+
     @property
     def standard_matrix(self) -> np.ndarray:
         return self._standard_matrix
 
     @property
     def n_cg_sites(self) -> int:
-        return self._standard_matrix.shape[0]
+        return self._shape[0]
 
     @property
     def n_fg_sites(self) -> int:
-        return self._standard_matrix.shape[1]
+        return self._shape[1]
 
     @property
     def participating_fg(self) -> List[List[int]]:
@@ -99,6 +130,8 @@ class LinearMap:
 
     # ------------------------------------------------------------------ application
     def _compile(self) -> _engine.CompiledMap:
+        if self._matrix is None:  # device fit nobody has looked at (or edited) yet
+            return self._compiled[1]  # type: ignore[index]
         m = self._standard_matrix
         # ``standard_matrix`` hands out the live array and the reference re-reads it on every call
         # (core.py:240), so in-place edits must be seen: digest of the WHOLE matrix (microseconds at
@@ -110,6 +143,9 @@ class LinearMap:
         else:
             digest = self._frozen_digest
         digest += repr((m.shape, str(m.dtype), bool(self.handle_nans))).encode()
+        if self._compiled is not None and self._compiled[0] == b"device-fit":
+            # the downloaded matrix of a device fit: adopt its digest, keep the device copy
+            self._compiled = (digest, self._compiled[1])
         if self._compiled is not None and self._compiled[0] != digest:
             self._column_labels = None  # matrix was edited in place: the fit's column structure is stale
         if self._compiled is None or self._compiled[0] != digest:
@@ -119,20 +155,30 @@ class LinearMap:
                                                           column_labels=self._column_labels))
         return self._compiled[1]
 
-    def _launch(self, points, want_sumsq: bool = False):
+    def _launch(self, points, want_sumsq: bool = False, status: Optional[torch.Tensor] = None):
         """Enqueue the kernel; returns ``(frames, out_dev, status_dev)`` without synchronising.
-        ``status_dev`` is a float64[3] device tensor ``[saw_nan, nan_violation, sum(out**2)]``."""
+        ``status_dev`` is a float64[2] device tensor ``[sum(out**2), flags]`` whose second slot holds
+        the two int32 flags ``(saw_nan, nan_violation)``; pass a zeroed slice of a larger buffer as
+        ``status`` to have several launches report through ONE read."""
         frames = _engine.Frames(points)
-        out, sumsq, flags = _engine.map_apply(
+        if status is None:
+            status = torch.zeros(2, dtype=torch.float64, device=_engine.device())
+        out, _, _ = _engine.map_apply(
             frames, self._compile(), nan_mode=1 if self.handle_nans else 0,
             nan_atol=self.nan_check_threshold, want_sumsq=want_sumsq,
+            sumsq=status[0:1] if want_sumsq else None, flags=status[1:2].view(torch.int32),
         )
-        status = torch.cat([flags.to(torch.float64), sumsq if sumsq is not None else flags.new_zeros(1, dtype=torch.float64)])
         return frames, out, status
+
+    @staticmethod
+    def _decode(status_host: np.ndarray) -> Tuple[float, int, int]:
+        """``(sum(out**2), saw_nan, nan_violation)`` from a downloaded status pair."""
+        flags = np.ascontiguousarray(status_host[1:2]).view(np.int32)
+        return float(status_host[0]), int(flags[0]), int(flags[1])
 
     def _finish(self, frames, out, status_host, host_copy=None):
         """``host_copy``: pinned tensor of an already started download (``_engine.start_d2h``)."""
-        if self.handle_nans and status_host[1] != 0:
+        if self.handle_nans and self._decode(status_host)[2] != 0:
             raise ValueError(
                 "NaN handling is on and results seem to depend on NaN "
                 "positions in input array. Check input and standard_matrix."
@@ -147,9 +193,9 @@ class LinearMap:
     def _apply(self, points, want_sumsq: bool = False):
         frames, out, status = self._launch(points, want_sumsq)
         if _engine.sharded():  # every rank must raise (or not) together: the next collective would hang
-            _engine.allreduce_max_(status[:2])
-        host = status.cpu().numpy()  # one synchronising read: NaN flags and the residual sum together
-        return self._finish(frames, out, host), float(host[2])
+            _engine.allreduce_max_(status[1:2].view(torch.int32))
+        host = _engine.to_host(status)  # one synchronising read: NaN flags and the residual sum together
+        return self._finish(frames, out, host), float(host[0])
 
     def __call__(self, points):
         """Map ``(n_steps, n_fg_sites, 3)`` points to ``(n_steps, n_cg_sites, 3)``."""

@@ -11,7 +11,7 @@ import numpy as np
 import scipy.sparse as ss
 import torch
 
-from .. import _engine
+from .. import _engine, _lib
 from ..constraints import Constraints, constraint_lookup_dict, merged_groups
 from ..map import LinearMap, SeperableTMap
 from ..trajectory import ForcesTrajectory
@@ -74,9 +74,96 @@ def force_gram(forces, n_sites: int, constraints: Constraints):
     return _engine.to_host_overlapped(gram), cols
 
 
-# reduced problems at least this large are solved on the device (cuSOLVER through torch.linalg);
-# below it the host solve is faster than the launch + synchronisation overhead
+# reduced problems at least this large are solved on the device by cuSOLVER (through torch.linalg);
+# small ones (n_red <= 128, n_cg <= 32) by the one-CTA kernel agf_qp_equality_small, so that
+# Gram -> solve -> force application never stops at the host; what lies between goes to the host
 _DEVICE_SOLVE_MIN = 512
+
+
+class _DeviceFit:
+    """Result of ``agf_qp_equality_small`` that still lives on the device.
+
+    ``buf`` is ONE float64 device buffer ``[qp status | apply status slots | X (n_cg x n_red)]`` so that
+    ``project_forces`` gets the solver status, both applications' NaN flags, the residual sum and the
+    fitted coefficients with a single read.  ``matrix()`` is what ``LinearMap.standard_matrix`` calls
+    on first access when nobody resolved the fit before."""
+
+    N_HEAD = 6  # [0] qp status (int32), [1:3] coordinate-map status, [3:5] force-map status, [5] spare
+
+    def __init__(self, buf, gram, order, cols, n_red, n_cg, diag, a_mat, solver_args) -> None:
+        self.buf, self.gram, self.order, self.cols = buf, gram, order, cols
+        self.n_red, self.n_cg, self.diag, self.a_mat, self.solver_args = n_red, n_cg, diag, a_mat, solver_args
+        self.expanded: Union[None, np.ndarray] = None
+        self.fell_back = False
+
+    def resolve(self, host_buf: np.ndarray) -> np.ndarray:
+        """Check the solver status in a downloaded copy of ``buf`` and return the expanded matrix
+        (host fallback -- exact solve with its null-space branch -- when the device solve failed)."""
+        if self.expanded is None:
+            status = int(np.ascontiguousarray(host_buf[0:1]).view(np.int32)[0])
+            if status == 0:
+                reduced = host_buf[self.N_HEAD:].reshape(self.n_cg, self.n_red)
+            else:
+                self.fell_back = True
+                gram = self.gram.clone()
+                _lib.call("agf_symmetrize", _engine.ptr(gram), self.n_red, _engine.stream_ptr())
+                qp_mat = _engine.to_host(gram)
+                back = np.empty(self.n_red, dtype=np.int64)
+                back[self.order] = np.arange(self.n_red)
+                qp_mat = qp_mat[back][:, back]
+                qp_mat[np.diag_indices(self.n_red)] += self.diag
+                sol = solve(qp_mat, self.a_mat, np.eye(self.n_cg), self.solver_args)
+                if sol is None:
+                    raise ValueError("Map optimization failed.")
+                reduced = sol.T
+            self.expanded = np.ascontiguousarray(reduced[:, self.cols])
+            self.gram = None
+        return self.expanded
+
+    def matrix(self) -> np.ndarray:
+        if self.expanded is None:
+            self.resolve(_engine.to_host(self.buf))
+        return self.expanded
+
+
+def _equality_rows(coord_map: LinearMap, cols: np.ndarray, n_red: int) -> np.ndarray:
+    """``A = coord_map @ C``: the coordinate-map columns of every group summed (qplinear.py:82)."""
+    n_fg = coord_map.n_fg_sites
+    cmat = np.asarray(coord_map.standard_matrix, dtype=np.float64)
+    if n_fg * coord_map.n_cg_sites <= (1 << 16):  # small: a scatter-add beats building a sparse one-hot
+        a_mat = np.zeros((coord_map.n_cg_sites, n_red))
+        np.add.at(a_mat.T, cols, cmat.T)
+        return a_mat
+    onehot = ss.csr_matrix((np.ones(n_fg), (np.arange(n_fg), cols)), shape=(n_fg, n_red))
+    return np.asarray((onehot.T @ cmat.T).T)
+
+
+def _fit_small_on_device(traj, coord_map: LinearMap, cols: np.ndarray, n_red: int, l2: float,
+                         solver_args) -> SeperableTMap:
+    """Gram (kernel a) -> ``agf_qp_equality_small`` -> a ``LinearMap`` whose coefficients are already
+    where kernel (d) reads them.  Nothing synchronises here when called through ``project_forces``
+    (which reads status + coefficients once, after the applications); a direct call resolves the fit
+    before returning, as the reference raises at fit time."""
+    n_cg = coord_map.n_cg_sites
+    gram, order = _engine.gram_linear_raw(_engine.Frames(traj.forces), cols, n_red)
+    _engine.run_deferred()
+    group_size = np.bincount(cols, minlength=n_red).astype(np.float64)
+    diag = (l2 if l2 > 0.0 else 0.0) * group_size
+    a_mat = _equality_rows(coord_map, cols, n_red)
+    compiled, ucol_of_col = _engine.CompiledMap.from_labels(cols, n_cg, n_red)
+    buf = torch.zeros(_DeviceFit.N_HEAD + n_cg * n_red, dtype=torch.float64, device=gram.device)
+    p = _engine.ptr
+    _lib.call("agf_qp_equality_small", p(gram), n_red, p(_engine.dev_f64(diag[order])) if l2 > 0.0 else p(None),
+              p(_engine.dev_f64(a_mat[:, order])), n_cg, p(_engine.dev_i32(order)), p(buf[_DeviceFit.N_HEAD:]),
+              p(_engine.dev_i32(ucol_of_col[order])), p(compiled.umat_t), p(buf[0:1]), _engine.stream_ptr())
+    fit = _DeviceFit(buf, gram, order, cols, n_red, n_cg, diag, a_mat, solver_args)
+    force_map = LinearMap.from_device_fit(fit, n_cg, cols, compiled)
+    if not _engine.fits_deferred():
+        fit.matrix()  # direct call: synchronise, check the solver status (ValueError on failure)
+        if fit.fell_back:
+            force_map = LinearMap(fit.expanded)
+            force_map._column_labels = cols
+    return SeperableTMap(coord_map=coord_map, force_map=force_map)
 
 
 def qp_linear_map(
@@ -101,6 +188,10 @@ def qp_linear_map(
     cols = reduced_columns(n_fg, constraints)
     n_red = int(cols.max()) + 1
     on_device = backend == "exact" and n_red >= _DEVICE_SOLVE_MIN
+    n_cg = coord_map.n_cg_sites
+    if (backend == "exact" and not on_device and isinstance(coord_map, LinearMap)
+            and _lib.lib().agf_qp_equality_small_supported(n_red, n_cg)):
+        return _fit_small_on_device(traj, coord_map, cols, n_red, l2_regularization, solver_args)
     if on_device:
         qp_mat = _engine.gram_linear(_engine.Frames(traj.forces), cols, n_red)  # stays on the device
         _engine.run_deferred()
@@ -112,14 +203,7 @@ def qp_linear_map(
             qp_mat.diagonal().add_(torch.as_tensor(l2_regularization * group_size, device=qp_mat.device))
         else:
             qp_mat[np.diag_indices(n_red)] += l2_regularization * group_size
-    # A = coord_map @ C : sum the coordinate-map columns of every group
-    cmat = np.asarray(coord_map.standard_matrix, dtype=np.float64)
-    if n_fg * coord_map.n_cg_sites <= (1 << 16):  # small: a scatter-add beats building a sparse one-hot
-        a_mat = np.zeros((coord_map.n_cg_sites, n_red))
-        np.add.at(a_mat.T, cols, cmat.T)
-    else:
-        onehot = ss.csr_matrix((np.ones(n_fg), (np.arange(n_fg), cols)), shape=(n_fg, n_red))
-        a_mat = np.asarray((onehot.T @ cmat.T).T)
+    a_mat = _equality_rows(coord_map, cols, n_red)
     if backend == "exact":
         sol = None
         if on_device:

@@ -170,6 +170,18 @@ int agf_pair_first(const void* xyz, const void* other, int dtype, int32_t n_site
 int agf_pair_screen(const void* xyz, const void* other, int dtype, int64_t n_frames,
                     int32_t n_sites, int32_t n_other, double* m2, void* stream);
 
+/* Ordered compaction of the screened pair matrix (small systems, n_other * n_sites <= 2^18): the
+ * device-side form of constfinder.py:52  nonzero(sds < threshold)  applied to the pruning bound --
+ * pairs with m2 <= bound (bound_dev, a device scalar, overrides `bound` when not NULL) in row-major
+ * order, each with its frame-0 distance (the `shift` of agf_pair_moments) and zeroed accumulators.
+ *   xyz / other   device frame 0 of the arrays passed to agf_pair_screen, [n_sites, 3] / [n_other, 3]
+ *   pairs int32 [cap, 2], shift f64 [cap], acc f64 [cap, 2]   device, written for the survivors
+ *   count int32 [1]  survivors, or -(survivors) when they exceed cap (then nothing else is written)
+ */
+int agf_pair_select(const double* m2, double bound, const double* bound_dev, const void* xyz,
+                    const void* other, int dtype, int32_t n_sites, int32_t n_other, int32_t cap,
+                    int32_t* pairs, double* shift, double* acc, int32_t* count, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * (b) featurised Gram for Multifeaturize([id_feat, gb_feat]).
  * Replaces  src/aggforce/qp/featlinearmap.py:361-370 (einsum + kbt*div + reg.T @ reg) and the
@@ -255,6 +267,27 @@ int agf_feat_apply(const void* coords, const void* forces, int dtype, int64_t n_
                    const int32_t* bead_sites, const double* bead_w, int32_t n_cg,
                    const double* centers, int32_t nb, double width, double clip,
                    const double* coefs, void* out, int out_dtype, double* sumsq, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Equality-constrained QP of qp_linear_map on the device, small reduced problems.
+ * Replaces  src/aggforce/qp/qplinear.py:76-86 (P += l2 C'C; per bead solve_qp(P, 0, A, e_bead)):
+ * all beads at once,  X = P^-1 A' (A P^-1 A')^-1,  one CTA, P in shared memory.
+ *   gram      device f64 [n_red, n_red]; only the (element-wise) upper triangle is read, which is
+ *             what agf_gram_linear accumulates -- no symmetrise pass needed in between
+ *   diag_add  device f64 [n_red] added to the diagonal (l2 * group size) or NULL
+ *   a_mat     device f64 [n_cg, n_red] equality rows (cmap C), same column order as gram
+ *   x_out     device f64 [n_cg, n_red]:  x_out[c, x_index[p]] = X[p, c]   (x_index: a permutation)
+ *   u_out     device f64 [n_ucol, n_cg] or NULL:  u_out[u_index[p], c] = X[p, c]  -- the `umat_t`
+ *             operand of agf_map_apply, so the fitted map is applied without a host round trip
+ *   status    device int32 [1], written only on failure: 1 P not positive definite, 2 Schur
+ *             complement not positive definite, 3 non-finite solution, 4 equality constraints missed by
+ *             more than 1e-6 (caller falls back to the host)
+ * Limits: n_red <= 128, n_cg <= 32 (agf_qp_equality_small_supported).
+ */
+int agf_qp_equality_small(const double* gram, int32_t n_red, const double* diag_add,
+                          const double* a_mat, int32_t n_cg, const int32_t* x_index, double* x_out,
+                          const int32_t* u_index, double* u_out, int32_t* status, void* stream);
+int agf_qp_equality_small_supported(int32_t n_red, int32_t n_cg);
 
 /* ------------------------------------------------------------------------------------
  * Validation projections on random Gaussian force fields.

@@ -272,3 +272,112 @@ def test_config4_shape_properties():
     mapped, sumsq = lm.apply_with_sumsq(forces)
     assert abs(sumsq / float((mapped.double() ** 2).sum().item()) - 1) < 1e-12
     assert guess_pairwise_constraints(coords) == cons
+
+
+# --------------------------------------------------------------------------------------
+# device QP for small reduced problems (agf_qp_equality_small) and the one-read project_forces
+# --------------------------------------------------------------------------------------
+def _qp_small(gram_upper, diag, a_mat, x_index, u_index=None, n_ucol=0):
+    import ctypes as C
+
+    from aggforce_b200 import _engine, _lib
+
+    n, m = gram_upper.shape[0], a_mat.shape[0]
+    dev = "cuda"
+    g = torch.as_tensor(gram_upper, device=dev).contiguous()
+    d = None if diag is None else torch.as_tensor(diag, device=dev).contiguous()
+    a = torch.as_tensor(a_mat, device=dev).contiguous()
+    xi = torch.as_tensor(np.asarray(x_index, dtype=np.int32), device=dev)
+    x = torch.full((m, n), float("nan"), dtype=torch.float64, device=dev)
+    ui = None if u_index is None else torch.as_tensor(np.asarray(u_index, dtype=np.int32), device=dev)
+    u = None if u_index is None else torch.full((n_ucol, m), float("nan"), dtype=torch.float64, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    p = _engine.ptr
+    _lib.call("agf_qp_equality_small", p(g), n, p(d), p(a), m, p(xi), p(x), p(ui), p(u), p(status), _engine.stream_ptr())
+    return x.cpu().numpy(), None if u is None else u.cpu().numpy(), int(status.item())
+
+
+@pytest.mark.parametrize("n,m", [(97, 10), (6, 2), (128, 32), (33, 1)])
+def test_qp_equality_small_matches_oracle(n, m):
+    rng = np.random.default_rng(n * 100 + m)
+    r = rng.normal(size=(3 * n + 5, n)) * rng.uniform(0.5, 300.0, size=n)
+    gram = r.T @ r
+    diag = rng.uniform(0.0, 1e3, size=n)
+    a = np.zeros((m, n))
+    a[np.arange(m), rng.choice(n, size=m, replace=False)] = 1.0
+    a += 0.1 * rng.normal(size=(m, n)) * (rng.random((m, n)) < 0.2)
+    want = oracle.solve_equality_qp(gram + np.diag(diag), a, np.eye(m)).T  # [m, n]
+    upper = np.triu(gram) + np.tril(np.full((n, n), np.nan), k=-1)  # the kernel must not read below the diagonal
+    perm = rng.permutation(n).astype(np.int32)
+    uidx = rng.permutation(n).astype(np.int32)
+    x, u, status = _qp_small(upper, diag, a, perm, uidx, n)
+    assert status == 0
+    got = np.empty_like(x)
+    got[:, np.arange(n)] = x[:, perm]  # x_out[c, x_index[p]] = X[p, c]
+    assert rel_fro(got, want) < 1e-9  # north star: weights within 1e-6
+    assert np.abs(a @ got.T - np.eye(m)).max() < 1e-9
+    assert np.array_equal(u[uidx].T, got)
+    x0, _, status0 = _qp_small(np.triu(gram), None, a, np.arange(n))
+    assert status0 == 0 and rel_fro(x0, oracle.solve_equality_qp(gram, a, np.eye(m)).T) < 1e-7
+
+
+def test_qp_equality_small_reports_failures():
+    rng = np.random.default_rng(0)
+    n, m = 12, 3
+    r = rng.normal(size=(4, n))  # rank 4 < n: P is singular
+    a = np.zeros((m, n))
+    a[np.arange(m), [0, 5, 9]] = 1.0
+    _, _, status = _qp_small(np.triu(r.T @ r), None, a, np.arange(n))
+    assert status != 0
+    r = rng.normal(size=(40, n))
+    a[2] = a[1]  # dependent equality rows: Schur complement singular
+    _, _, status = _qp_small(np.triu(r.T @ r), None, a, np.arange(n))
+    assert status != 0
+    g = np.triu(r.T @ r)
+    g[3, 7] = np.nan
+    _, _, status = _qp_small(g, None, a, np.arange(n))
+    assert status != 0
+
+
+def test_project_forces_falls_back_to_the_host_solver_when_the_device_solve_declines():
+    """Fewer frames than reduced columns and no l2: P is singular, agf_qp_equality_small reports it,
+    the host solver's null-space branch answers and the forces are re-applied with ITS map."""
+    from aggforce_b200 import LinearMap, project_forces, qp_linear_map
+    from aggforce_b200.trajectory import Trajectory
+
+    rng = np.random.default_rng(5)
+    coords = rng.normal(size=(2, 9, 3)).astype(np.float32)
+    forces = rng.normal(size=(2, 9, 3)).astype(np.float32)
+    cmap = LinearMap([[0], [4]], n_fg_sites=9)
+    res = project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds=set())
+    w = res["tmap"].force_map.standard_matrix
+    ref = oracle.qp_linear_weights(forces, cmap.standard_matrix, set(), 0.0)
+    assert np.abs(cmap.standard_matrix @ w.T - np.eye(2)).max() < 1e-9
+    # the null-space solution maps these two frames to (numerically) zero forces: absolute bars
+    assert np.abs(res["mapped_forces"] - oracle.apply_map(forces, w)).max() < 1e-12
+    assert abs(res["residual"] - oracle.force_smoothness(oracle.apply_map(forces, w))) < 1e-20
+    assert oracle.force_smoothness(oracle.apply_map(forces, ref)) < 1e-20
+    # a direct call resolves (and falls back) before returning
+    tm = qp_linear_map(Trajectory(coords=coords, forces=forces), cmap, constraints=set())
+    assert np.abs(cmap.standard_matrix @ tm.force_map.standard_matrix.T - np.eye(2)).max() < 1e-9
+
+
+def test_device_fit_is_lazy_and_editable():
+    """project_forces keeps the fitted matrix on the device until somebody asks; an in-place edit of
+    the downloaded matrix must still reach later applications."""
+    from aggforce_b200 import LinearMap, project_forces
+
+    rng = np.random.default_rng(6)
+    coords = rng.normal(size=(300, 12, 3)).astype(np.float32)
+    forces = rng.normal(size=(300, 12, 3)).astype(np.float32)
+    cmap = LinearMap([[0], [4], [8]], n_fg_sites=12)
+    cons = {frozenset({0, 1}), frozenset({4, 5})}
+    res = project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds=cons, l2_regularization=10.0)
+    fm = res["tmap"].force_map
+    w = oracle.qp_linear_weights(forces, cmap.standard_matrix, cons, 10.0)
+    assert fm.n_cg_sites == 3 and fm.n_fg_sites == 12
+    assert rel_fro(fm.standard_matrix, w) < 1e-9
+    assert rel_fro(fm(forces), oracle.apply_map(forces, w)) < 1e-9
+    fm.standard_matrix[1, 3] += 2.0
+    assert rel_fro(fm(forces), oracle.apply_map(forces, fm.standard_matrix)) < 1e-9
+    assert rel_fro((2.0 * fm).standard_matrix, 2.0 * fm.standard_matrix) < 1e-15
