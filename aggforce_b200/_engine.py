@@ -249,17 +249,100 @@ def shard_rank() -> int:
     return _dist().get_rank(_Sharding.group) if sharded() else 0
 
 
+class _PeerLink:
+    """Symmetric peer-mapped buffers for ``agf_peer_exchange`` (one-shot all-reduce / all-gather of
+    small float64 payloads over NVLink, csrc/peer.cu).  ``torch.distributed._symmetric_memory`` only
+    does the rendezvous (allocation + exchange of the mappings); the exchange itself is our kernel
+    on the caller's stream.  Falls back to the library collectives when the rendezvous is not
+    available (decision agreed by all ranks)."""
+
+    SLOT_DOUBLES = 1 << 16  # 512 KiB per slot: the 175 x 175 screening matrix is 245 KB
+    links: dict = {}
+
+    def __init__(self, group) -> None:
+        import os
+        import sys
+
+        dist = _dist()
+        self.ok = False
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.seq = 0
+        want = (os.environ.get("AGF_PEER_REDUCE", "1") != "0" and dist.get_backend(group) == "nccl"
+                and self.world <= 16)
+        good = 0
+        if want:
+            try:
+                import torch.distributed._symmetric_memory as symm
+
+                nbytes = int(_lib.lib().agf_peer_buffer_bytes(self.SLOT_DOUBLES))
+                self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device())
+                self.buf.zero_()
+                self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+                ptrs = [int(v) for v in self.handle.buffer_ptrs]
+                self.d_ptrs = torch.tensor(ptrs, dtype=torch.int64, device=device())
+                self.err = torch.zeros(1, dtype=torch.int32, device=device())
+                good = 1
+            except Exception as exc:  # noqa: BLE001  (any failure means: use the library collectives)
+                print(f"aggforce_b200: peer-memory exchange unavailable ({type(exc).__name__}: {exc}); "
+                      "using NCCL collectives", file=sys.stderr)
+        flag = torch.tensor([good], dtype=torch.int32, device=device())
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)  # also orders the zeroing before any signal
+        torch.cuda.synchronize()
+        self.ok = bool(flag.item())
+
+    def exchange(self, t: torch.Tensor, op: int) -> torch.Tensor:
+        """op 0 sum / 1 max: reduced IN PLACE; op 2: returns the gathered ``[world, numel]`` tensor."""
+        self.seq += 1
+        out = t if op != 2 else torch.empty((self.world, t.numel()), dtype=torch.float64, device=t.device)
+        _lib.call("agf_peer_exchange", ptr(self.d_ptrs), self.rank, self.world, C.c_uint32(self.seq & 0xFFFFFFFF or 1),
+                  op, ptr(t), ptr(out), t.numel(), self.SLOT_DOUBLES, ptr(self.err), stream_ptr())
+        return out
+
+
+def _peer_link(t: torch.Tensor) -> Optional[_PeerLink]:
+    """The peer link of the active sharding group if ``t`` qualifies (float64, contiguous, fits)."""
+    if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and 0 < t.numel() <= _PeerLink.SLOT_DOUBLES):
+        return None
+    key = id(_Sharding.group)
+    link = _PeerLink.links.get(key)
+    if link is None:
+        link = _PeerLink.links[key] = _PeerLink(_Sharding.group)
+    return link if link.ok else None
+
+
+def peer_exchange_errors() -> int:
+    """Non-zero if any one-shot exchange gave up waiting for a peer (tests / bench check this)."""
+    return sum(int(link.err.item()) for link in _PeerLink.links.values() if link.ok)
+
+
 def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
     if sharded():
+        link = _peer_link(t)
+        if link is not None:
+            return link.exchange(t, 0)
         _dist().all_reduce(t, group=_Sharding.group)
     return t
 
 
 def allreduce_max_(t: torch.Tensor) -> torch.Tensor:
     if sharded():
+        link = _peer_link(t)
+        if link is not None:
+            return link.exchange(t, 1)
         dist = _dist()
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_Sharding.group)
     return t
+
+
+def allgather_dev(t: torch.Tensor) -> torch.Tensor:
+    """``[world, numel]`` float64 device tensor holding every rank's ``t``."""
+    link = _peer_link(t)
+    if link is not None:
+        return link.exchange(t, 2)
+    dist = _dist()
+    outs = [torch.empty_like(t) for _ in range(dist.get_world_size(_Sharding.group))]
+    dist.all_gather(outs, t, group=_Sharding.group)
+    return torch.stack(outs).reshape(len(outs), -1)
 
 
 def allreduce_min_(t: torch.Tensor) -> torch.Tensor:
@@ -789,8 +872,7 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
                 m2 = torch.where(torch.triu(torch.ones_like(m2), diagonal=1) > 0, m2, torch.full_like(m2, float("inf")))
         counts = torch.zeros(world, dtype=torch.float64, device=dev)
         counts[rank] = float(t_local)
-        buf = torch.cat([m2.reshape(-1), counts])
-        dist.all_reduce(buf, op=dist.ReduceOp.MAX, group=_Sharding.group)
+        buf = allreduce_max_(torch.cat([m2.reshape(-1), counts]))
         bound_dev = (float(threshold) ** 2 * buf[-world:].sum() * (1.0 + 1e-6) + 1e-300).reshape(1)
         m2 = buf[:-world].reshape(n_o, n)
     pairs = shift = acc = None
@@ -890,15 +972,13 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
     else:
         mean, m2_local = torch.zeros_like(shift), torch.zeros_like(shift)
     rec = torch.cat([torch.full((1,), float(t_local), dtype=torch.float64, device=dev), mean, m2_local])
-    dist = _dist()
-    outs = [torch.empty_like(rec) for _ in range(dist.get_world_size(_Sharding.group))]
-    dist.all_gather(outs, rec, group=_Sharding.group)
+    gathered = allgather_dev(rec)
     # the surviving pair list rides along (as float64) so that ONE synchronising read returns everything
     extra = [] if pairs_host is not None else [pairs.to(torch.float64).reshape(-1)]
-    flat = to_host(torch.cat([torch.stack(outs).reshape(-1), *extra]))
-    n_rec = rec.numel()
-    parts = [flat[i * n_rec : (i + 1) * n_rec] for i in range(len(outs))]
+    flat = to_host(torch.cat([gathered.reshape(-1), *extra]))
+    n_rec, n_ranks = rec.numel(), gathered.shape[0]
+    parts = [flat[i * n_rec : (i + 1) * n_rec] for i in range(n_ranks)]
     if pairs_host is None:
-        pairs_host = flat[len(outs) * n_rec :].astype(np.int64)
+        pairs_host = flat[n_ranks * n_rec :].astype(np.int64)
     sd = merge_moments(parts, n_pairs)
     return pairs_host.reshape(-1, 2), sd

@@ -48,11 +48,12 @@ SIGNATURES = {
     "agf_gauss_field_moments": [_vp, _vp, C.c_int, _i64, _i32, _vp, _i32, _dbl, _vp, _vp],
     "agf_sq_gaussian_forces": [_vp, C.c_int, _i64, _i32, _dbl, _dbl, _vp, C.c_int, _vp],
     "agf_qp_equality_small": [_vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp],
+    "agf_peer_exchange": [_vp, _i32, _i32, C.c_uint32, _i32, _vp, _vp, _i64, _i64, _vp, _vp],
     "agf_probe_dmma": [_i32, _vp, _vp, _vp],
     "agf_probe_read": [_vp, _i64, _vp, _vp],
     "agf_synth_frames": [_vp, _vp, _vp, _i32, _i64, _i64, _u64, _flt, _flt, _flt, _vp, _vp, _vp],
 }
-PLAIN = {"agf_version": (C.c_int, []), "agf_qp_equality_small_supported": (C.c_int, [_i32, _i32]), "agf_last_error": (C.c_char_p, []), "agf_device_sm_count": (C.c_int, []),
+PLAIN = {"agf_version": (C.c_int, []), "agf_peer_buffer_bytes": (C.c_size_t, [_i64]), "agf_qp_equality_small_supported": (C.c_int, [_i32, _i32]), "agf_last_error": (C.c_char_p, []), "agf_device_sm_count": (C.c_int, []),
          "agf_gram_linear_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64]),
          "agf_map_apply_workspace_bytes": (C.c_size_t, [C.c_int, _i32, _i32, _i32, _i32, _i64]),
          "agf_gram_feat_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i64])}

@@ -82,17 +82,18 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
     coords_in, forces_in = _engine.Frames(coords), _engine.Frames(forces)
     if auto:
         constrained_inds = guess_pairwise_constraints(coords_in)
-    # ONE status buffer for both applications: [sum(out_c^2), flags_c, sum(out_f^2), flags_f]
+    # ONE status buffer for both applications: [sum(out_c^2), sum(out_f^2), flags_c, flags_f]
     stat = torch.zeros(4, dtype=torch.float64, device=_engine.device())
+    slots_c, slots_f = (stat[0:1], stat[2:3]), (stat[1:2], stat[3:4])
     # The coordinate map does not depend on the fit: its application is deferred to the moment the
     # fit has enqueued its last kernel (or launched right here when the fit never asks), so it runs
     # on the GPU while the host builds / solves the map.
     early: Dict[str, Any] = {}
     if isinstance(coord_map, LinearMap) and coords is not None:
         if method is qp_linear_map:  # [Gram][coordinate map] | QP
-            _engine.defer(lambda: early.update(launch=coord_map._launch(coords_in, status=stat[0:2])))
+            _engine.defer(lambda: early.update(launch=coord_map._launch(coords_in, slots=slots_c)))
         elif method is constraint_aware_uni_map:  # runs while the host builds the uniform map
-            early["launch"] = coord_map._launch(coords_in, status=stat[0:2])
+            early["launch"] = coord_map._launch(coords_in, slots=slots_c)
         # other methods return maps that are applied as a whole (featurised / augmented): nothing to hoist
     try:
         with _engine.deferred_fits():  # a device-side fit reports through the read below
@@ -114,11 +115,11 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
             _engine.clear_deferred()
             if "launch" in early:
                 early.clear()
-                stat[0:2].zero_()
+                stat.zero_()
         _engine.run_deferred()
-        fc, oc, _ = early["launch"] if "launch" in early else cm._launch(coords_in, status=stat[0:2])
+        fc, oc, _ = early["launch"] if "launch" in early else cm._launch(coords_in, slots=slots_c)
         host_c = _engine.start_d2h(oc) if fc.on_host else None  # downloads overlap the force upload
-        ff, of, _ = fm._launch(forces_in, want_sumsq=True, status=stat[2:4])
+        ff, of, _ = fm._launch(forces_in, want_sumsq=True, slots=slots_f)
         host_f = _engine.start_d2h(of) if ff.on_host else None
         pend = fm._pending if fm._matrix is None else None
         n_elem = float(np.prod(of.shape))
@@ -126,15 +127,15 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
             # residual sums are added over ranks, and so are the NaN flags, so that a violated NaN
             # protocol raises on every rank (a lone raiser would leave the others in the next collective)
             # (flags are >= 0, so their sum is non-zero exactly when any rank's is: ONE collective)
-            payload = torch.cat([stat[0::2], stat[1::2].view(torch.int32).to(torch.float64),
+            payload = torch.cat([stat[0:2], stat[2:4].view(torch.int32).to(torch.float64),
                                  torch.full((1,), n_elem, dtype=torch.float64, device=stat.device)])
             _engine.allreduce_sum_(payload)
             got = _engine.read_many([payload] + ([pend.buf] if pend is not None else []))
             pay = got[0]
             sums, flags, n_elem = pay[0:2], (pay[2:6] != 0).astype(np.int32), float(pay[6])
             status = np.empty(4)
-            status[0::2] = sums
-            status[1::2] = flags.view(np.float64)
+            status[0:2] = sums
+            status[2:4] = flags.view(np.float64)
         else:
             got = _engine.read_many([stat] + ([pend.buf] if pend is not None else []))
             status = got[0]
@@ -146,13 +147,13 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
             fm = LinearMap(pend.expanded, handle_nans=fm.handle_nans, nan_check_threshold=fm.nan_check_threshold)
             fm._column_labels = pend.cols
             traj_map = SeperableTMap(coord_map=cm, force_map=fm)
-            mapped_coords = cm._finish(fc, oc, status[0:2], host_c)
+            mapped_coords = cm._finish(fc, oc, status[2:3], host_c)
             mapped_forces = fm(forces_in)
             residual = _global_mean_sq(float((torch.as_tensor(mapped_forces).double() ** 2).sum()), mapped_forces.shape)
         else:
-            mapped_coords = cm._finish(fc, oc, status[0:2], host_c)
-            mapped_forces = fm._finish(ff, of, status[2:4], host_f)
-            residual = float(status[2] / n_elem)
+            mapped_coords = cm._finish(fc, oc, status[2:3], host_c)
+            mapped_forces = fm._finish(ff, of, status[3:4], host_f)
+            residual = float(status[1] / n_elem)
     else:
         _engine.clear_deferred()
         mapped = traj_map(t)

@@ -155,30 +155,34 @@ class LinearMap:
                                                           column_labels=self._column_labels))
         return self._compiled[1]
 
-    def _launch(self, points, want_sumsq: bool = False, status: Optional[torch.Tensor] = None):
+    def _launch(self, points, want_sumsq: bool = False, status: Optional[torch.Tensor] = None,
+                slots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
         """Enqueue the kernel; returns ``(frames, out_dev, status_dev)`` without synchronising.
         ``status_dev`` is a float64[2] device tensor ``[sum(out**2), flags]`` whose second slot holds
-        the two int32 flags ``(saw_nan, nan_violation)``; pass a zeroed slice of a larger buffer as
-        ``status`` to have several launches report through ONE read."""
+        the two int32 flags ``(saw_nan, nan_violation)``.  ``slots = (sum_slot, flag_slot)`` -- two
+        zeroed one-element float64 views of a larger buffer -- makes several launches report through
+        ONE read (then ``status_dev`` is ``None``)."""
         frames = _engine.Frames(points)
-        if status is None:
-            status = torch.zeros(2, dtype=torch.float64, device=_engine.device())
+        if slots is None:
+            if status is None:
+                status = torch.zeros(2, dtype=torch.float64, device=_engine.device())
+            slots = (status[0:1], status[1:2])
         out, _, _ = _engine.map_apply(
             frames, self._compile(), nan_mode=1 if self.handle_nans else 0,
             nan_atol=self.nan_check_threshold, want_sumsq=want_sumsq,
-            sumsq=status[0:1] if want_sumsq else None, flags=status[1:2].view(torch.int32),
+            sumsq=slots[0] if want_sumsq else None, flags=slots[1].view(torch.int32),
         )
         return frames, out, status
 
     @staticmethod
-    def _decode(status_host: np.ndarray) -> Tuple[float, int, int]:
-        """``(sum(out**2), saw_nan, nan_violation)`` from a downloaded status pair."""
-        flags = np.ascontiguousarray(status_host[1:2]).view(np.int32)
-        return float(status_host[0]), int(flags[0]), int(flags[1])
+    def _decode_flags(flag_slot_host: np.ndarray) -> Tuple[int, int]:
+        """``(saw_nan, nan_violation)`` from a downloaded flag slot (one float64 holding two int32)."""
+        flags = np.ascontiguousarray(flag_slot_host).reshape(-1)[:1].view(np.int32)
+        return int(flags[0]), int(flags[1])
 
-    def _finish(self, frames, out, status_host, host_copy=None):
+    def _finish(self, frames, out, flag_slot_host, host_copy=None):
         """``host_copy``: pinned tensor of an already started download (``_engine.start_d2h``)."""
-        if self.handle_nans and self._decode(status_host)[2] != 0:
+        if self.handle_nans and self._decode_flags(flag_slot_host)[1] != 0:
             raise ValueError(
                 "NaN handling is on and results seem to depend on NaN "
                 "positions in input array. Check input and standard_matrix."
@@ -195,7 +199,7 @@ class LinearMap:
         if _engine.sharded():  # every rank must raise (or not) together: the next collective would hang
             _engine.allreduce_max_(status[1:2].view(torch.int32))
         host = _engine.to_host(status)  # one synchronising read: NaN flags and the residual sum together
-        return self._finish(frames, out, host), float(host[0])
+        return self._finish(frames, out, host[1:2]), float(host[0])
 
     def __call__(self, points):
         """Map ``(n_steps, n_fg_sites, 3)`` points to ``(n_steps, n_cg_sites, 3)``."""

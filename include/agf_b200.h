@@ -326,6 +326,23 @@ int agf_synth_frames(const float* ref_pos, const int32_t* parent, const float* b
                      float* forces, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * One-shot exchange of small float64 payloads between the ranks of a frame-sharded fit, over
+ * NVLink peer memory (the all-reduce of Gram / pair moments / residual sums; the
+ * reference has no multi-device code).  Every rank owns one symmetric buffer of
+ * agf_peer_buffer_bytes(slot_doubles) bytes, zero-initialised, that all peers have mapped;
+ * peer_ptrs is a DEVICE array [world] with every rank's buffer address in this process.  One
+ * kernel on `stream`: copy-in, signal / wait (release / acquire, system scope), combine.
+ *   op 0: out[i] = sum_r in_r[i]   op 1: out[i] = max_r in_r[i] (NaN wins)
+ *   op 2: out[r * count + i] = in_r[i] (all-gather)
+ *   seq   call number, the same on all ranks, starting at 1 and increasing by 1 per call
+ *   error device int32 [1], set to 1 if a peer's signal never arrived (result then invalid)
+ */
+size_t agf_peer_buffer_bytes(int64_t slot_doubles);
+int agf_peer_exchange(const uint64_t* peer_ptrs, int32_t rank, int32_t world, uint32_t seq,
+                      int32_t op, const double* in, double* out, int64_t count,
+                      int64_t slot_doubles, int32_t* error, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Roofline probes (bench.py measures its denominators in the run that quotes them; no reference
  * counterpart).  agf_probe_dmma: every SM streams independent DMMA.8x8x4 tiles for `iters`
  * iterations; *flop_out = flops issued; sink: device f64 [sm_count * 8 * 256].

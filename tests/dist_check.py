@@ -81,12 +81,36 @@ def main() -> None:
     c2_all = [torch.empty_like(c2) for _ in range(world)]
     dist.all_gather(c2_all, c2)
     ok = ok and all(torch.equal(c2_all[0], c) for c in c2_all)
+    # the one-shot peer-memory exchange (csrc/peer.cu) against the library collectives
+    peer = "n/a"
+    with agf.frame_sharding():
+        g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+        for n in (1, 7, 2048, 2049, 30633, 65536):
+            x = torch.randn(n, dtype=torch.float64, device="cuda", generator=g)
+            x[n // 2] = float(rank)
+            want_sum, want_max = x.clone(), x.clone()
+            dist.all_reduce(want_sum)
+            dist.all_reduce(want_max, op=dist.ReduceOp.MAX)
+            outs = [torch.empty_like(x) for _ in range(world)]
+            dist.all_gather(outs, x)
+            got_sum = _engine.allreduce_sum_(x.clone())
+            got_max = _engine.allreduce_max_(x.clone())
+            got_all = _engine.allgather_dev(x.clone())
+            # sums in fixed rank order: every rank holds bit-identical results (NCCL's order may differ)
+            ok = ok and torch.allclose(got_sum, want_sum, rtol=1e-14, atol=1e-14) and torch.equal(got_max, want_max)
+            ok = ok and torch.equal(got_all, torch.stack(outs))
+            same = [torch.empty_like(got_sum) for _ in range(world)]
+            dist.all_gather(same, got_sum)
+            ok = ok and all(torch.equal(same[0], t) for t in same)
+        link = _engine._PeerLink.links.get(id(None))
+        peer = "on" if (link is not None and link.ok) else "off (NCCL fallback)"
+        ok = ok and _engine.peer_exchange_errors() == 0
     flag = torch.tensor([int(ok)], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"dist_check world={world}: constraints={len(res['constraints'])} rel_w={rel_w:.2e} rel_f={rel_f:.2e} "
               f"residual={res['residual']:.6g} feat rel_coef={rel_c:.2e} rel_mapped={rel_ff:.2e} "
-              f"-> {'OK' if flag.item() else 'FAILED'}")
+              f"peer exchange {peer} -> {'OK' if flag.item() else 'FAILED'}")
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
 
