@@ -626,6 +626,14 @@ def csr_from_labels(labels: np.ndarray, n_groups: int) -> Tuple[np.ndarray, np.n
 # --------------------------------------------------------------------------------------
 # kernel wrappers
 # --------------------------------------------------------------------------------------
+import os as _os
+
+# int8 / tcgen05 Gram (csrc/gram_i8.cu): on by default for long float32 trajectories with n_red <= 97;
+# AGF_GRAM_I8=0 selects the FP64 DMMA kernel everywhere (A/B measurements, bit-exact FP64 products)
+_GRAM_I8 = [_os.environ.get("AGF_GRAM_I8", "1") != "0"]
+_GRAM_I8_MIN_FRAMES = 8192
+
+
 def gram_linear_raw(frames: Frames, col_of_site: np.ndarray, n_red: int) -> Tuple[torch.Tensor, np.ndarray]:
     """Kernel (a): accumulated and all-reduced second-moment matrix as the kernels leave it --
     ``(gram f64 [n_red, n_red] with the element-wise UPPER triangle valid, order)`` where
@@ -640,6 +648,14 @@ def gram_linear_raw(frames: Frames, col_of_site: np.ndarray, n_red: int) -> Tupl
     # 3- and 4-member columns is then also the one holding pairs, and the ragged last group holds
     # singles -- the number of (warp-wide) f64 additions per frame drops from 33 to 12 at cln025
     order = np.argsort(-sizes, kind="stable")  # internal position -> caller's column
+    use_i8 = _GRAM_I8[0] and frames.np_dtype == np.float32 and n_red <= 97 and n_red and 1 <= int(sizes.max()) <= 4
+    if use_i8:
+        # int8 / tcgen05 kernel: a lane owns the column quad 4q..4q+3; slot c of every quad should hold
+        # columns of similar group size (uniform member loops): deal the size-sorted columns slot by slot
+        n_main = min(n_red, 96)
+        slot_major = np.full(96, -1, dtype=np.int64)
+        slot_major[(np.arange(n_main) % 24) * 4 + np.arange(n_main) // 24] = order[:n_main]
+        order = np.concatenate([slot_major[slot_major >= 0], order[n_main:]]) if n_main == 96 else order
     if n_red > 128:
         # packed-panel path: no per-lane member walk to balance; keep the caller's order (columns follow
         # their first site), so the pack kernel's gathers of neighbouring columns hit neighbouring sites
@@ -650,7 +666,23 @@ def gram_linear_raw(frames: Frames, col_of_site: np.ndarray, n_red: int) -> Tupl
     ptr_, sites = csr_from_labels(internal, n_red)
     d_ptr, d_sites = dev_i32(ptr_), dev_i32(sites)
     gram = torch.zeros((n_red, n_red), dtype=torch.float64, device=device())
+    max_group = int(sizes.max()) if n_red else 0
     for _, piece in frames.pieces():
+        need_i8 = 0
+        if (_GRAM_I8[0] and piece.dtype == torch.float32 and n_red <= 97 and 1 <= max_group <= 4
+                and piece.shape[0] >= _GRAM_I8_MIN_FRAMES):
+            need_i8 = int(_lib.lib().agf_gram_linear_i8_workspace_bytes(frames.n_sites, n_red, piece.shape[0]))
+        if need_i8 > 0:  # tcgen05 int8 slices (Ozaki): the Blackwell tensor-core path
+            ws = workspace(need_i8)
+            isz = sizes[order]  # group size of every internal column
+            slot_members = 0
+            for c in range(4):
+                members = isz[c:96:4]
+                slot_members |= (int(members.max()) if members.size else 1) << (8 * c)
+            _lib.call("agf_gram_linear_i8", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites, ptr(d_ptr),
+                      ptr(d_sites), n_red, max_group, C.c_uint32(slot_members), ptr(gram), ptr(ws),
+                      C.c_size_t(ws.numel()), stream_ptr())
+            continue
         need = int(_lib.lib().agf_gram_linear_workspace_bytes(frames.n_sites, n_red, piece.shape[0]))
         if need > 0:  # n_red > 128: pack group sums once, TMA-fed SYRK
             ws = workspace(need)

@@ -407,6 +407,10 @@ def main() -> None:
     launches_of = {k: len(v) for k, v in per_kernel.items()}
     algo = {  # summed over the launches of one step
         "agf_gram_linear": ("tensor", (3 * n_red * (n_red + 1) + 3 * n) * T * launches_of.get("agf_gram_linear", 1)),
+        # the int8 / tcgen05 kernel computes the same float64 Gram: same algorithmic flops, quoted against the
+        # FP64 tensor roof it replaces (its own int8 roof, 3.4 POP/s measured by tools/ozaki/i8_syrk_probe.cu,
+        # is 40x away; see kernels[...]["note"])
+        "agf_gram_linear_i8": ("tensor", (3 * n_red * (n_red + 1) + 3 * n) * T * launches_of.get("agf_gram_linear_i8", 1)),
         "agf_pair_moments": ("hbm", 12 * n * T * launches_of.get("agf_pair_moments", 1)),
         "agf_map_apply": ("hbm", (12 * n + 24 * n_cg) * T * launches_of.get("agf_map_apply", 1)),
         # slice: the coordinate map of both project_forces calls (10 sites); sparse: the uniform force map
@@ -415,6 +419,14 @@ def main() -> None:
         "agf_map_apply_sparse": ("hbm", (uni_nnz * 12 + 24 * n_cg) * T * launches_of.get("agf_map_apply_sparse", 1)),
     }
     kernels = kernel_table(per_kernel, algo, peaks, hbm_peak, traffic)
+    if "agf_gram_linear_i8" in kernels:
+        k8 = kernels["agf_gram_linear_i8"]
+        k8["hbm_gbs"] = 12 * n * T * k8["launches"] / (k8["ms_total"] * 1e-3) / 1e9
+        k8["hbm_frac"] = k8["hbm_gbs"] / hbm_peak
+        k8["note"] = ("float64 Gram through int8 digit planes on tcgen05 (TMEM accumulators): `achieved` is "
+                      "float64-EQUIVALENT flop/s (algorithmic flops of the float64 Gram / time) against the FP64 "
+                      "DMMA peak that bounds the FP64 formulation; the kernel itself is bounded by its digit "
+                      "fill, not by the int8 tensor pipe (about 25 % active) nor by HBM (hbm_frac)")
     dominant = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
     roofline = None
     if dominant and "frac" in kernels[dominant]:

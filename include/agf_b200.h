@@ -75,6 +75,26 @@ int agf_gram_linear_ws(const void* forces, int dtype, int64_t n_frames, int32_t 
                        const int32_t* col_ptr, const int32_t* col_sites, int32_t n_red,
                        double* gram, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same Gram through the 5th-generation tensor cores (tcgen05.mma kind::i8, accumulators in
+ * TMEM): float32 forces, n_red <= 97, constraint groups of at most 4 sites.  Group sums are scaled per
+ * column by a power of two taken from a sample of the frames, rounded to 39-bit fixed point and split
+ * into five signed 8-bit digits; the 15 digit-plane products with s + t <= 4 are accumulated exactly
+ * in int32 and recombined in float64 (Ozaki scheme; 2e-12 relative Frobenius error on cln025, bar
+ * 1e-9).  Frames holding a value outside the fixed-point range (or a non-finite one) are added in
+ * float64 by a second kernel.  Accumulates into the upper triangle of gram like agf_gram_linear.
+ *   max_group   largest number of sites in one reduced column
+ *   slot_members  performance hint, 0 = none: byte c = largest group size among the columns
+ *               4 q + c (q = 0..23), i.e. of "slot c" of the column quads a lane of the fill owns; with
+ *               columns dealt to the slots by size (largest groups to slot 0) the fill runs straight-line
+ *   workspace   device, agf_gram_linear_i8_workspace_bytes(...) bytes (0: shape not supported --
+ *               use agf_gram_linear), 16-byte aligned
+ */
+size_t agf_gram_linear_i8_workspace_bytes(int32_t n_sites, int32_t n_red, int64_t n_frames);
+int agf_gram_linear_i8(const void* forces, int dtype, int64_t n_frames, int32_t n_sites,
+                       const int32_t* col_ptr, const int32_t* col_sites, int32_t n_red,
+                       int32_t max_group, uint32_t slot_members, double* gram, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* gram[j, i] = gram[i, j] for i < j (device f64 [n, n]). */
 int agf_symmetrize(double* gram, int32_t n, void* stream);
 

@@ -381,3 +381,80 @@ def test_device_fit_is_lazy_and_editable():
     fm.standard_matrix[1, 3] += 2.0
     assert rel_fro(fm(forces), oracle.apply_map(forces, fm.standard_matrix)) < 1e-9
     assert rel_fro((2.0 * fm).standard_matrix, 2.0 * fm.standard_matrix) < 1e-15
+
+
+# --------------------------------------------------------------------------------------
+# int8 / tcgen05 Gram (agf_gram_linear_i8): the Blackwell tensor-core path of kernel (a)
+# --------------------------------------------------------------------------------------
+def _gram_caller_order(forces, cols, n_red, use_i8):
+    from aggforce_b200 import _engine
+
+    prev = _engine._GRAM_I8[0]
+    _engine._GRAM_I8[0] = use_i8
+    try:
+        g, order = _engine.gram_linear_raw(_engine.Frames(forces), cols, n_red)
+    finally:
+        _engine._GRAM_I8[0] = prev
+    u = torch.triu(g).cpu().numpy()
+    full = u + np.triu(u, 1).T
+    out = np.empty_like(full)
+    out[np.ix_(order, order)] = full
+    return out
+
+
+def test_gram_i8_matches_the_float64_oracle():
+    """North-star bar for the Gram: 1e-9 relative Frobenius against float64 numpy.  The int8-sliced
+    tensor-core kernel (5 signed 8-bit digits, 15 exact int32 products) sits near 1e-11."""
+    from aggforce_b200 import _lib
+    from aggforce_b200.qp.qplinear import reduced_columns
+    from aggforce_b200.synth import chignolin_topology, synth_trajectory_host
+
+    topo = chignolin_topology()
+    cols = reduced_columns(175, topo.xh_constraints)
+    n_red = int(cols.max()) + 1
+    _, forces = synth_trajectory_host(topo, 20011, seed=21)  # odd count: head / tail chunks, odd sub-chunk totals
+    ref = oracle.gram_linear(forces, topo.xh_constraints)
+    n0 = _lib.LAUNCHES["count"]
+    _lib.timing(True)
+    got = _gram_caller_order(forces, cols, n_red, True)
+    names = {n for n, _ in _lib.timing_records()}
+    _lib.timing(False)
+    assert "agf_gram_linear_i8" in names and _lib.LAUNCHES["count"] > n0
+    assert rel_fro(got, ref) < 1e-9
+    assert rel_fro(got, ref) < 1e-10  # what the scheme delivers on this data
+    assert rel_fro(_gram_caller_order(forces, cols, n_red, False), ref) < 1e-13  # the FP64 DMMA kernel
+    # an unaligned device view (frames 3..) and a smaller system (n_red < 96: no ride-along column)
+    dev = torch.as_tensor(forces, device="cuda")
+    assert rel_fro(_gram_caller_order(dev[3:], cols, n_red, True), oracle.gram_linear(forces[3:], topo.xh_constraints)) < 1e-9
+    sub = {c for c in topo.xh_constraints if max(c) < 100}
+    scols = reduced_columns(100, sub)
+    fsub = np.ascontiguousarray(forces[:, :100])
+    assert rel_fro(_gram_caller_order(fsub, scols, int(scols.max()) + 1, True), oracle.gram_linear(fsub, sub)) < 1e-9
+
+
+def test_gram_i8_hands_out_of_range_frames_to_the_float64_pass():
+    """Values far outside the scale taken from the sample (and non-finite ones) must not be clipped: their
+    frames are added exactly by the leftover kernel."""
+    from aggforce_b200.qp.qplinear import reduced_columns
+    from aggforce_b200.synth import chignolin_topology, synth_trajectory_host
+
+    topo = chignolin_topology()
+    cols = reduced_columns(175, topo.xh_constraints)
+    n_red = int(cols.max()) + 1
+    _, forces = synth_trajectory_host(topo, 12000, seed=22)
+    forces[7000, 5, 1] = 3.0e7
+    forces[9000, 100, 2] = -1.0e9
+    forces[11999, 174, 0] = 4.0e8
+    ref = oracle.gram_linear(forces, topo.xh_constraints)
+    got = _gram_caller_order(forces, cols, n_red, True)
+    assert rel_fro(got, ref) < 1e-12  # the three huge frames dominate and are exact
+    small = ref.copy()
+    mask = np.abs(ref) < 1e12  # entries the outliers do not touch: still at the 1e-9 bar
+    assert np.abs(got - ref)[mask].max() < 1e-9 * np.abs(ref[mask]).max()
+    forces[8000, 17, 0] = np.nan
+    got = _gram_caller_order(forces, cols, n_red, True)
+    want = _gram_caller_order(forces, cols, n_red, False)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(got).any()
+    ok = ~np.isnan(want)
+    assert np.abs(got[ok] - want[ok]).max() <= 1e-9 * np.abs(want[ok]).max()
+    del small
