@@ -97,7 +97,8 @@ def test_gram_is_additive_over_frame_shards(topo):
     whole, _ = force_gram(forces, topo.n_sites, topo.xh_constraints)
     parts = sum(force_gram(forces[a:b], topo.n_sites, topo.xh_constraints)[0]
                 for a, b in [(0, 12_345), (12_345, 30_001), (30_001, 50_000)])
-    assert rel_fro(whole, parts) < 1e-12
+    # (the int8 / tcgen05 kernel scales every call by its own sample: additive to its 1e-11, not to the last bit)
+    assert rel_fro(whole, parts) < 1e-10
     sub = forces[:3000].cpu().numpy()
     assert rel_fro(force_gram(forces[:3000], topo.n_sites, topo.xh_constraints)[0],
                    oracle.gram_linear(sub, topo.xh_constraints)) < GRAM_TOL
