@@ -47,7 +47,9 @@ def device() -> torch.device:
 
 
 def stream_ptr() -> C.c_void_p:
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The current torch stream of the current device as a raw ``cudaStream_t`` (the C-level getter:
+    ``torch.cuda.current_stream()`` builds a Python Stream object on every call)."""
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
 
 def ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
@@ -293,7 +295,7 @@ class _PeerLink:
     def exchange(self, t: torch.Tensor, op: int) -> torch.Tensor:
         """op 0 sum / 1 max: reduced IN PLACE; op 2: returns the gathered ``[world, numel]`` tensor."""
         self.seq += 1
-        out = t if op != 2 else torch.empty((self.world, t.numel()), dtype=torch.float64, device=t.device)
+        out = t if (op & 0xff) != 2 else torch.empty((self.world, t.numel()), dtype=torch.float64, device=t.device)
         _lib.call("agf_peer_exchange", ptr(self.d_ptrs), self.rank, self.world, C.c_uint32(self.seq & 0xFFFFFFFF or 1),
                   op, ptr(t), ptr(out), t.numel(), self.SLOT_DOUBLES, ptr(self.err), stream_ptr())
         return out
@@ -331,6 +333,18 @@ def allreduce_max_(t: torch.Tensor) -> torch.Tensor:
             return link.exchange(t, 1)
         dist = _dist()
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_Sharding.group)
+    return t
+
+
+def allreduce_sum_max_(t: torch.Tensor, n_sum: int) -> torch.Tensor:
+    """In place: the first ``n_sum`` values are summed over ranks, the rest max-ed (one message)."""
+    if sharded():
+        link = _peer_link(t)
+        if link is not None:
+            return link.exchange(t, 3 | (int(n_sum) << 8))
+        dist = _dist()
+        dist.all_reduce(t[:n_sum], group=_Sharding.group)
+        dist.all_reduce(t[n_sum:], op=dist.ReduceOp.MAX, group=_Sharding.group)
     return t
 
 
@@ -634,53 +648,60 @@ _GRAM_I8 = [_os.environ.get("AGF_GRAM_I8", "1") != "0"]
 _GRAM_I8_MIN_FRAMES = 8192
 
 
-def gram_linear_raw(frames: Frames, col_of_site: np.ndarray, n_red: int) -> Tuple[torch.Tensor, np.ndarray]:
+class GramPlan:
+    """Column order and device-side CSR of the constraint groups for kernel (a) -- a function of the
+    column table only, so fits over the same constraints build it once."""
+
+    def __init__(self, col_of_site: np.ndarray, n_red: int, want_i8: bool = True) -> None:
+        col_of_site = np.asarray(col_of_site, dtype=np.int64)
+        sizes = np.bincount(col_of_site[col_of_site >= 0], minlength=n_red)
+        # largest groups first: with lane = column in 32-column groups the group holding the few
+        # 3- and 4-member columns is then also the one holding pairs, and the ragged last group holds
+        # singles -- the number of (warp-wide) f64 additions per frame drops from 33 to 12 at cln025
+        order = np.argsort(-sizes, kind="stable")  # internal position -> caller's column
+        self.i8_shape = bool(want_i8 and n_red and n_red <= 97 and 1 <= int(sizes.max()) <= 4)
+        if self.i8_shape and n_red >= 96:
+            # int8 / tcgen05 kernel: a lane owns the column quad 4q..4q+3; slot c of every quad should hold
+            # columns of similar group size (uniform member loops): deal the size-sorted columns slot by slot
+            slot_major = np.empty(96, dtype=np.int64)
+            slot_major[(np.arange(96) % 24) * 4 + np.arange(96) // 24] = order[:96]
+            order = np.concatenate([slot_major, order[96:]])
+        if n_red > 128:
+            # packed-panel path: no per-lane member walk to balance; keep the caller's order (columns follow
+            # their first site), so the pack kernel's gathers of neighbouring columns hit neighbouring sites
+            order = np.arange(n_red)
+        rank = np.empty(n_red, dtype=np.int64)
+        rank[order] = np.arange(n_red)
+        internal = np.where(col_of_site >= 0, rank[np.maximum(col_of_site, 0)], -1)
+        ptr_, sites = csr_from_labels(internal, n_red)
+        self.order, self.n_red = order, n_red
+        self.d_ptr, self.d_sites = dev_i32(ptr_), dev_i32(sites)
+        self.max_group = int(sizes.max()) if n_red else 0
+        isz = sizes[order]  # group size of every internal column
+        self.slot_members = 0
+        for c in range(4):
+            members = isz[c:96:4]
+            self.slot_members |= (int(members.max()) if members.size else 1) << (8 * c)
+
+
+def gram_linear_raw(frames: Frames, col_of_site: np.ndarray, n_red: int,
+                    plan: Optional[GramPlan] = None) -> Tuple[torch.Tensor, np.ndarray]:
     """Kernel (a): accumulated and all-reduced second-moment matrix as the kernels leave it --
     ``(gram f64 [n_red, n_red] with the element-wise UPPER triangle valid, order)`` where
-    ``order[p]`` is the caller's column held at internal position ``p``.
-
-    Internally the reduced columns are ordered by group size (largest first) so that the lanes of a
-    warp walk member lists of similar length while they build the f64 panel.
-    """
-    col_of_site = np.asarray(col_of_site, dtype=np.int64)
-    sizes = np.bincount(col_of_site[col_of_site >= 0], minlength=n_red)
-    # largest groups first: with lane = column in 32-column groups the group holding the few
-    # 3- and 4-member columns is then also the one holding pairs, and the ragged last group holds
-    # singles -- the number of (warp-wide) f64 additions per frame drops from 33 to 12 at cln025
-    order = np.argsort(-sizes, kind="stable")  # internal position -> caller's column
-    use_i8 = _GRAM_I8[0] and frames.np_dtype == np.float32 and n_red <= 97 and n_red and 1 <= int(sizes.max()) <= 4
-    if use_i8:
-        # int8 / tcgen05 kernel: a lane owns the column quad 4q..4q+3; slot c of every quad should hold
-        # columns of similar group size (uniform member loops): deal the size-sorted columns slot by slot
-        n_main = min(n_red, 96)
-        slot_major = np.full(96, -1, dtype=np.int64)
-        slot_major[(np.arange(n_main) % 24) * 4 + np.arange(n_main) // 24] = order[:n_main]
-        order = np.concatenate([slot_major[slot_major >= 0], order[n_main:]]) if n_main == 96 else order
-    if n_red > 128:
-        # packed-panel path: no per-lane member walk to balance; keep the caller's order (columns follow
-        # their first site), so the pack kernel's gathers of neighbouring columns hit neighbouring sites
-        order = np.arange(n_red)
-    rank = np.empty(n_red, dtype=np.int64)
-    rank[order] = np.arange(n_red)
-    internal = np.where(col_of_site >= 0, rank[np.maximum(col_of_site, 0)], -1)
-    ptr_, sites = csr_from_labels(internal, n_red)
-    d_ptr, d_sites = dev_i32(ptr_), dev_i32(sites)
+    ``order[p]`` is the caller's column held at internal position ``p``."""
+    if plan is None:
+        plan = GramPlan(col_of_site, n_red, want_i8=_GRAM_I8[0] and frames.np_dtype == np.float32)
+    d_ptr, d_sites, order = plan.d_ptr, plan.d_sites, plan.order
     gram = torch.zeros((n_red, n_red), dtype=torch.float64, device=device())
-    max_group = int(sizes.max()) if n_red else 0
     for _, piece in frames.pieces():
         need_i8 = 0
-        if (_GRAM_I8[0] and piece.dtype == torch.float32 and n_red <= 97 and 1 <= max_group <= 4
+        if (_GRAM_I8[0] and plan.i8_shape and piece.dtype == torch.float32
                 and piece.shape[0] >= _GRAM_I8_MIN_FRAMES):
             need_i8 = int(_lib.lib().agf_gram_linear_i8_workspace_bytes(frames.n_sites, n_red, piece.shape[0]))
         if need_i8 > 0:  # tcgen05 int8 slices (Ozaki): the Blackwell tensor-core path
             ws = workspace(need_i8)
-            isz = sizes[order]  # group size of every internal column
-            slot_members = 0
-            for c in range(4):
-                members = isz[c:96:4]
-                slot_members |= (int(members.max()) if members.size else 1) << (8 * c)
             _lib.call("agf_gram_linear_i8", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites, ptr(d_ptr),
-                      ptr(d_sites), n_red, max_group, C.c_uint32(slot_members), ptr(gram), ptr(ws),
+                      ptr(d_sites), n_red, plan.max_group, C.c_uint32(plan.slot_members), ptr(gram), ptr(ws),
                       C.c_size_t(ws.numel()), stream_ptr())
             continue
         need = int(_lib.lib().agf_gram_linear_workspace_bytes(frames.n_sites, n_red, piece.shape[0]))
@@ -787,8 +808,16 @@ class CompiledMap:
         ptr_, sites = csr_from_labels(rank[labels], n_labels)
         self.n_ucol, self.nnz = int(n_labels), int(sites.size)
         self.ucol_ptr, self.ucol_sites = dev_i32(ptr_), dev_i32(sites)
-        self.umat_t = torch.empty((n_labels, n_cg), dtype=torch.float64, device=device())
+        self.umat_t = None  # filled per fit: see with_values
         return self, rank
+
+    def with_values(self, umat_t: torch.Tensor) -> "CompiledMap":
+        """A map sharing this one's (immutable) structure with its own coefficient operand."""
+        import copy
+
+        other = copy.copy(self)
+        other.umat_t = umat_t
+        return other
 
 
 def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float, want_sumsq: bool = False,
@@ -858,6 +887,16 @@ _RESCREEN_FRAMES = 4096
 _SELECT_CAP = 8192  # survivor capacity of the one-kernel compaction (small systems)
 
 
+def _screen_frames(t_est_total: float, threshold: float, t_local: int) -> int:
+    """Frames of the literal all-pairs screen.  A flexible pair is pruned once its partial sum of squared
+    deviations exceeds threshold^2 * T_total, which grows with the trajectory: 32 frames are enough up
+    to about a million frames at the default threshold; longer (e.g. sharded) trajectories get a
+    proportionally longer prefix, so that the survivors are the O(n) rigid pairs and no second pruning
+    pass (with its extra collective) is needed."""
+    want = _SCREEN_FRAMES * max(1.0, threshold * threshold * t_est_total / 1.0)
+    return int(min(t_local, min(512, int(np.ceil(want / 32.0)) * 32)))
+
+
 def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
     """Kernel (c) with exact progressive pruning.  Returns ``(pairs int64 [P, 2], sd float64 [P])``
     for every pair that survived pruning (the caller applies ``sd < threshold``)."""
@@ -867,8 +906,8 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
     t_local = frames.n_frames
     empty = (np.zeros((0, 2), dtype=np.int64), np.zeros(0))
     # Under frame sharding with a small pair matrix the global frame count travels with the screening
-    # statistics (one MAX all-reduce of [M2 | per-rank counts], no separate count round trip).
-    fused = sharded() and n * n_o <= (1 << 22) and _dist().get_backend(_Sharding.group) == "nccl"
+    # statistics (one MAX exchange of [M2 | per-rank counts], no separate count round trip).
+    fused = sharded() and n * n_o <= (1 << 16) - 64 and _dist().get_backend(_Sharding.group) == "nccl"
     t_total = None if fused else global_count(t_local)
     if not fused and (t_total == 0 or t_local == 0 and not sharded()):
         return empty
@@ -876,6 +915,7 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
     # M2 never exceeds the total, so anything above the (slightly widened) bound is pruned for good.
     bound = None if fused else float(threshold) ** 2 * t_total * (1.0 + 1e-6) + 1e-300
     dev = device()
+    world = _dist().get_world_size(_Sharding.group) if sharded() else 1
 
     def other_piece(piece_t0: int, count: int) -> Optional[torch.Tensor]:
         if other is None:
@@ -883,39 +923,41 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
         return other.resident()[piece_t0 : piece_t0 + count]
 
     # ---- stage 0: literal all-pairs pass over a short prefix
-    n0 = min(t_local, _SCREEN_FRAMES)
+    n0 = _screen_frames(float(t_total if t_total is not None else world * t_local), float(threshold), t_local)
     x0 = o0 = None
+    n_mat = n_o * n
+    buf = torch.empty(n_mat + (world if fused else 0), dtype=torch.float64, device=dev)
+    m2 = buf[:n_mat].view(n_o, n)
     if n0 > 0:
         x0 = frames.prefix(n0)
         o0 = None if other is None else other.prefix(n0)
         if o0 is not None and o0.dtype != x0.dtype:
             o0 = o0.to(x0.dtype)
-        m2 = torch.empty((n_o, n), dtype=torch.float64, device=dev)
         _lib.call("agf_pair_screen", ptr(x0), ptr(o0), dtype_code(x0), n0, n, n_o, ptr(m2), stream_ptr())
+    elif fused:  # a rank without frames constrains nothing: zeros under the MAX (inf below the diagonal)
+        m2.zero_()
+        if other is None:
+            m2.copy_(torch.where(torch.triu(torch.ones_like(m2), diagonal=1) > 0, m2, torch.full_like(m2, float("inf"))))
     else:
-        m2 = torch.full((n_o, n), float("inf"), dtype=torch.float64, device=dev)
-    bound_dev = None
+        m2.fill_(float("inf"))
+    counts_dev = None
     if fused:
-        dist = _dist()
-        world, rank = dist.get_world_size(_Sharding.group), dist.get_rank(_Sharding.group)
-        if n0 == 0:  # a rank without frames constrains nothing
-            m2 = torch.zeros_like(m2)
-            if other is None:
-                m2 = torch.where(torch.triu(torch.ones_like(m2), diagonal=1) > 0, m2, torch.full_like(m2, float("inf")))
-        counts = torch.zeros(world, dtype=torch.float64, device=dev)
-        counts[rank] = float(t_local)
-        buf = allreduce_max_(torch.cat([m2.reshape(-1), counts]))
-        bound_dev = (float(threshold) ** 2 * buf[-world:].sum() * (1.0 + 1e-6) + 1e-300).reshape(1)
-        m2 = buf[:-world].reshape(n_o, n)
-    pairs = shift = acc = None
-    if n0 > 0 and n * n_o <= (1 << 18) and (fused or not sharded()):
+        rank = _dist().get_rank(_Sharding.group)
+        mine = np.zeros(world)
+        mine[rank] = float(t_local)
+        buf[n_mat:].copy_(_dev_cached(mine))  # cached: the same shard sizes come back every call
+        allreduce_max_(buf)
+        counts_dev = buf[n_mat:]
+    pairs = shift = acc = pairs_host = None
+    if n0 > 0 and n_mat <= (1 << 18) and (fused or not sharded()):
         # small systems: ONE kernel turns the screened matrix into the ordered survivor list, their
         # frame-0 distances and zeroed accumulators; one small read returns the count and the list
-        cap = min(n * n_o, _SELECT_CAP)
+        cap = min(n_mat, _SELECT_CAP)
         ints = torch.empty(1 + 2 * cap, dtype=torch.int32, device=dev)
         fl = torch.empty(3 * cap, dtype=torch.float64, device=dev)
-        _lib.call("agf_pair_select", ptr(m2), 0.0 if bound is None else bound, ptr(bound_dev), ptr(x0), ptr(o0),
-                  dtype_code(x0), n, n_o, cap, ptr(ints[1:]), ptr(fl), ptr(fl[cap:]), ptr(ints), stream_ptr())
+        _lib.call("agf_pair_select", ptr(m2), float(threshold) ** 2 if fused else bound, ptr(counts_dev), world if fused else 0,
+                  ptr(x0), ptr(o0), dtype_code(x0), n, n_o, cap, ptr(ints[1:]), ptr(fl), ptr(fl[cap:]), ptr(ints),
+                  stream_ptr())
         host_ints = to_host(ints)
         n_pairs = int(host_ints[0])
         if n_pairs == 0:
@@ -924,8 +966,10 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
             pairs_host = host_ints[1 : 1 + 2 * n_pairs].reshape(-1, 2).astype(np.int64)
             pairs = ints[1 : 1 + 2 * n_pairs].view(n_pairs, 2)
             shift, acc = fl[:n_pairs], fl[cap : cap + 2 * n_pairs].view(n_pairs, 2)
+    bound_dev = None
     if pairs is None:  # general path (large systems, or more survivors than the capacity)
         if fused:
+            bound_dev = (float(threshold) ** 2 * counts_dev.sum() * (1.0 + 1e-6) + 1e-300).reshape(1)
             alive = m2 <= bound_dev
         else:
             if n0 > 0:
@@ -937,7 +981,6 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
             allreduce_min_(alive)
         pairs = torch.nonzero(alive).to(torch.int32).contiguous()  # [P, 2] = (i over other, j over xyz)
         del alive
-        pairs_host = None
         n_pairs = int(pairs.shape[0])
         if n_pairs == 0:
             return empty
@@ -948,7 +991,6 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
             _lib.call("agf_pair_first", ptr(xf), ptr(of_), dtype_code(xf), n, n_o, ptr(pairs), n_pairs, ptr(shift),
                       stream_ptr())
         acc = torch.zeros((n_pairs, 2), dtype=torch.float64, device=dev)
-    del m2
 
     # ---- stage 1..: stream all frames for the survivors
     def run(a: int, b: int) -> None:
@@ -960,14 +1002,16 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
                       ptr(pairs), int(pairs.shape[0]), ptr(shift), ptr(acc), stream_ptr())
 
     # second pruning point after a few thousand frames: bounds the survivor count for flexible
-    # molecules (at n = 5000 the 32-frame screen leaves ~10^5 pairs, 4096 frames leave the bonded
-    # ones).  Under sharding every rank holds the same pair list and a pair dead on any rank is dead
-    # globally (M2_global >= M2_rank), so the keep masks are combined with one MIN all-reduce; the
-    # branch depends on the (global) pair count only, so all ranks take it together.
+    # molecules (at n = 5000 the screen leaves ~10^5 pairs, 4096 frames leave the bonded ones).  Under
+    # sharding every rank holds the same pair list and a pair dead on any rank is dead globally
+    # (M2_global >= M2_rank), so the keep masks are combined with one MIN all-reduce; the branch depends
+    # on the (global) pair count only, so all ranks take it together.
     done = 0
     if n_pairs > 4 * max(n, n_o) and (sharded() or t_local > 4 * _RESCREEN_FRAMES):
         done = min(_RESCREEN_FRAMES, t_local)
         run(0, done)
+        if fused and bound_dev is None:
+            bound_dev = (float(threshold) ** 2 * counts_dev.sum() * (1.0 + 1e-6) + 1e-300).reshape(1)
         if done > 0:
             m2p = acc[:, 1] - acc[:, 0] ** 2 / done
             keep_mask = m2p <= (bound_dev if fused else bound)
@@ -985,32 +1029,25 @@ def pair_constraints(frames: Frames, other: Optional[Frames], threshold: float):
             return empty
     run(done, t_local)
 
-    # ---- per-rank (count, mean, M2), gathered across ranks, merged (Chan) in float64 on the host;
-    #      P is O(n).  One synchronising read.
+    # ---- per-rank (count, shift, running sums) go to the host as they are -- gathered across ranks
+    #      under sharding -- and the moments are formed and merged (Chan) there in float64; P is O(n).
+    #      One synchronising read.
+    def record(t_cnt: float, sh: np.ndarray, ac: np.ndarray) -> np.ndarray:
+        with np.errstate(invalid="ignore", over="ignore", divide="ignore"):
+            d = max(t_cnt, 1.0)
+            return np.concatenate([[t_cnt], sh + ac[:, 0] / d, ac[:, 1] - ac[:, 0] ** 2 / d])
+
     if not sharded():
-        # shift and the two running sums come back as they are; the moments are formed on the host
         want = [shift, acc] if pairs_host is not None else [shift, acc, pairs]
         got = read_many(want)
-        sh, ac = got[0], got[1]
         if pairs_host is None:
             pairs_host = got[2].astype(np.int64)
-        with np.errstate(invalid="ignore", over="ignore"):
-            rec = np.concatenate([[float(t_local)], sh + ac[:, 0] / max(t_local, 1),
-                                  ac[:, 1] - ac[:, 0] ** 2 / max(t_local, 1)])
-        return pairs_host.reshape(-1, 2), merge_moments([rec], n_pairs)
-    if t_local > 0:
-        mean = shift + acc[:, 0] / t_local
-        m2_local = acc[:, 1] - acc[:, 0] ** 2 / t_local
-    else:
-        mean, m2_local = torch.zeros_like(shift), torch.zeros_like(shift)
-    rec = torch.cat([torch.full((1,), float(t_local), dtype=torch.float64, device=dev), mean, m2_local])
-    gathered = allgather_dev(rec)
-    # the surviving pair list rides along (as float64) so that ONE synchronising read returns everything
-    extra = [] if pairs_host is not None else [pairs.to(torch.float64).reshape(-1)]
-    flat = to_host(torch.cat([gathered.reshape(-1), *extra]))
-    n_rec, n_ranks = rec.numel(), gathered.shape[0]
-    parts = [flat[i * n_rec : (i + 1) * n_rec] for i in range(n_ranks)]
+        return pairs_host.reshape(-1, 2), merge_moments([record(float(t_local), got[0], got[1])], n_pairs)
+    packed = torch.cat([_dev_cached(np.array([float(t_local)])), shift, acc.reshape(-1)])
+    gathered = allgather_dev(packed)
+    want = [gathered] if pairs_host is not None else [gathered, pairs]
+    got = read_many(want)
     if pairs_host is None:
-        pairs_host = flat[n_ranks * n_rec :].astype(np.int64)
-    sd = merge_moments(parts, n_pairs)
-    return pairs_host.reshape(-1, 2), sd
+        pairs_host = got[1].astype(np.int64)
+    parts = [record(float(row[0]), row[1 : 1 + n_pairs], row[1 + n_pairs :].reshape(n_pairs, 2)) for row in got[0]]
+    return pairs_host.reshape(-1, 2), merge_moments(parts, n_pairs)

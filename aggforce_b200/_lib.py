@@ -33,7 +33,7 @@ SIGNATURES = {
     "agf_map_apply_slice": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _vp, C.c_int, _vp, C.c_int, _dbl, _vp, _vp],
     "agf_pair_moments": [_vp, _vp, C.c_int, _i64, _i32, _i32, _vp, _i64, _vp, _vp, _vp],
     "agf_pair_first": [_vp, _vp, C.c_int, _i32, _i32, _vp, _i64, _vp, _vp],
-    "agf_pair_select": [_vp, _dbl, _vp, _vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
+    "agf_pair_select": [_vp, _dbl, _vp, _i32, _vp, _vp, C.c_int, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp],
     "agf_pair_screen": [_vp, _vp, C.c_int, _i64, _i32, _i32, _vp, _vp],
     "agf_gram_feat": [_vp, _vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _dbl, _dbl,
                       _dbl, _vp, _vp],

@@ -82,9 +82,12 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
     coords_in, forces_in = _engine.Frames(coords), _engine.Frames(forces)
     if auto:
         constrained_inds = guess_pairwise_constraints(coords_in)
-    # ONE status buffer for both applications: [sum(out_c^2), sum(out_f^2), flags_c, flags_f]
-    stat = torch.zeros(4, dtype=torch.float64, device=_engine.device())
-    slots_c, slots_f = (stat[0:1], stat[2:3]), (stat[1:2], stat[3:4])
+    # ONE status buffer for both applications: [sum(out_c^2), sum(out_f^2), n_elements, flags_c, flags_f]
+    # (each flag slot holds two int32: saw_nan, nan_violation).  Under frame sharding the first three are
+    # summed and the flag slots max-ed over the ranks by one exchange -- as float64 bit patterns two small
+    # non-negative int32 order like the pair (violation, saw), so a violation on any rank survives.
+    stat = torch.zeros(5, dtype=torch.float64, device=_engine.device())
+    slots_c, slots_f = (stat[0:1], stat[3:4]), (stat[1:2], stat[4:5])
     # The coordinate map does not depend on the fit: its application is deferred to the moment the
     # fit has enqueued its last kernel (or launched right here when the fit never asks), so it runs
     # on the GPU while the host builds / solves the map.
@@ -124,21 +127,16 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
         pend = fm._pending if fm._matrix is None else None
         n_elem = float(np.prod(of.shape))
         if _engine.sharded():
-            # residual sums are added over ranks, and so are the NaN flags, so that a violated NaN
-            # protocol raises on every rank (a lone raiser would leave the others in the next collective)
-            # (flags are >= 0, so their sum is non-zero exactly when any rank's is: ONE collective)
-            payload = torch.cat([stat[0:2], stat[2:4].view(torch.int32).to(torch.float64),
-                                 torch.full((1,), n_elem, dtype=torch.float64, device=stat.device)])
-            _engine.allreduce_sum_(payload)
-            got = _engine.read_many([payload] + ([pend.buf] if pend is not None else []))
-            pay = got[0]
-            sums, flags, n_elem = pay[0:2], (pay[2:6] != 0).astype(np.int32), float(pay[6])
-            status = np.empty(4)
-            status[0:2] = sums
-            status[2:4] = flags.view(np.float64)
-        else:
-            got = _engine.read_many([stat] + ([pend.buf] if pend is not None else []))
-            status = got[0]
+            # residual numerator / denominator are summed over ranks and the NaN flags max-ed, so that a
+            # violated NaN protocol raises on every rank (a lone raiser would leave the others in the next
+            # collective): ONE message
+            stat[2:3].copy_(_engine.dev_f64([n_elem]))
+            _engine.allreduce_sum_max_(stat, 3)
+        got = _engine.read_many([stat] + ([pend.buf] if pend is not None else []))
+        st = got[0]
+        if _engine.sharded():
+            n_elem = float(st[2])
+        status = np.array([st[0], st[1], st[3], st[4]])
         if pend is not None:
             fm._matrix = pend.resolve(got[1])  # raises ValueError("Map optimization failed.") like the host path
         if pend is not None and pend.fell_back:

@@ -31,6 +31,7 @@ def guess_pairwise_constraints(xyz, cross_xyz=None, threshold: float = 1e-3) -> 
     pairs, sd = _engine.pair_constraints(x, o, threshold)
     with np.errstate(invalid="ignore"):
         hit = sd < threshold
+    found = pairs[hit].tolist()  # Python ints in one pass
     if o is None:
-        return {frozenset((int(i), int(j))) for i, j in pairs[hit]}
-    return {(int(i), int(j)) for i, j in pairs[hit]}
+        return {frozenset(p) for p in found}
+    return {(p[0], p[1]) for p in found}

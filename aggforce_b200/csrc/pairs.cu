@@ -130,28 +130,43 @@ __global__ void pair_first_kernel(const T* __restrict__ xyz, const T* __restrict
   shift[pidx] = pair_dist<T>(other + (int64_t)i * 3, xyz + (int64_t)j * 3);
 }
 
-// all pairs over a short frame prefix; thread (j fastest) -> coalesced reads of xyz[t, j]
+// all pairs over a short frame prefix.  Block = one site i of `other` x 32 sites j of `xyz` (coalesced
+// reads of xyz[t, j]) x 8 frame slices: the eight warps of a block split the frames of the prefix and
+// combine their (s1, s2) through shared memory, so a longer prefix costs latency, not a longer serial loop.
 template <typename T>
 __global__ void __launch_bounds__(256) pair_screen_kernel(const T* __restrict__ xyz, const T* __restrict__ other,
                                                           int64_t n_frames, int n_sites, int n_other, bool self,
                                                           double* __restrict__ m2) {
-  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int i = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (i >= n_other || j >= n_sites) return;
-  double* dst = m2 + (int64_t)i * n_sites + j;
-  if (self && i >= j) {
-    *dst = __longlong_as_double(0x7ff0000000000000LL);
-    return;
+  __shared__ double red[2][8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  const int i = blockIdx.y;
+  const bool live = j < n_sites && !(self && i >= j);
+  double s1 = 0.0, s2 = 0.0;
+  if (live) {
+    const double c = pair_dist<T>(other + (int64_t)i * 3, xyz + (int64_t)j * 3);  // frame 0
+    for (int64_t t = slice; t < n_frames; t += 8) {
+      const double e = pair_dist<T>(other + (t * n_other + i) * 3, xyz + (t * n_sites + j) * 3) - c;
+      s1 += e;
+      s2 = fma(e, e, s2);
+    }
   }
-  double c = 0.0, s1 = 0.0, s2 = 0.0;
-  for (int64_t t = 0; t < n_frames; ++t) {
-    const double d = pair_dist<T>(other + (t * n_other + i) * 3, xyz + (t * n_sites + j) * 3);
-    if (t == 0) c = d;
-    const double e = d - c;
-    s1 += e;
-    s2 = fma(e, e, s2);
+  red[0][slice][lane] = s1;
+  red[1][slice][lane] = s2;
+  __syncthreads();
+  if (slice == 0 && j < n_sites) {
+    double* dst = m2 + (int64_t)i * n_sites + j;
+    if (!live) {
+      *dst = __longlong_as_double(0x7ff0000000000000LL);
+      return;
+    }
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      s1 += red[0][k][lane];
+      s2 += red[1][k][lane];
+    }
+    *dst = s2 - s1 * s1 / (double)n_frames;
   }
-  *dst = s2 - s1 * s1 / (double)n_frames;
 }
 
 // Ordered compaction of the screened pair matrix by ONE CTA (small systems: n_other * n_sites <= 2^18):
@@ -163,7 +178,7 @@ constexpr int kSelectThreads = 1024;
 
 template <typename T>
 __global__ void __launch_bounds__(kSelectThreads) pair_select_kernel(const double* __restrict__ m2, double bound,
-                                                                     const double* __restrict__ bound_dev,
+                                                                     const double* __restrict__ counts, int n_counts,
                                                                      const T* __restrict__ xyz0,
                                                                      const T* __restrict__ other0, int n_sites,
                                                                      int n_other, int cap, int32_t* __restrict__ pairs,
@@ -175,7 +190,13 @@ __global__ void __launch_bounds__(kSelectThreads) pair_select_kernel(const doubl
   const int total = n_sites * n_other;
   const int per = (total + kSelectThreads - 1) / kSelectThreads;
   const int lo = min(total, (int)threadIdx.x * per), hi = min(total, lo + per);
-  const double b = bound_dev ? __ldg(bound_dev) : bound;
+  // sharded runs: `bound` holds threshold^2 and the (reduced) per-rank frame counts follow the matrix
+  double b = bound;
+  if (counts) {
+    double total = 0.0;
+    for (int r = 0; r < n_counts; ++r) total += __ldg(counts + r);
+    b = bound * total * (1.0 + 1e-6) + 1e-300;
+  }
   int mine = 0;
   for (int e = lo; e < hi; ++e) mine += (__ldg(m2 + e) <= b) ? 1 : 0;
   // block-wide exclusive scan of `mine`
@@ -309,7 +330,7 @@ extern "C" int agf_pair_screen(const void* xyz, const void* other, int dtype, in
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool self = (other == nullptr || other == xyz);
   const int n_o = self ? n_sites : n_other;
-  dim3 grid((n_sites + 31) / 32, (n_o + 7) / 8);
+  dim3 grid((n_sites + 31) / 32, n_o);
   AGF_REQUIRE(grid.y <= 65535, "agf_pair_screen: too many sites in `other` (%d)", n_o);
   if (dtype == AGF_F32)
     pair_screen_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(xyz),
@@ -323,7 +344,7 @@ extern "C" int agf_pair_screen(const void* xyz, const void* other, int dtype, in
   return AGF_OK;
 }
 
-extern "C" int agf_pair_select(const double* m2, double bound, const double* bound_dev, const void* xyz,
+extern "C" int agf_pair_select(const double* m2, double bound, const double* counts, int32_t n_counts, const void* xyz,
                                const void* other, int dtype, int32_t n_sites, int32_t n_other, int32_t cap,
                                int32_t* pairs, double* shift, double* acc, int32_t* count, void* stream) {
   using namespace agf;
@@ -335,11 +356,11 @@ extern "C" int agf_pair_select(const double* m2, double bound, const double* bou
               "agf_pair_select: at most 2^18 candidate pairs (got %d x %d)", n_o, n_sites);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == AGF_F32)
-    pair_select_kernel<float><<<1, kSelectThreads, 0, s>>>(m2, bound, bound_dev, reinterpret_cast<const float*>(xyz),
+    pair_select_kernel<float><<<1, kSelectThreads, 0, s>>>(m2, bound, counts, n_counts, reinterpret_cast<const float*>(xyz),
                                                            reinterpret_cast<const float*>(self ? xyz : other),
                                                            n_sites, n_o, cap, pairs, shift, acc, count);
   else
-    pair_select_kernel<double><<<1, kSelectThreads, 0, s>>>(m2, bound, bound_dev, reinterpret_cast<const double*>(xyz),
+    pair_select_kernel<double><<<1, kSelectThreads, 0, s>>>(m2, bound, counts, n_counts, reinterpret_cast<const double*>(xyz),
                                                             reinterpret_cast<const double*>(self ? xyz : other),
                                                             n_sites, n_o, cap, pairs, shift, acc, count);
   AGF_CUDA_TRY(cudaGetLastError());

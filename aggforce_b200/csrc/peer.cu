@@ -26,7 +26,8 @@ struct PeerParams {
   const uint64_t* ptrs;  // device array [world]: base address of every rank's buffer in THIS process
   int32_t rank, world;
   uint32_t seq;          // call number, identical on all ranks, starts at 1
-  int32_t op;            // 0 sum, 1 max, 2 gather (out[r * count + i] = rank r's in[i])
+  int32_t op;            // 0 sum, 1 max, 2 gather (out[r * count + i] = rank r's in[i]), 3 sum for i < n_sum else max
+  int64_t n_sum;
   const double* in;
   double* out;
   int64_t count;
@@ -93,7 +94,8 @@ __global__ void __launch_bounds__(kPeerThreads) peer_exchange_kernel(const __gri
     double acc = ld_peer(reinterpret_cast<const double*>(s_base[0] + slot_off) + i);
     for (int r = 1; r < p.world; ++r) {
       const double v = ld_peer(reinterpret_cast<const double*>(s_base[r] + slot_off) + i);
-      acc = p.op == 0 ? acc + v : (v > acc || v != v ? v : acc);
+      const bool add = p.op == 0 || (p.op == 3 && i < p.n_sum);
+      acc = add ? acc + v : (v > acc || v != v ? v : acc);
     }
     p.out[i] = acc;
   }
@@ -111,7 +113,9 @@ extern "C" int agf_peer_exchange(const uint64_t* peer_ptrs, int32_t rank, int32_
   using namespace agf;
   AGF_REQUIRE(peer_ptrs && in && out && error, "agf_peer_exchange: null pointer");
   AGF_REQUIRE(world >= 1 && world <= kPeerMaxRanks && rank >= 0 && rank < world, "agf_peer_exchange: bad rank/world");
-  AGF_REQUIRE(op >= 0 && op <= 2 && seq != 0, "agf_peer_exchange: bad op / sequence number");
+  const int64_t n_sum = op >> 8;  // op = 3 | (n_sum << 8): the first n_sum values are summed, the rest max-ed
+  op &= 0xff;
+  AGF_REQUIRE(op >= 0 && op <= 3 && seq != 0, "agf_peer_exchange: bad op / sequence number");
   AGF_REQUIRE(count >= 0 && count <= slot_doubles, "agf_peer_exchange: %lld values exceed the slot (%lld)",
               (long long)count, (long long)slot_doubles);
   PeerParams p;
@@ -120,6 +124,7 @@ extern "C" int agf_peer_exchange(const uint64_t* peer_ptrs, int32_t rank, int32_
   p.world = world;
   p.seq = seq;
   p.op = op;
+  p.n_sum = n_sum;
   p.in = in;
   p.out = out;
   p.count = count;

@@ -16,6 +16,9 @@ from .. import _engine
 from ..util import trjdot
 
 
+_COMPILED_BY_CONTENT: Dict[Tuple[bytes, int], "_engine.CompiledMap"] = {}
+
+
 class _Taggable:
     """Holds a free-form ``tags`` dictionary (fit logs such as feature coefficients)."""
 
@@ -137,7 +140,11 @@ class LinearMap:
         # (core.py:240), so in-place edits must be seen: digest of the WHOLE matrix (microseconds at
         # cln025, 20 ms for a 500 x 5000 map), taken once only for arrays nobody can write to
         if m.flags.writeable or self._frozen_digest is None:
-            digest = hashlib.blake2b(np.ascontiguousarray(m).tobytes(), digest_size=16).digest()
+            raw = np.ascontiguousarray(m).tobytes()
+            # small matrices (every call of a cln025-sized map): the interpreter's 64-bit keyed hash of the
+            # bytes, a few microseconds; large ones: a 128-bit digest
+            digest = hash(raw).to_bytes(8, "little", signed=True) if len(raw) <= (1 << 16) else hashlib.blake2b(
+                raw, digest_size=16).digest()
             if not m.flags.writeable:
                 self._frozen_digest = digest
         else:
@@ -149,10 +156,19 @@ class LinearMap:
         if self._compiled is not None and self._compiled[0] != digest:
             self._column_labels = None  # matrix was edited in place: the fit's column structure is stale
         if self._compiled is None or self._compiled[0] != digest:
-            # plain mode keeps all-zero columns so that 0 * NaN = NaN exactly as numpy computes it
-            self._compiled = (digest, _engine.CompiledMap(self._standard_matrix,
-                                                          keep_zero_columns=not self.handle_nans,
-                                                          column_labels=self._column_labels))
+            # maps with the same content (the coordinate map of every call, the uniform map rebuilt from
+            # the same constraints) share ONE device form: compiled maps are immutable
+            key = (digest, _engine.device().index)
+            shared = _COMPILED_BY_CONTENT.get(key) if self._column_labels is None else None
+            if shared is None:
+                # plain mode keeps all-zero columns so that 0 * NaN = NaN exactly as numpy computes it
+                shared = _engine.CompiledMap(self._standard_matrix, keep_zero_columns=not self.handle_nans,
+                                             column_labels=self._column_labels)
+                if self._column_labels is None:
+                    if len(_COMPILED_BY_CONTENT) > 64:
+                        _COMPILED_BY_CONTENT.clear()
+                    _COMPILED_BY_CONTENT[key] = shared
+            self._compiled = (digest, shared)
         return self._compiled[1]
 
     def _launch(self, points, want_sumsq: bool = False, status: Optional[torch.Tensor] = None,

@@ -33,7 +33,7 @@ from ..map import CLAFTMap, CLAMap, LinearMap
 from ..trajectory import Trajectory
 from ..util import Curry
 from .gbfeat import GbSpec, gb_feat
-from .solver import DEFAULT_SOLVER_OPTIONS, SolverOptions, solve, solve_equality_qp_device
+from .solver import DEFAULT_SOLVER_OPTIONS, SolverOptions, solve, solve_equality_qp_device, warn_if_solver_ignored
 
 _DEVICE_SOLVE_MIN = 512  # feature counts from which the per-bead QP is solved on the device
 
@@ -403,6 +403,7 @@ def qp_feat_linear_map(
     """
     if constraints is None:
         constraints = set()
+    warn_if_solver_ignored(solver_args)
     plan = _fusable(featurizer)
     if plan is not None:
         return _fit_fused(traj, coord_map, featurizer, plan, kbt, n_constraint_frames, constraints, solver_args,

@@ -5,6 +5,7 @@ Drop-in for the reference's ``src/aggforce/qp/qplinear.py``.
 from __future__ import annotations
 
 import functools
+import hashlib
 from typing import Union
 
 import numpy as np
@@ -15,7 +16,8 @@ from .. import _engine, _lib
 from ..constraints import Constraints, constraint_lookup_dict, merged_groups
 from ..map import LinearMap, SeperableTMap
 from ..trajectory import ForcesTrajectory
-from .solver import DEFAULT_SOLVER_OPTIONS, SolverOptions, solve, solve_equality_qp_device
+from .solver import (DEFAULT_SOLVER_OPTIONS, SolverOptions, solve, solve_equality_qp_device,
+                     warn_if_solver_ignored)
 
 
 def reduced_columns(n_sites: int, constraints: Constraints) -> np.ndarray:
@@ -138,25 +140,58 @@ def _equality_rows(coord_map: LinearMap, cols: np.ndarray, n_red: int) -> np.nda
     return np.asarray((onehot.T @ cmat.T).T)
 
 
-def _fit_small_on_device(traj, coord_map: LinearMap, cols: np.ndarray, n_red: int, l2: float,
+class _SmallFitPlan:
+    """Everything about a small device-side fit that depends only on (coordinate map, constraints, l2):
+    column order, CSR of the groups, equality rows, index maps of the QP kernel's outputs and the
+    structure of the fitted map -- host bookkeeping and small device tables, built once and reused."""
+
+    cache: dict = {}
+
+    def __init__(self, coord_map: LinearMap, cols: np.ndarray, n_red: int, l2: float) -> None:
+        self.cols, self.n_red, self.n_cg = cols, n_red, coord_map.n_cg_sites
+        self.gram_plan = _engine.GramPlan(cols, n_red)
+        order = self.gram_plan.order
+        group_size = np.bincount(cols, minlength=n_red).astype(np.float64)
+        self.diag = (l2 if l2 > 0.0 else 0.0) * group_size
+        self.a_mat = _equality_rows(coord_map, cols, n_red)
+        self.compiled_structure, ucol_of_col = _engine.CompiledMap.from_labels(cols, self.n_cg, n_red)
+        self.d_diag = _engine.dev_f64(self.diag[order]) if l2 > 0.0 else None
+        self.d_a = _engine.dev_f64(self.a_mat[:, order])
+        self.d_x_index = _engine.dev_i32(order)
+        self.d_u_index = _engine.dev_i32(ucol_of_col[order])
+
+    @classmethod
+    def get(cls, coord_map: LinearMap, constraints, cols: np.ndarray, n_red: int, l2: float) -> "_SmallFitPlan":
+        try:
+            m = np.asarray(coord_map.standard_matrix)
+            key = (m.shape, hashlib.blake2b(np.ascontiguousarray(m, dtype=np.float64).tobytes(), digest_size=16).digest(),
+                   frozenset(constraints), float(l2), _engine.device().index)
+        except TypeError:
+            return cls(coord_map, cols, n_red, l2)
+        plan = cls.cache.get(key)
+        if plan is None:
+            if len(cls.cache) > 16:
+                cls.cache.clear()
+            plan = cls.cache[key] = cls(coord_map, cols, n_red, l2)
+        return plan
+
+
+def _fit_small_on_device(traj, coord_map: LinearMap, constraints, cols: np.ndarray, n_red: int, l2: float,
                          solver_args) -> SeperableTMap:
     """Gram (kernel a) -> ``agf_qp_equality_small`` -> a ``LinearMap`` whose coefficients are already
     where kernel (d) reads them.  Nothing synchronises here when called through ``project_forces``
     (which reads status + coefficients once, after the applications); a direct call resolves the fit
     before returning, as the reference raises at fit time."""
-    n_cg = coord_map.n_cg_sites
-    gram, order = _engine.gram_linear_raw(_engine.Frames(traj.forces), cols, n_red)
+    plan = _SmallFitPlan.get(coord_map, constraints, cols, n_red, l2)
+    n_cg = plan.n_cg
+    gram, order = _engine.gram_linear_raw(_engine.Frames(traj.forces), cols, n_red, plan=plan.gram_plan)
     _engine.run_deferred()
-    group_size = np.bincount(cols, minlength=n_red).astype(np.float64)
-    diag = (l2 if l2 > 0.0 else 0.0) * group_size
-    a_mat = _equality_rows(coord_map, cols, n_red)
-    compiled, ucol_of_col = _engine.CompiledMap.from_labels(cols, n_cg, n_red)
+    compiled = plan.compiled_structure.with_values(torch.empty((n_red, n_cg), dtype=torch.float64, device=gram.device))
     buf = torch.zeros(_DeviceFit.N_HEAD + n_cg * n_red, dtype=torch.float64, device=gram.device)
     p = _engine.ptr
-    _lib.call("agf_qp_equality_small", p(gram), n_red, p(_engine.dev_f64(diag[order])) if l2 > 0.0 else p(None),
-              p(_engine.dev_f64(a_mat[:, order])), n_cg, p(_engine.dev_i32(order)), p(buf[_DeviceFit.N_HEAD:]),
-              p(_engine.dev_i32(ucol_of_col[order])), p(compiled.umat_t), p(buf[0:1]), _engine.stream_ptr())
-    fit = _DeviceFit(buf, gram, order, cols, n_red, n_cg, diag, a_mat, solver_args)
+    _lib.call("agf_qp_equality_small", p(gram), n_red, p(plan.d_diag), p(plan.d_a), n_cg, p(plan.d_x_index),
+              p(buf[_DeviceFit.N_HEAD:]), p(plan.d_u_index), p(compiled.umat_t), p(buf[0:1]), _engine.stream_ptr())
+    fit = _DeviceFit(buf, gram, order, cols, n_red, n_cg, plan.diag, plan.a_mat, solver_args)
     force_map = LinearMap.from_device_fit(fit, n_cg, cols, compiled)
     if not _engine.fits_deferred():
         fit.matrix()  # direct call: synchronise, check the solver status (ValueError on failure)
@@ -178,9 +213,15 @@ def qp_linear_map(
     Same contract as the reference: constrained sites share coefficients, the map satisfies
     ``coord_map @ W.T = I`` on the reduced coefficients, ``l2_regularization`` penalises the
     expanded coefficient vector and is relative to the *unnormalised* frame sum.
+
+    ``solver_args``: the reference hands them to ``qpsolvers.solve_qp`` (OSQP by default).  Here the
+    problem is solved exactly (closed form, on the device for small and for large reduced problems)
+    unless ``solver_args={"backend": "qpsolvers", ...}``; other keys given without that backend are
+    reported once with a warning and not used.
     """
     if constraints is None:
         constraints = set()
+    warn_if_solver_ignored(solver_args)
     n_fg = coord_map.n_fg_sites
     if traj.forces.shape[1] != n_fg:
         raise ValueError("coord_map and forces disagree on the number of fine-grained sites.")
@@ -191,7 +232,7 @@ def qp_linear_map(
     n_cg = coord_map.n_cg_sites
     if (backend == "exact" and not on_device and isinstance(coord_map, LinearMap)
             and _lib.lib().agf_qp_equality_small_supported(n_red, n_cg)):
-        return _fit_small_on_device(traj, coord_map, cols, n_red, l2_regularization, solver_args)
+        return _fit_small_on_device(traj, coord_map, constraints, cols, n_red, l2_regularization, solver_args)
     if on_device:
         qp_mat = _engine.gram_linear(_engine.Frames(traj.forces), cols, n_red)  # stays on the device
         _engine.run_deferred()

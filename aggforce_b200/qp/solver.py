@@ -99,6 +99,26 @@ def solve_equality_qp_device(P, A, b) -> Optional[np.ndarray]:
     return out[:, 0] if vec else out
 
 
+_WARNED = [False]
+
+
+def warn_if_solver_ignored(solver_args: Optional[SolverOptions]) -> None:
+    """The reference forwards ``solver_args`` to ``qpsolvers.solve_qp`` (``solver="osqp"``, tolerances,
+    ...).  Here the equality QP is solved exactly unless ``backend="qpsolvers"`` is given: say so once
+    when a caller passes its own solver options, instead of silently ignoring them."""
+    if solver_args is None or solver_args is DEFAULT_SOLVER_OPTIONS or _WARNED[0]:
+        return
+    opts = dict(solver_args)
+    if opts.get("backend", "exact") == "exact" and any(k != "backend" for k in opts):
+        import warnings
+
+        _WARNED[0] = True
+        warnings.warn("aggforce_b200 solves the equality-constrained QP exactly (closed form); the given "
+                      f"solver options {sorted(k for k in opts if k != 'backend')} are not used.  Pass "
+                      'solver_args={"backend": "qpsolvers", ...} to hand the problem to qpsolvers as the '
+                      "reference does.", stacklevel=3)
+
+
 def solve(P, A, b, solver_args: Optional[SolverOptions] = None) -> Optional[np.ndarray]:
     """Dispatch: exact solve by default, ``qpsolvers`` on request (vector ``b`` only)."""
     opts = dict(solver_args or {})

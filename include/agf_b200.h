@@ -192,14 +192,16 @@ int agf_pair_screen(const void* xyz, const void* other, int dtype, int64_t n_fra
 
 /* Ordered compaction of the screened pair matrix (small systems, n_other * n_sites <= 2^18): the
  * device-side form of constfinder.py:52  nonzero(sds < threshold)  applied to the pruning bound --
- * pairs with m2 <= bound (bound_dev, a device scalar, overrides `bound` when not NULL) in row-major
- * order, each with its frame-0 distance (the `shift` of agf_pair_moments) and zeroed accumulators.
+ * pairs with m2 <= bound in row-major order (sharded runs: counts != NULL is a device array of the
+ * n_counts per-rank frame counts and `bound` is threshold^2 -- the kernel forms
+ * threshold^2 * sum(counts) itself, so the reduced screening buffer is consumed as it arrives), each with its frame-0 distance (the `shift` of agf_pair_moments) and zeroed accumulators.
  *   xyz / other   device frame 0 of the arrays passed to agf_pair_screen, [n_sites, 3] / [n_other, 3]
  *   pairs int32 [cap, 2], shift f64 [cap], acc f64 [cap, 2]   device, written for the survivors
  *   count int32 [1]  survivors, or -(survivors) when they exceed cap (then nothing else is written)
  */
-int agf_pair_select(const double* m2, double bound, const double* bound_dev, const void* xyz,
-                    const void* other, int dtype, int32_t n_sites, int32_t n_other, int32_t cap,
+int agf_pair_select(const double* m2, double bound, const double* counts, int32_t n_counts,
+                    const void* xyz, const void* other, int dtype, int32_t n_sites, int32_t n_other,
+                    int32_t cap,
                     int32_t* pairs, double* shift, double* acc, int32_t* count, void* stream);
 
 /* ------------------------------------------------------------------------------------
@@ -354,6 +356,7 @@ int agf_synth_frames(const float* ref_pos, const int32_t* parent, const float* b
  * kernel on `stream`: copy-in, signal / wait (release / acquire, system scope), combine.
  *   op 0: out[i] = sum_r in_r[i]   op 1: out[i] = max_r in_r[i] (NaN wins)
  *   op 2: out[r * count + i] = in_r[i] (all-gather)
+ *   op 3 | (k << 8): sum for i < k, max for i >= k (residual sums and NaN flags in one message)
  *   seq   call number, the same on all ranks, starting at 1 and increasing by 1 per call
  *   error device int32 [1], set to 1 if a peer's signal never arrived (result then invalid)
  */

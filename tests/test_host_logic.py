@@ -271,3 +271,20 @@ def test_cv_helpers_match_reference_semantics():
     assert mean([]) is None and sample_sd([]) is None
     assert mean([1.0, 2.0, 6.0]) == 3.0
     assert abs(sample_sd([1.0, 2.0, 6.0]) - np.std([1.0, 2.0, 6.0], ddof=1)) < 1e-15
+
+
+def test_ignored_solver_options_are_reported_once():
+    import warnings
+
+    from aggforce_b200.qp import solver
+
+    solver._WARNED[0] = False
+    with warnings.catch_warnings(record=True) as seen:
+        warnings.simplefilter("always")
+        solver.warn_if_solver_ignored(solver.DEFAULT_SOLVER_OPTIONS)  # the default dictionary: silent
+        solver.warn_if_solver_ignored({"backend": "qpsolvers", "solver": "scs"})  # honoured: silent
+        assert not seen
+        solver.warn_if_solver_ignored({"solver": "scs"})
+        solver.warn_if_solver_ignored({"solver": "scs"})
+    assert len(seen) == 1 and "qpsolvers" in str(seen[0].message)
+    solver._WARNED[0] = False
