@@ -230,16 +230,21 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
     // ------------------------------------------------ fill warps
     const int ft = threadIdx.x;
     const float* forces = p.forces;
+    // Regular chunks (neither the head chunk 0 nor the last one) hold kI8SubFrames frames = a multiple of
+    // 16 bytes and start 16-byte aligned when the first regular chunk does: one flag instead of
+    // per-chunk 64-bit arithmetic in the steady state.
+    const int64_t last_chunk = p.sch.n_chunks - 1;
+    const bool aligned = (reinterpret_cast<uintptr_t>(forces + (int64_t)p.sch.head * frame_elems) % 16) == 0;
     auto bulkable = [&](int64_t c) {
+      if (c > 0 && c < last_chunk) return aligned;
       const int64_t bytes = (int64_t)p.sch.count(c) * frame_elems * 4;
       const uintptr_t a = reinterpret_cast<uintptr_t>(forces + p.sch.start(c) * frame_elems);
       return c != 0 && bytes > 0 && (bytes % 16) == 0 && (a % 16) == 0;
     };
-    auto issue = [&](int64_t j) {
+    auto issue = [&](int64_t j, int stage) {
       if (j >= n_mine) return;
       const int64_t c = first + j * step;
       if (!bulkable(c)) return;
-      const int stage = (int)(j % kI8RawStages);
       const uint32_t bytes = (uint32_t)((int64_t)p.sch.count(c) * frame_elems * 4);
       fence_proxy_async();
       mbar_expect_tx(&raw_full[stage], bytes);
@@ -253,7 +258,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
       }
     };
     if (ft == 0)
-      for (int j = 0; j < kI8RawStages; ++j) issue(j);
+      for (int j = 0; j < kI8RawStages; ++j) issue(j, j);
 
     // warp = frame of the sub-chunk; lane q < 24 owns the COLUMN QUAD 4q..4q+3 (columns 0..95), one xyz
     // component per pass, so the four digits of a plane form one 32-bit word and every store is an STS.32.
@@ -303,14 +308,15 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
     }
     const uint32_t frame_bytes = (uint32_t)frame_elems * 4u;
     uint32_t raw_phase = 0;
-    for (int64_t j = 0; j < n_mine; ++j) {
-      const int64_t c = first + j * step;
-      const int nf = p.sch.count(c);
-      const int stage = (int)(j % kI8RawStages);
+    int stage = 0;
+    int64_t c = first;
+    for (int64_t j = 0; j < n_mine; ++j, c += step, stage = stage == kI8RawStages - 1 ? 0 : stage + 1) {
+      const bool regular = c > 0 && c < last_chunk;
+      const int nf = regular ? kI8SubFrames : p.sch.count(c);
+      const int pb = (int)((j >> 1) & 1), half = (int)(j & 1);
       const int64_t pj = j >> 1;
-      const int pb = (int)(pj & 1), half = (int)(j & 1);
       float* stage_ptr = raw + (int64_t)stage * stage_elems;
-      if (bulkable(c)) {
+      if (regular ? aligned : bulkable(c)) {
         mbar_wait(&raw_full[stage], (raw_phase >> stage) & 1u);
         raw_phase ^= (1u << stage);
       } else {
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
       }
       if (ft == 0) {
         if (half == 1 || j == n_mine - 1) mbar_arrive(&panel_full[pb]);
-        issue(j + kI8RawStages);
+        issue(j + kI8RawStages, stage);
       }
     }
 
