@@ -129,6 +129,21 @@ def start_d2h(t: torch.Tensor) -> torch.Tensor:
     return host
 
 
+def start_d2h_piece(host: torch.Tensor, a: int, part: torch.Tensor) -> None:
+    """Asynchronous copy of ``part`` (just produced on the current stream) into ``host[a : a + len(part)]``
+    on the download stream: the output of one upload piece leaves while the next piece arrives."""
+    dev = torch.cuda.current_device()
+    if dev not in _D2H_STREAMS:
+        _D2H_STREAMS[dev] = torch.cuda.Stream(device=dev)
+    ds = _D2H_STREAMS[dev]
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    with torch.cuda.stream(ds):
+        ds.wait_event(ev)
+        host[a : a + part.shape[0]].copy_(part, non_blocking=True)
+    part.record_stream(ds)
+
+
 def finish_d2h() -> None:
     ds = _D2H_STREAMS.get(torch.cuda.current_device())
     if ds is not None:
@@ -822,9 +837,13 @@ class CompiledMap:
 
 def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float, want_sumsq: bool = False,
               start: int = 0, stop: Optional[int] = None, sumsq: Optional[torch.Tensor] = None,
-              flags: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
+              flags: Optional[torch.Tensor] = None, download: Optional[list] = None
+              ) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor]:
     """Kernel (d).  Returns ``(out [T, n_cg, 3] device, sumsq device f64[1] | None, nan_flags int32[2])``.
-    ``sumsq`` / ``flags``: zeroed slots of a caller-owned status buffer to accumulate into."""
+    ``sumsq`` / ``flags``: zeroed slots of a caller-owned status buffer to accumulate into.
+    ``download``: an empty list; for a host array the pinned copy of ``out`` is started here -- piece by
+    piece behind each piece's kernel when the array is still being uploaded -- and appended to it
+    (``finish_d2h`` before reading)."""
     if frames.n_sites != cmap.n_fg:
         raise ValueError(
             f"map expects {cmap.n_fg} fine-grained sites but the array has {frames.n_sites}"
@@ -836,6 +855,10 @@ def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float,
         sumsq = torch.zeros(1, dtype=torch.float64, device=device()) if want_sumsq else None
     if flags is None:
         flags = torch.zeros(2, dtype=torch.int32, device=device())
+    host_out = None
+    by_piece = download is not None and frames.on_host and frames._dev is None
+    if by_piece:
+        host_out = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
     for t0, piece in frames.pieces(start, stop):
         o = out[t0 - start : t0 - start + piece.shape[0]]
         if cmap.sparse and cmap.slice:
@@ -860,6 +883,10 @@ def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float,
                           ptr(cmap.ucol_ptr), ptr(cmap.ucol_sites), cmap.n_ucol, cmap.nnz, ptr(cmap.umat_t),
                           cmap.n_cg, ptr(o), dtype_code(o), ptr(sumsq), nan_mode, float(nan_atol), ptr(flags),
                           stream_ptr())
+        if by_piece:
+            start_d2h_piece(host_out, t0 - start, o)
+    if download is not None and frames.on_host:
+        download.append(host_out if by_piece else start_d2h(out))
     return out, sumsq, flags
 
 

@@ -92,11 +92,15 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
     # fit has enqueued its last kernel (or launched right here when the fit never asks), so it runs
     # on the GPU while the host builds / solves the map.
     early: Dict[str, Any] = {}
+    dl_c: list = []  # pinned copies of the mapped arrays whose download has been started (host input only)
+    dl_f: list = []
     if isinstance(coord_map, LinearMap) and coords is not None:
-        if method is qp_linear_map:  # [Gram][coordinate map] | QP
+        if method is qp_linear_map and not coords_in.on_host:  # [Gram][coordinate map] | QP
             _engine.defer(lambda: early.update(launch=coord_map._launch(coords_in, slots=slots_c)))
-        elif method is constraint_aware_uni_map:  # runs while the host builds the uniform map
-            early["launch"] = coord_map._launch(coords_in, slots=slots_c)
+        elif method is qp_linear_map or method is constraint_aware_uni_map:
+            # runs while the host builds the uniform map; for host arrays its download (started inside)
+            # leaves over PCIe while the forces arrive and the fit runs
+            early["launch"] = coord_map._launch(coords_in, slots=slots_c, download=dl_c)
         # other methods return maps that are applied as a whole (featurised / augmented): nothing to hoist
     try:
         with _engine.deferred_fits():  # a device-side fit reports through the read below
@@ -118,12 +122,13 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
             _engine.clear_deferred()
             if "launch" in early:
                 early.clear()
+                dl_c.clear()
                 stat.zero_()
         _engine.run_deferred()
-        fc, oc, _ = early["launch"] if "launch" in early else cm._launch(coords_in, slots=slots_c)
-        host_c = _engine.start_d2h(oc) if fc.on_host else None  # downloads overlap the force upload
-        ff, of, _ = fm._launch(forces_in, want_sumsq=True, slots=slots_f)
-        host_f = _engine.start_d2h(of) if ff.on_host else None
+        fc, oc, _ = early["launch"] if "launch" in early else cm._launch(coords_in, slots=slots_c, download=dl_c)
+        ff, of, _ = fm._launch(forces_in, want_sumsq=True, slots=slots_f, download=dl_f)
+        host_c = dl_c[0] if dl_c else None  # downloads overlap the force upload, piece by piece
+        host_f = dl_f[0] if dl_f else None
         pend = fm._pending if fm._matrix is None else None
         n_elem = float(np.prod(of.shape))
         if _engine.sharded():

@@ -172,12 +172,12 @@ class LinearMap:
         return self._compiled[1]
 
     def _launch(self, points, want_sumsq: bool = False, status: Optional[torch.Tensor] = None,
-                slots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+                slots: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, download: Optional[list] = None):
         """Enqueue the kernel; returns ``(frames, out_dev, status_dev)`` without synchronising.
         ``status_dev`` is a float64[2] device tensor ``[sum(out**2), flags]`` whose second slot holds
         the two int32 flags ``(saw_nan, nan_violation)``.  ``slots = (sum_slot, flag_slot)`` -- two
         zeroed one-element float64 views of a larger buffer -- makes several launches report through
-        ONE read (then ``status_dev`` is ``None``)."""
+        ONE read (then ``status_dev`` is ``None``).  ``download``: see ``_engine.map_apply``."""
         frames = _engine.Frames(points)
         if slots is None:
             if status is None:
@@ -186,7 +186,7 @@ class LinearMap:
         out, _, _ = _engine.map_apply(
             frames, self._compile(), nan_mode=1 if self.handle_nans else 0,
             nan_atol=self.nan_check_threshold, want_sumsq=want_sumsq,
-            sumsq=slots[0] if want_sumsq else None, flags=slots[1].view(torch.int32),
+            sumsq=slots[0] if want_sumsq else None, flags=slots[1].view(torch.int32), download=download,
         )
         return frames, out, status
 
@@ -211,11 +211,12 @@ class LinearMap:
         return _engine.to_host(out)
 
     def _apply(self, points, want_sumsq: bool = False):
-        frames, out, status = self._launch(points, want_sumsq)
+        dl: list = []
+        frames, out, status = self._launch(points, want_sumsq, download=dl)
         if _engine.sharded():  # every rank must raise (or not) together: the next collective would hang
             _engine.allreduce_max_(status[1:2].view(torch.int32))
         host = _engine.to_host(status)  # one synchronising read: NaN flags and the residual sum together
-        return self._finish(frames, out, host[1:2]), float(host[0])
+        return self._finish(frames, out, host[1:2], dl[0] if dl else None), float(host[0])
 
     def __call__(self, points):
         """Map ``(n_steps, n_fg_sites, 3)`` points to ``(n_steps, n_cg_sites, 3)``."""
