@@ -19,9 +19,11 @@
 //   * a frame with a value outside the fixed-point range (|v| >= 2^(E_x - 1), or not finite) is left
 //     out of the digit planes and appended to a list; gram_leftover_kernel adds those frames in
 //     float64 afterwards, so the result does not depend on the sample being representative.
-// Roles in the CTA (one per SM): 16 fill warps (TMA ring of raw frames -> digits, as the DMMA kernel's
-// fill but without a competitor for the FP64 pipe), 1 MMA warp (TMEM allocation, MMA issue,
-// tcgen05.commit onto the panel barriers); fill warps 0-3 read the accumulators back (tcgen05.ld).
+// Roles in the CTA (one per SM): 16 frame warps (raw frame -> digits of its three rows), 1 load warp (1-D TMA
+// ring of raw frames), 1 MMA warp (TMEM allocation, MMA issue, tcgen05.commit onto the panel barriers);
+// frame warps 0-3 read the accumulators back (tcgen05.ld).  All hand-offs are mbarriers -- no block-wide
+// barrier in the main loop, so the frame warps drift apart and their conversion (XU pipe), integer and
+// shared-memory phases overlap instead of running in lock step.
 #ifndef AGF_BULK_PIECE
 #define AGF_BULK_PIECE 16384u
 #endif
@@ -42,9 +44,9 @@ constexpr int kI8PlaneBytes = (kI8PanelRows / 8) * kI8GroupBytes;  // 10 752
 constexpr int kI8PanelBytes = (kI8Slices * kI8PlaneBytes + kI8BlockBytes + 1023) / 1024 * 1024;  // + the block A reads past the end
 constexpr int kI8RawStages = 3;
 constexpr int kI8FrameWarps = 16;                    // one frame of the sub-chunk each
-constexpr int kI8FillWarps = kI8FrameWarps + 1;       // + one warp for column 96 (lane = frame)
-constexpr int kI8FillThreads = kI8FillWarps * 32;
-constexpr int kI8Threads = kI8FillThreads + 32;       // + the MMA warp
+constexpr int kI8LoadWarp = kI8FrameWarps;            // TMA producer of the raw-frame ring
+constexpr int kI8MmaWarp = kI8FrameWarps + 1;         // TMEM allocation, MMA issue
+constexpr int kI8Threads = (kI8FrameWarps + 2) * 32;
 constexpr int kI8MaxFramesPerCta = 8192;  // 5 products of at most 2^14 per row and level: 24 576 rows stay below 2^31
 constexpr int kI8SampleFrames = 4096;
 constexpr long long kI8Bias = 0x8080808080LL;
@@ -108,10 +110,6 @@ __device__ __forceinline__ uint32_t gather_bytes(uint32_t w0, uint32_t w1, uint3
   const uint32_t t01 = __byte_perm(w0, w1, sel), t23 = __byte_perm(w2, w3, sel);
   return __byte_perm(t01, t23, 0x5410);
 }
-__device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-
 // byte offset of (row k, column x) inside one digit plane
 __device__ __forceinline__ uint32_t plane_off(int k, int x) {
   return (uint32_t)((k >> 3) * kI8GroupBytes + (x >> 4) * kI8BlockBytes + (k & 7) * 16 + (x & 15));
@@ -125,17 +123,6 @@ __device__ __forceinline__ int column_exponent(unsigned long long max_bits) {
   return e < -900 ? -900 : (e > 900 ? 900 : e);
 }
 
-// the five digits of q go to the five planes at byte offset `off`
-__device__ __forceinline__ void store_digits(uint32_t panel, uint32_t off, long long q) {
-  const unsigned long long w = (unsigned long long)(q + kI8Bias) ^ (unsigned long long)kI8Bias;
-  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-  sts_u8(panel + 0 * kI8PlaneBytes + off, hi);        // most significant digit
-  sts_u8(panel + 1 * kI8PlaneBytes + off, lo >> 24);
-  sts_u8(panel + 2 * kI8PlaneBytes + off, lo >> 16);
-  sts_u8(panel + 3 * kI8PlaneBytes + off, lo >> 8);
-  sts_u8(panel + 4 * kI8PlaneBytes + off, lo);
-}
-
 // W0..W3: members visited for slot 0..3 of a column quad (the largest group size of that slot over all
 // quads; lanes with fewer members multiply by a 0 mask).  Compile-time trip counts: straight-line fill.
 template <int W0, int W1, int W2, int W3>
@@ -145,15 +132,13 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
   unsigned char* panels = smem;                                       // 2 digit panels
   size_t off = (size_t)2 * kI8PanelBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off);
-  uint64_t* raw_full = bars;                      // [kI8RawStages]
-  uint64_t* panel_full = raw_full + kI8RawStages; // [2]
-  uint64_t* panel_empty = panel_full + 2;         // [2]
-  uint64_t* acc_done = panel_empty + 2;           // [1]
-  off += 64;
+  uint64_t* ring_bars = bars;                          // [2 * kI8RawStages]: raw stage full / empty
+  uint64_t* panel_full = ring_bars + 2 * kI8RawStages; // [2]
+  uint64_t* panel_empty = panel_full + 2;              // [2]
+  uint64_t* acc_done = panel_empty + 2;                // [1]
+  off += 128;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem + off);
-  int32_t* s_anybad = reinterpret_cast<int32_t*>(smem + off + 8);  // [2]
-  int32_t* s_bad = reinterpret_cast<int32_t*>(smem + off + 16);    // [2][kI8SubFrames]
-  off += 16 + 2 * kI8SubFrames * 4;
+  off += 16;
   int32_t* s_exp = reinterpret_cast<int32_t*>(smem + off);       // [kI8Cols]
   off += kI8Cols * 4;
   int32_t* s_ptr = reinterpret_cast<int32_t*>(smem + off);       // CSR copy
@@ -162,26 +147,24 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
   off = (off + 127) / 128 * 128;
   float* raw = reinterpret_cast<float*>(smem + off);
   const int64_t frame_elems = (int64_t)p.n_sites * 3;
-  const int64_t stage_elems = ((int64_t)kI8SubFrames * frame_elems * 4 + 15) / 16 * 16 / 4;
 
   for (int i = threadIdx.x; i <= p.n_red; i += blockDim.x) s_ptr[i] = p.col_ptr[i];
   for (int i = threadIdx.x; i < p.col_ptr[p.n_red]; i += blockDim.x) s_sites[i] = p.col_sites[i];
   for (int i = threadIdx.x; i < 2 * kI8PanelBytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(panels)[i] = make_uint4(0, 0, 0, 0);  // columns >= n_red and the pad stay zero
   for (int i = threadIdx.x; i < kI8Cols; i += blockDim.x) s_exp[i] = i < p.n_red ? column_exponent(p.colmax_bits[i]) : 0;
-  for (int i = threadIdx.x; i < 2 * kI8SubFrames; i += blockDim.x) s_bad[i] = 0;
-  if (threadIdx.x < 2) s_anybad[threadIdx.x] = 0;
+  FrameRing<float, kI8RawStages> ring;
+  ring.init(raw, ring_bars, p.forces, frame_elems, p.sch, kI8FrameWarps);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kI8RawStages; ++i) mbar_init(&raw_full[i], 1);
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&panel_full[i], 1);
+      mbar_init(&panel_full[i], 2 * kI8FrameWarps);  // every frame warp arrives once per half panel
       mbar_init(&panel_empty[i], 1);
     }
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == kI8FillWarps) {
+  if (warp == kI8MmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -198,7 +181,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
   const int64_t n_mine = p.sch.n_chunks > first ? (p.sch.n_chunks - first + step - 1) / step : 0;
   const int64_t n_panels = (n_mine + 1) / 2;
 
-  if (warp == kI8FillWarps) {
+  if (warp == kI8MmaWarp) {
     // ------------------------------------------------ MMA warp: one thread issues
     if (lane == 0) {
       const uint32_t pbase = smem_u32(panels);
@@ -226,48 +209,23 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
       }
       umma_commit(acc_done);
     }
+  } else if (warp == kI8LoadWarp) {
+    // ------------------------------------------------ load warp: keeps the ring of raw frames full
+    ring.produce(first, step);
   } else {
-    // ------------------------------------------------ fill warps
-    const int ft = threadIdx.x;
-    const float* forces = p.forces;
-    // Regular chunks (neither the head chunk 0 nor the last one) hold kI8SubFrames frames = a multiple of
-    // 16 bytes and start 16-byte aligned when the first regular chunk does: one flag instead of
-    // per-chunk 64-bit arithmetic in the steady state.
-    const int64_t last_chunk = p.sch.n_chunks - 1;
-    const bool aligned = (reinterpret_cast<uintptr_t>(forces + (int64_t)p.sch.head * frame_elems) % 16) == 0;
-    auto bulkable = [&](int64_t c) {
-      if (c > 0 && c < last_chunk) return aligned;
-      const int64_t bytes = (int64_t)p.sch.count(c) * frame_elems * 4;
-      const uintptr_t a = reinterpret_cast<uintptr_t>(forces + p.sch.start(c) * frame_elems);
-      return c != 0 && bytes > 0 && (bytes % 16) == 0 && (a % 16) == 0;
-    };
-    auto issue = [&](int64_t j, int stage) {
-      if (j >= n_mine) return;
-      const int64_t c = first + j * step;
-      if (!bulkable(c)) return;
-      const uint32_t bytes = (uint32_t)((int64_t)p.sch.count(c) * frame_elems * 4);
-      fence_proxy_async();
-      mbar_expect_tx(&raw_full[stage], bytes);
-      const char* src = reinterpret_cast<const char*>(forces + p.sch.start(c) * frame_elems);
-      char* dst = reinterpret_cast<char*>(raw + (int64_t)stage * stage_elems);
-      uint32_t done = 0;
-      while (done < bytes) {
-        const uint32_t piece = bytes - done < kBulkPiece ? bytes - done : kBulkPiece;
-        tma_bulk_g2s(dst + done, src + done, piece, &raw_full[stage]);
-        done += piece;
-      }
-    };
-    if (ft == 0)
-      for (int j = 0; j < kI8RawStages; ++j) issue(j, j);
-
-    // warp = frame of the sub-chunk; lane q < 24 owns the COLUMN QUAD 4q..4q+3 (columns 0..95), one xyz
-    // component per pass, so the four digits of a plane form one 32-bit word and every store is an STS.32.
-    // The host orders the columns so that SLOT c of every quad holds columns of similar group size
-    // (slot 0 the largest groups ... slot 3 single sites): the member loop of a slot then has a
-    // warp-uniform trip count and lanes without that member multiply by a 0 mask -- no divergence.
+    // ------------------------------------------------ frame warps.  No block-wide barrier in the loop: a warp
+    // waits for its raw stage and its panel, fills the three rows of ITS frame and arrives on the two
+    // mbarriers, so the warps drift apart and their conversion (XU), integer and store phases overlap.
+    //
+    // warp = frame of the sub-chunk; lane q owns the COLUMN QUAD 4q..4q+3 (24 quads = columns 0..95, quad 24
+    // = column 96 when n_red = 97), one xyz component per pass, so the four digits of a plane form one
+    // 32-bit word and every store is an STS.32.  The host orders the columns so that SLOT c of every quad
+    // holds columns of similar group size (slot 0 the largest groups ... slot 3 single sites): the member
+    // loop of a slot then has a warp-uniform trip count and lanes without that member multiply by a 0
+    // mask -- no divergence.
     // Fixed point in ONE instruction: t = fma(v, 2^(39-E), 1.5 * 2^52 + B) holds q + B in its low 40 bits
     // (round to nearest), and its upper 24 bits are a known constant exactly when |q| is in range.
-    constexpr int kQuads = kI8N / 4;
+    const int n_quads = p.n_red > kI8N ? kI8N / 4 + 1 : kI8N / 4;
     uint32_t moff[4][4];
     float mask[4][4];
     double scale[4];
@@ -280,7 +238,7 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
         moff[cc][m] = 0;
         mask[cc][m] = 0.f;
       }
-      if (lane < kQuads && x < p.n_red) {
+      if (lane < n_quads && x < p.n_red) {
         const int b = s_ptr[x];
         const int n = s_ptr[x + 1] - b;
 #pragma unroll
@@ -295,47 +253,28 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
     const double magic = 6755399441055744.0 + 551911719040.0;  // 1.5 * 2^52 + 0x8080808080
     const uint32_t hi_expect = 0x43380000u;                    // upper word of 1.5 * 2^52 (low byte: digit 0)
     const uint32_t lane_off = (uint32_t)((lane >> 2) * kI8BlockBytes + (lane & 3) * 4);  // block and byte of x = 4 lane
-    // column 96 (n_red == 97): lanes 0..15 of warp 0 take one frame each
-    const bool extra = p.n_red > kI8N && warp == kI8FrameWarps && lane < kI8SubFrames;
-    int ecnt = 0;
-    uint32_t eoff[4] = {0, 0, 0, 0};
-    double escale = 0.0, side = 0.0;
-    if (extra) {
-      const int b = s_ptr[kI8N];
-      ecnt = s_ptr[kI8N + 1] - b;
-      for (int m = 0; m < 4 && m < ecnt; ++m) eoff[m] = (uint32_t)s_sites[b + m] * 12u;
-      escale = ldexp(1.0, 39 - s_exp[kI8N]);
-    }
+    const bool side_lane = p.n_red > kI8N && lane == kI8N / 4;  // owns column 96: its diagonal element is a side sum
+    double side = 0.0;
     const uint32_t frame_bytes = (uint32_t)frame_elems * 4u;
-    uint32_t raw_phase = 0;
-    int stage = 0;
+    const int t = warp;
+    RingCursor<kI8RawStages> cur;
     int64_t c = first;
-    for (int64_t j = 0; j < n_mine; ++j, c += step, stage = stage == kI8RawStages - 1 ? 0 : stage + 1) {
-      const bool regular = c > 0 && c < last_chunk;
-      const int nf = regular ? kI8SubFrames : p.sch.count(c);
+    for (int64_t j = 0; j < n_mine; ++j, c += step) {
+      const int nf = p.sch.count(c);
       const int pb = (int)((j >> 1) & 1), half = (int)(j & 1);
       const int64_t pj = j >> 1;
-      float* stage_ptr = raw + (int64_t)stage * stage_elems;
-      if (regular ? aligned : bulkable(c)) {
-        mbar_wait(&raw_full[stage], (raw_phase >> stage) & 1u);
-        raw_phase ^= (1u << stage);
-      } else {
-        const float* src = forces + p.sch.start(c) * frame_elems;
-        for (int64_t i = ft; i < (int64_t)nf * frame_elems; i += kI8FillThreads) stage_ptr[i] = src[i];
-        asm volatile("bar.sync 1, %0;" ::"n"(kI8FillThreads) : "memory");
-      }
+      mbar_wait(&ring.full[cur.stage], cur.phase);
       if (half == 0) mbar_wait(&panel_empty[pb], (uint32_t)(((pj >> 1) & 1) ^ 1));
       const uint32_t panel = smem_u32(panels) + (uint32_t)pb * kI8PanelBytes;
-      int32_t* bad = s_bad + (j & 1) * kI8SubFrames;
 
       // group sums -> fixed point -> digits, written at once; a frame with a value out of range is
-      // flagged and its rows are cleared again below (rare)
-      const int t = warp < kI8FrameWarps ? warp : 0;  // (the column-96 warp owns no frame: its `range` stays 0)
-      const bool live = warp < kI8FrameWarps && t < nf;
-      const uint32_t fbase = smem_u32(stage_ptr) + (uint32_t)(live ? t : 0) * frame_bytes;
+      // cleared again below and listed for the float64 pass (rare)
+      const bool live = t < nf;
+      const uint32_t fbase = smem_u32(ring.stage_ptr(cur.stage)) + (uint32_t)(live ? t : 0) * frame_bytes;
       const double live_scale = live ? 1.0 : 0.0;
       uint32_t range = 0;  // any bit above the low byte set: some value left the fixed-point range
-      if (lane < kQuads && warp < kI8FrameWarps) {
+      double sq = 0.0;
+      if (lane < n_quads) {
         uint32_t lo[3][4], hi[3][4];
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
@@ -353,6 +292,10 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
           }
           const double sc = scale[cc] * live_scale;
           const double t0 = fma(v0, sc, magic), t1 = fma(v1, sc, magic), t2 = fma(v2, sc, magic);
+          if (cc == 0) {  // q = t - magic exactly: the values the tensor core sees, so that row and column 96 agree
+            const double q0 = t0 - magic, q1 = t1 - magic, q2 = t2 - magic;
+            sq = fma(q0, q0, fma(q1, q1, q2 * q2));
+          }
           lo[0][cc] = (uint32_t)__double2loint(t0);
           hi[0][cc] = (uint32_t)__double2hiint(t0);
           lo[1][cc] = (uint32_t)__double2loint(t1);
@@ -374,78 +317,38 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
           sts_u32(dst + 4 * kI8PlaneBytes, gather_bytes(lo[d][0], lo[d][1], lo[d][2], lo[d][3], 0) ^ 0x80808080u);
         }
       }
-      const bool ovf = (range & 0xFFFFFF00u) != 0;
-      long long eq[3] = {0, 0, 0};
-      bool eok = false;
-      if (extra) {
-        double ev[3] = {0.0, 0.0, 0.0};
-        if (lane < nf) {
-          for (int m = 0; m < ecnt && m < 4; ++m) {
-            const uint32_t a = smem_u32(stage_ptr) + (uint32_t)lane * frame_bytes + eoff[m];
-            ev[0] += (double)lds_f32(a);
-            ev[1] += (double)lds_f32(a + 4u);
-            ev[2] += (double)lds_f32(a + 8u);
-          }
+      // the raw frame has been read (its values sit in the digits): hand the stage back to the load warp
+      const bool ovf = __any_sync(0xffffffffu, (range & 0xFFFFFF00u) != 0);
+      if (lane == 0) mbar_arrive(&ring.empty[cur.stage]);
+      if (ovf) {  // warp-uniform: this warp's frame goes to the float64 pass; clear its rows, list it
+        __syncwarp();
+        for (int i = lane; i < kI8Slices * 3 * (kI8Cols / 4); i += 32) {
+          const int sidx = i / (3 * (kI8Cols / 4)), r = i - sidx * 3 * (kI8Cols / 4);
+          const int d = r / (kI8Cols / 4), x = 4 * (r - d * (kI8Cols / 4));
+          sts_u32(panel + sidx * kI8PlaneBytes + plane_off(half * 48 + t * 3 + d, x), 0u);
         }
-        bool eovf = false;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const double f = ev[d] * escale;
-          eovf |= !(fabs(f) < 274877906944.0);  // 2^38
-          eq[d] = eovf ? 0ll : __double2ll_rn(f);
+        if (live && lane == 0) {
+          const int slot = atomicAdd(p.leftover_count, 1);
+          p.leftover[slot] = (int32_t)(p.frame0 + p.sch.start(c) + t);
         }
-        if (eovf) {
-          atomicOr(&bad[lane], 1);
-          s_anybad[j & 1] = 1;
-        }
-        eok = !eovf;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) store_digits(panel, plane_off(half * 48 + lane * 3 + d, kI8N), eovf ? 0ll : eq[d]);
+      } else if (side_lane) {
+        side += sq;
       }
-      if (__any_sync(0xffffffffu, ovf) && lane == 0) {
-        atomicOr(&bad[t], 1);
-        s_anybad[j & 1] = 1;
-      }
-      if (half == 0 && j == n_mine - 1) {  // odd number of sub-chunks: the second half of the last panel is empty
-        for (int i = ft; i < kI8Slices * 48 * kI8Cols / 4; i += kI8FillThreads) {
-          const int sidx = i / (48 * kI8Cols / 4), r = i - sidx * (48 * kI8Cols / 4);
-          const int k = 48 + r / (kI8Cols / 4), x = 4 * (r - (r / (kI8Cols / 4)) * (kI8Cols / 4));
-          sts_u32(panel + sidx * kI8PlaneBytes + plane_off(k, x), 0u);
+      const bool tail_half = half == 0 && j == n_mine - 1;  // odd number of sub-chunks: the other half stays empty
+      if (tail_half) {
+        for (int i = lane; i < kI8Slices * 3 * (kI8Cols / 4); i += 32) {
+          const int sidx = i / (3 * (kI8Cols / 4)), r = i - sidx * 3 * (kI8Cols / 4);
+          const int d = r / (kI8Cols / 4), x = 4 * (r - d * (kI8Cols / 4));
+          sts_u32(panel + sidx * kI8PlaneBytes + plane_off(48 + t * 3 + d, x), 0u);
         }
       }
       fence_proxy_async();  // digit stores (generic proxy) -> visible to the tensor core (async proxy)
-      asm volatile("bar.sync 1, %0;" ::"n"(kI8FillThreads) : "memory");
-      // frames handed to the float64 leftover pass: clear their rows, list them
-      const int any_bad = s_anybad[j & 1];
-      if (any_bad) {  // uniform over the fill warps
-        if (warp < kI8FrameWarps && bad[t] != 0) {
-          for (int i = lane; i < kI8Slices * 3 * (kI8Cols / 4); i += 32) {
-            const int sidx = i / (3 * (kI8Cols / 4)), r = i - sidx * 3 * (kI8Cols / 4);
-            const int d = r / (kI8Cols / 4), x = 4 * (r - d * (kI8Cols / 4));
-            sts_u32(panel + sidx * kI8PlaneBytes + plane_off(half * 48 + t * 3 + d, x), 0u);
-          }
-          if (live && lane == 0) {
-            const int slot = atomicAdd(p.leftover_count, 1);
-            p.leftover[slot] = (int32_t)(p.frame0 + p.sch.start(c) + t);
-          }
-        }
-        if (extra && bad[lane] != 0) eok = false;
-        fence_proxy_async();
-        asm volatile("bar.sync 1, %0;" ::"n"(kI8FillThreads) : "memory");
-        if (ft < kI8SubFrames) bad[ft] = 0;
-        if (ft == 0) s_anybad[j & 1] = 0;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&panel_full[pb]);
+        if (tail_half) mbar_arrive(&panel_full[pb]);
       }
-      if (extra && eok && lane < nf) {  // the values the tensor core sees, so that row and column 96 stay consistent
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const double vq = (double)eq[d];
-          side = fma(vq, vq, side);
-        }
-      }
-      if (ft == 0) {
-        if (half == 1 || j == n_mine - 1) mbar_arrive(&panel_full[pb]);
-        issue(j + kI8RawStages, stage);
-      }
+      cur.advance();
     }
 
     // ------------------------------------------------ epilogue: fill warps 0..3 own TMEM lanes 32 w .. 32 w + 31
@@ -486,16 +389,11 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
         }
       }
     }
-    if (extra) {
-      double tot = side;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) tot += __shfl_xor_sync(0x0000ffffu, tot, o);
-      if (lane == 0) atomicAdd(p.gram + (int64_t)kI8N * p.n_red + kI8N, ldexp(tot, 2 * s_exp[kI8N] - 78));
-    }
+    if (side_lane) atomicAdd(p.gram + (int64_t)kI8N * p.n_red + kI8N, ldexp(side, 2 * s_exp[kI8N] - 78));
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == kI8FillWarps) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  if (warp == kI8MmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
 // Column maxima of the group sums over a sample of frames (thread = (frame, column)).
@@ -552,7 +450,7 @@ __global__ void __launch_bounds__(256) gram_leftover_kernel(const float* __restr
 }
 
 static size_t gram_i8_smem(int n_sites, int n_red) {
-  size_t off = (size_t)2 * kI8PanelBytes + 64 + 16 + 2 * kI8SubFrames * 4 + kI8Cols * 4 + (size_t)(n_red + 1 + n_sites) * 4;
+  size_t off = (size_t)2 * kI8PanelBytes + 128 + 16 + kI8Cols * 4 + (size_t)(n_red + 1 + n_sites) * 4;
   off = (off + 127) / 128 * 128;
   const size_t stage = ((size_t)kI8SubFrames * n_sites * 12 + 15) / 16 * 16;
   return off + kI8RawStages * stage;
