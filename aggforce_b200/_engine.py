@@ -657,10 +657,11 @@ def csr_from_labels(labels: np.ndarray, n_groups: int) -> Tuple[np.ndarray, np.n
 # --------------------------------------------------------------------------------------
 import os as _os
 
-# int8 / tcgen05 Gram (csrc/gram_i8.cu): on by default for long float32 trajectories with n_red <= 97;
+# int8 / tcgen05 Gram (csrc/gram_i8.cu, csrc/gram_i8t.cu): on by default for long float32 trajectories;
 # AGF_GRAM_I8=0 selects the FP64 DMMA kernel everywhere (A/B measurements, bit-exact FP64 products)
 _GRAM_I8 = [_os.environ.get("AGF_GRAM_I8", "1") != "0"]
 _GRAM_I8_MIN_FRAMES = 8192
+_GRAM_I8T_MIN_FRAMES = int(_os.environ.get("AGF_GRAM_I8T_MIN_FRAMES", "2048"))  # tiled variant, n_red > 97
 
 
 class GramPlan:
@@ -719,6 +720,14 @@ def gram_linear_raw(frames: Frames, col_of_site: np.ndarray, n_red: int,
                       ptr(d_sites), n_red, plan.max_group, C.c_uint32(plan.slot_members), ptr(gram), ptr(ws),
                       C.c_size_t(ws.numel()), stream_ptr())
             continue
+        if (_GRAM_I8[0] and n_red > 97 and piece.dtype == torch.float32
+                and piece.shape[0] >= _GRAM_I8T_MIN_FRAMES):
+            need_i8 = int(_lib.lib().agf_gram_linear_i8t_workspace_bytes(frames.n_sites, n_red, piece.shape[0]))
+            if need_i8 > 0:  # the same digit scheme tiled over the Gram (csrc/gram_i8t.cu)
+                ws = workspace(need_i8)
+                _lib.call("agf_gram_linear_i8t", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites,
+                          ptr(d_ptr), ptr(d_sites), n_red, ptr(gram), ptr(ws), C.c_size_t(ws.numel()), stream_ptr())
+                continue
         need = int(_lib.lib().agf_gram_linear_workspace_bytes(frames.n_sites, n_red, piece.shape[0]))
         if need > 0:  # n_red > 128: pack group sums once, TMA-fed SYRK
             ws = workspace(need)

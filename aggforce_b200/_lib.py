@@ -23,6 +23,7 @@ SIGNATURES = {
     "agf_gram_linear": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _vp, _vp],
     "agf_gram_linear_ws": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _vp, _vp, C.c_size_t, _vp],
     "agf_gram_linear_i8": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, C.c_uint32, _vp, _vp, C.c_size_t, _vp],
+    "agf_gram_linear_i8t": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _vp, _vp, C.c_size_t, _vp],
     "agf_symmetrize": [_vp, _i32, _vp],
     "agf_map_apply": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, C.c_int, _vp, C.c_int, _dbl,
                       _vp, _vp],
@@ -57,6 +58,7 @@ SIGNATURES = {
 PLAIN = {"agf_version": (C.c_int, []), "agf_peer_buffer_bytes": (C.c_size_t, [_i64]), "agf_qp_equality_small_supported": (C.c_int, [_i32, _i32]), "agf_last_error": (C.c_char_p, []), "agf_device_sm_count": (C.c_int, []),
          "agf_gram_linear_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64]),
          "agf_gram_linear_i8_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64]),
+         "agf_gram_linear_i8t_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64]),
          "agf_map_apply_workspace_bytes": (C.c_size_t, [C.c_int, _i32, _i32, _i32, _i32, _i64]),
          "agf_gram_feat_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i64])}
 

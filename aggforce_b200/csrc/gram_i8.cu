@@ -28,6 +28,7 @@
 #define AGF_BULK_PIECE 16384u
 #endif
 #include "frame_pipe.cuh"
+#include "i8.cuh"
 
 namespace agf {
 
@@ -50,8 +51,7 @@ constexpr int kI8Threads = (kI8FrameWarps + 2) * 32;
 constexpr int kI8MaxFramesPerCta = 8192;  // 5 products of at most 2^14 per row and level: 24 576 rows stay below 2^31
 constexpr int kI8SampleFrames = 4096;
 constexpr long long kI8Bias = 0x8080808080LL;
-constexpr uint32_t kI8Idesc = (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
-                              ((uint32_t)(kI8N >> 3) << 17) | ((uint32_t)(kI8M >> 4) << 24);
+constexpr uint32_t kI8Idesc = umma_idesc_i8(kI8M, kI8N);
 
 struct GramI8Params {
   const float* forces;
@@ -69,22 +69,12 @@ struct GramI8Params {
 };
 
 __device__ __forceinline__ uint64_t umma_desc_mn(uint32_t addr) {
-  // canonical MN-major, no swizzle, 8-bit: core matrix = 8 k-rows x 16 bytes; MN blocks kI8BlockBytes apart (SBO),
-  // groups of 8 k-rows kI8GroupBytes apart (LBO); descriptor version 1
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((kI8GroupBytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((kI8BlockBytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+  // MN blocks kI8BlockBytes apart (SBO), groups of 8 k-rows kI8GroupBytes apart (LBO)
+  return umma_desc_mn_i8(addr, kI8GroupBytes, kI8BlockBytes);
 }
 
 __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(kI8Idesc), "r"(accumulate)
-      : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+  umma_i8_issue(tmem_d, da, db, kI8Idesc, accumulate);
 }
 
 // not volatile: the compiler may batch these loads (the mbarrier waits around them carry memory clobbers)
@@ -93,34 +83,9 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
   asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
   return v;
 }
-// predicated load: 0 when the lane has no such member (no branch)
-__device__ __forceinline__ float lds_f32_if(uint32_t addr, bool on) {
-  float v;
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@p ld.shared.f32 %0, [%1];\n\t}"
-               : "=f"(v)
-               : "r"(addr), "r"((uint32_t)on));
-  return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-  asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-// byte `b` of four words -> one word (byte i from word i)
-__device__ __forceinline__ uint32_t gather_bytes(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int b) {
-  const uint32_t sel = (uint32_t)b | ((uint32_t)(4 + b) << 4);  // result byte 0 = w0.b, byte 1 = w1.b
-  const uint32_t t01 = __byte_perm(w0, w1, sel), t23 = __byte_perm(w2, w3, sel);
-  return __byte_perm(t01, t23, 0x5410);
-}
 // byte offset of (row k, column x) inside one digit plane
 __device__ __forceinline__ uint32_t plane_off(int k, int x) {
   return (uint32_t)((k >> 3) * kI8GroupBytes + (x >> 4) * kI8BlockBytes + (k & 7) * 16 + (x & 15));
-}
-
-// Scale of a column: values below 2^(E-1) fit the 39-bit fixed point; E leaves 2-4x headroom over the sample.
-__device__ __forceinline__ int column_exponent(unsigned long long max_bits) {
-  const double m = __longlong_as_double((long long)max_bits);
-  if (!(m > 0.0) || !(m < 1.0e300)) return -900;
-  int e = ilogb(m) + 3;
-  return e < -900 ? -900 : (e > 900 ? 900 : e);
 }
 
 // W0..W3: members visited for slot 0..3 of a column quad (the largest group size of that slot over all

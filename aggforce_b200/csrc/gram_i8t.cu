@@ -1,0 +1,512 @@
+// Kernel (a), Blackwell tensor-core path for LARGE reduced problems (n_red > 97): the linear Gram through
+// int8 digit planes on tcgen05, tiled over the Gram (the n_red <= 97 variant in gram_i8.cu keeps the whole
+// Gram in one accumulator set and builds its digits in shared memory).
+//
+// Same result as agf_gram_linear_ws (src/aggforce/qp/qplinear.py:66-71 of the reference: P = (R C)' (R C) in
+// float64) for float32 forces.  Two kernels per slab of frames:
+//
+//   1. i8t_digits_kernel: group sums (float64, exact) -> 39-bit fixed point with a per-column power-of-two
+//      scale -> five signed 8-bit digit planes, written to the workspace in the layout the tensor core reads:
+//          D[chunk][plane s][x-block][k-group][k-row][16 columns]       one byte per entry
+//      chunk = 32 frames of ONE xyz component (any order of the contraction rows gives the same Gram),
+//      x-block = 16 reduced columns, k-group = 8 frames: one x-block of a chunk and plane is 512 contiguous
+//      bytes = four 8 x 16 core matrices of the canonical MN-major no-swizzle UMMA layout, and any window of
+//      x-blocks is one contiguous span -> one 1-D TMA bulk copy per operand plane, no tensor map.
+//   2. i8t_syrk_kernel (persistent, one CTA per SM): work unit = (slice of <= kT_SliceChunks chunks, tile of
+//      128 x 96 Gram elements on or above the diagonal).  Warp 0 streams the unit's operand planes through a
+//      6-stage ring (per chunk: 5 x 4 KB for the 128 rows, 5 x 3 KB for the 96 columns), warp 1 issues
+//      tcgen05.mma.kind::i8 (M 128, N 96, K 32): the 15 plane products with s + t <= 4, accumulated EXACTLY
+//      in int32 in five TMEM accumulators (one per level l = s + t, 480 of 512 columns), warps 2-5 read the
+//      accumulators back (tcgen05.ld), recombine the levels in float64,
+//          G[x][y] += 2^(E_x + E_y - 14) sum_l 2^(-8 l) acc_l[x][y],
+//      and add the upper-triangle elements to the Gram.  Units are ordered slice-major so that the CTAs
+//      running at one time read the same ~50 MB of digits: the operands come from L2, not HBM.
+// Frames holding a value outside the fixed-point range (or a non-finite one) are left out of the planes and
+// added in float64 by i8t_leftover_kernel, so the result does not depend on the scale sample.
+#include "i8.cuh"
+
+namespace agf {
+
+constexpr int kT_M = 128, kT_N = 96, kT_K = 32;
+constexpr int kT_Slices = 5;
+constexpr int kT_ChunkFrames = 32;                       // one chunk = one MMA k-block
+constexpr int kT_XbBytes = (kT_ChunkFrames / 8) * 128;   // x-block of one chunk and plane: 512 B
+constexpr int kT_APlane = (kT_M / 16) * kT_XbBytes;      // 4096
+constexpr int kT_BPlane = (kT_N / 16) * kT_XbBytes;      // 3072
+constexpr int kT_StageBytes = kT_Slices * (kT_APlane + kT_BPlane);  // 35 840
+constexpr int kT_Stages = 6;
+constexpr int kT_SliceChunks = 128;     // 4 096 contraction rows per unit (int32 headroom allows 768)
+constexpr int kT_SlabFrames = 16384;    // frames whose digits are resident at a time
+constexpr int kT_SyrkThreads = 192;     // load warp, MMA warp, four epilogue warps
+constexpr int kT_MaxRed = 8192;
+constexpr int kT_SampleFrames = 1024;
+constexpr uint32_t kT_Idesc = umma_idesc_i8(kT_M, kT_N);
+
+constexpr int kT_PanelCols = 128;                        // digits kernel: columns per pass
+constexpr int kT_TileXb = kT_XbBytes + 16;               // padded x-block stride in the staging tile (bank spread)
+constexpr int kT_TileBytes = 3 * kT_Slices * (kT_PanelCols / 16) * kT_TileXb;  // 63 360
+
+__host__ __device__ inline int i8t_pad(int n_red) {
+  const int a = (n_red + kT_M - 1) / kT_M * kT_M, b = (n_red + kT_N - 1) / kT_N * kT_N;
+  return a > b ? a : b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// column scales from a strided sample of the frames: thread = column, block row = frame group
+__global__ void __launch_bounds__(128) i8t_sample_kernel(const float* __restrict__ forces, int64_t n_frames, int64_t stride,
+                                                         int n_sites, const int32_t* __restrict__ col_ptr,
+                                                         const int32_t* __restrict__ col_sites, int n_red,
+                                                         unsigned long long* __restrict__ colmax_bits) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n_red) return;
+  const int b = __ldg(col_ptr + x), e = __ldg(col_ptr + x + 1);
+  double best = 0.0;
+  for (int64_t t = (int64_t)blockIdx.y * stride; t < n_frames; t += (int64_t)gridDim.y * stride) {
+    const float* fr = forces + t * (int64_t)n_sites * 3;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int m = b; m < e; ++m) {
+      const float* q = fr + 3 * __ldg(col_sites + m);
+      s0 += (double)__ldg(q);
+      s1 += (double)__ldg(q + 1);
+      s2 += (double)__ldg(q + 2);
+    }
+    const double m = fmax(fabs(s0), fmax(fabs(s1), fabs(s2)));
+    if (m < 1.0e300) best = fmax(best, m);
+  }
+  atomicMax(colmax_bits + x, (unsigned long long)__double_as_longlong(best));  // bits of x >= 0 order like x
+}
+
+__global__ void i8t_scale_kernel(const unsigned long long* __restrict__ colmax_bits, int n_red, int n_pad,
+                                 int32_t* __restrict__ exps, double* __restrict__ scales) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= n_pad) return;
+  const int e = x < n_red ? column_exponent(colmax_bits[x]) : 0;
+  exps[x] = e;
+  scales[x] = x < n_red ? ldexp(1.0, 39 - e) : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+struct I8tDigitsParams {
+  const float* forces;   // first frame of the slab
+  int64_t n_frames;      // frames in the slab
+  int64_t frame0;        // index of forces[0] in the call's array (leftover list)
+  int32_t n_sites, n_red, n_xb;
+  const int32_t* col_ptr;
+  const int32_t* col_sites;
+  const double* scales;  // [n_pad]
+  unsigned char* digits;
+  int32_t* leftover_count;
+  int32_t* leftover;
+};
+
+// CTA = 32 frames (three chunks) x all columns, 128 columns per pass: warp w owns frames w, w + 8, w + 16,
+// w + 24, lane q the column quad 4 q .. 4 q + 3 of the pass, so the four digits of a plane form one word.
+__global__ void __launch_bounds__(256) i8t_digits_kernel(const __grid_constant__ I8tDigitsParams p) {
+  extern __shared__ __align__(16) unsigned char tile[];  // [xyz][plane][x-block of the pass][kT_TileXb]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t fb = blockIdx.x;
+  const int64_t f0 = fb * kT_ChunkFrames;
+  const int64_t frame_elems = (int64_t)p.n_sites * 3;
+  const uint32_t tbase = smem_u32(tile);
+  const int n_pass = (p.n_xb * 16 + kT_PanelCols - 1) / kT_PanelCols;
+  uint32_t bad[4] = {0u, 0u, 0u, 0u};
+  for (int pass = 0; pass < n_pass; ++pass) {
+    const int x0 = pass * kT_PanelCols + 4 * lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = warp + 8 * i;
+      const int64_t gf = f0 + f;
+      const bool live = gf < p.n_frames;
+      const float* fr = p.forces + (live ? gf : p.n_frames - 1) * frame_elems;
+      uint32_t lo[3][4], hi[3][4];
+      uint32_t range = 0;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        const int x = x0 + cc;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, sc = 0.0;
+        if (x < p.n_red) {
+          const int b = __ldg(p.col_ptr + x), e = __ldg(p.col_ptr + x + 1);
+          for (int m = b; m < e; ++m) {
+            const float* q = fr + 3 * __ldg(p.col_sites + m);
+            v0 += (double)__ldg(q);
+            v1 += (double)__ldg(q + 1);
+            v2 += (double)__ldg(q + 2);
+          }
+          sc = live ? __ldg(p.scales + x) : 0.0;
+        }
+        const double t0 = fma(v0, sc, kI8Magic), t1 = fma(v1, sc, kI8Magic), t2 = fma(v2, sc, kI8Magic);
+        lo[0][cc] = (uint32_t)__double2loint(t0);
+        hi[0][cc] = (uint32_t)__double2hiint(t0);
+        lo[1][cc] = (uint32_t)__double2loint(t1);
+        hi[1][cc] = (uint32_t)__double2hiint(t1);
+        lo[2][cc] = (uint32_t)__double2loint(t2);
+        hi[2][cc] = (uint32_t)__double2hiint(t2);
+        range |= (hi[0][cc] ^ kI8HiExpect) | (hi[1][cc] ^ kI8HiExpect) | (hi[2][cc] ^ kI8HiExpect);
+      }
+      bad[i] |= range & 0xFFFFFF00u;
+      const uint32_t in_xb = (uint32_t)((f >> 3) * 128 + (f & 7) * 16 + (lane & 3) * 4);
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        const uint32_t dst = tbase + (uint32_t)((d * kT_Slices) * (kT_PanelCols / 16) + (lane >> 2)) * kT_TileXb + in_xb;
+        constexpr uint32_t ps = (kT_PanelCols / 16) * kT_TileXb;  // plane stride inside the tile
+        sts_u32(dst + 0 * ps, gather_bytes(hi[d][0], hi[d][1], hi[d][2], hi[d][3], 0) ^ 0x80808080u);
+        sts_u32(dst + 1 * ps, gather_bytes(lo[d][0], lo[d][1], lo[d][2], lo[d][3], 3) ^ 0x80808080u);
+        sts_u32(dst + 2 * ps, gather_bytes(lo[d][0], lo[d][1], lo[d][2], lo[d][3], 2) ^ 0x80808080u);
+        sts_u32(dst + 3 * ps, gather_bytes(lo[d][0], lo[d][1], lo[d][2], lo[d][3], 1) ^ 0x80808080u);
+        sts_u32(dst + 4 * ps, gather_bytes(lo[d][0], lo[d][1], lo[d][2], lo[d][3], 0) ^ 0x80808080u);
+      }
+    }
+    __syncthreads();
+    // tile -> workspace: per (xyz, plane) the pass's x-blocks are one contiguous span
+    for (int idx = threadIdx.x; idx < 3 * kT_Slices * (kT_PanelCols / 16) * (kT_XbBytes / 16); idx += blockDim.x) {
+      const int q = idx & (kT_XbBytes / 16 - 1);
+      const int r = idx / (kT_XbBytes / 16);
+      const int xb = r & (kT_PanelCols / 16 - 1), ds = r / (kT_PanelCols / 16);
+      const int gxb = pass * (kT_PanelCols / 16) + xb;
+      if (gxb >= p.n_xb) continue;
+      const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)(ds * (kT_PanelCols / 16) + xb) * kT_TileXb + q * 16);
+      const int d = ds / kT_Slices, s = ds - d * kT_Slices;
+      unsigned char* dst = p.digits + (((size_t)(fb * 3 + d) * kT_Slices + s) * p.n_xb + gxb) * kT_XbBytes + q * 16;
+      *reinterpret_cast<uint4*>(dst) = v;
+    }
+    __syncthreads();
+  }
+  // frames with a value out of range: clear their rows again (the float64 pass adds them), list the live ones
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (!__any_sync(0xffffffffu, bad[i] != 0)) continue;
+    const int f = warp + 8 * i;
+    const size_t in_xb = (size_t)((f >> 3) * 128 + (f & 7) * 16);
+    for (int idx = lane; idx < 3 * kT_Slices * p.n_xb; idx += 32) {
+      const int gxb = idx % p.n_xb, ds = idx / p.n_xb;
+      const int d = ds / kT_Slices, s = ds - d * kT_Slices;
+      unsigned char* dst = p.digits + (((size_t)(fb * 3 + d) * kT_Slices + s) * p.n_xb + gxb) * kT_XbBytes + in_xb;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+    if (lane == 0 && f0 + f < p.n_frames) {
+      const int slot = atomicAdd(p.leftover_count, 1);
+      p.leftover[slot] = (int32_t)(p.frame0 + f0 + f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct I8tSyrkParams {
+  const unsigned char* digits;
+  int32_t n_chunks;  // chunks of the slab (3 per 32 frames)
+  int32_t n_red, n_xb, n_mb, n_nb, n_tiles, n_slices;
+  const int32_t* exps;
+  double* gram;
+};
+
+// tile index -> (row block of 128, column block of 96); a row block keeps the column blocks that reach its
+// first row or beyond (elements with y >= x exist)
+__device__ __forceinline__ void i8t_tile(int t, int n_nb, int& mi, int& nj) {
+  mi = 0;
+  for (;;) {
+    const int nj0 = (kT_M * mi) / kT_N;  // first column block with 96 nj + 95 >= 128 mi
+    const int cnt = n_nb - nj0;
+    if (t < cnt) {
+      nj = nj0 + t;
+      return;
+    }
+    t -= cnt;
+    ++mi;
+  }
+}
+
+__global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __grid_constant__ I8tSyrkParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* stages = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)kT_Stages * kT_StageBytes);
+  uint64_t* full = bars;                  // [kT_Stages] TMA -> MMA
+  uint64_t* empty = full + kT_Stages;     // [kT_Stages] MMA -> TMA (tcgen05.commit)
+  uint64_t* acc_full = empty + kT_Stages; // MMA -> epilogue
+  uint64_t* acc_empty = acc_full + 1;     // epilogue (4 warps) -> MMA
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kT_Stages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    mbar_init(acc_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(s_tmem)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  const int n_units = p.n_slices * p.n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------ load warp: one thread, ten bulk copies per chunk
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const size_t plane_bytes = (size_t)p.n_xb * kT_XbBytes;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int ks = u / p.n_tiles;
+        int mi, nj;
+        i8t_tile(u - ks * p.n_tiles, p.n_nb, mi, nj);
+        const int c0 = ks * kT_SliceChunks;
+        const int c1 = c0 + kT_SliceChunks < p.n_chunks ? c0 + kT_SliceChunks : p.n_chunks;
+        const unsigned char* a_src = p.digits + (size_t)c0 * kT_Slices * plane_bytes + (size_t)mi * (kT_M / 16) * kT_XbBytes;
+        const unsigned char* b_src = p.digits + (size_t)c0 * kT_Slices * plane_bytes + (size_t)nj * (kT_N / 16) * kT_XbBytes;
+        for (int c = c0; c < c1; ++c) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          unsigned char* dst = stages + (size_t)stage * kT_StageBytes;
+          mbar_expect_tx(&full[stage], kT_StageBytes);
+#pragma unroll
+          for (int s = 0; s < kT_Slices; ++s) {
+            tma_bulk_g2s(dst + s * kT_APlane, a_src + s * plane_bytes, kT_APlane, &full[stage]);
+            tma_bulk_g2s(dst + kT_Slices * kT_APlane + s * kT_BPlane, b_src + s * plane_bytes, kT_BPlane, &full[stage]);
+          }
+          a_src += kT_Slices * plane_bytes;
+          b_src += kT_Slices * plane_bytes;
+          if (++stage == kT_Stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------ MMA warp: one thread issues
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t sbase = smem_u32(stages);
+      bool first_unit = true;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int ks = u / p.n_tiles;
+        const int c0 = ks * kT_SliceChunks;
+        const int c1 = c0 + kT_SliceChunks < p.n_chunks ? c0 + kT_SliceChunks : p.n_chunks;
+        if (!first_unit) {  // the epilogue warps have drained the accumulators of the previous unit
+          mbar_wait(acc_empty, acc_phase);
+          acc_phase ^= 1u;
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        first_unit = false;
+        for (int c = c0; c < c1; ++c) {
+          mbar_wait(&full[stage], phase);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = sbase + (uint32_t)stage * kT_StageBytes;
+          const uint32_t b0 = a0 + kT_Slices * kT_APlane;
+          uint32_t started = c > c0 ? 0x1Fu : 0u;  // bit l: accumulator l already holds a product of this unit
+#pragma unroll
+          for (int s = 0; s < kT_Slices; ++s) {
+#pragma unroll
+            for (int t = 0; t < kT_Slices - s; ++t) {
+              const int l = s + t;
+              const uint64_t da = umma_desc_mn_i8(a0 + s * kT_APlane, 128, kT_XbBytes);
+              const uint64_t db = umma_desc_mn_i8(b0 + t * kT_BPlane, 128, kT_XbBytes);
+              umma_i8_issue(tmem_base + (uint32_t)(l * kT_N), da, db, kT_Idesc, (started >> l) & 1u);
+              started |= 1u << l;
+            }
+          }
+          umma_commit(&empty[stage]);  // arrives when the tensor core has finished reading the stage
+          if (++stage == kT_Stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(acc_full);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue warps: warp w may touch TMEM lanes 32 (w % 4) ...
+    const int quarter = warp & 3;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int ks = u / p.n_tiles;
+      int mi, nj;
+      i8t_tile(u - ks * p.n_tiles, p.n_nb, mi, nj);
+      const int x = mi * kT_M + quarter * 32 + lane;
+      const int ex = x < p.n_red ? __ldg(p.exps + x) : 0;
+      mbar_wait(acc_full, acc_phase);
+      acc_phase ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int c0 = 0; c0 < kT_N; c0 += 16) {
+        double g[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) g[i] = 0.0;
+#pragma unroll
+        for (int l = kT_Slices - 1; l >= 0; --l) {
+          uint32_t r[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(l * kT_N + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) g[i] = g[i] * (1.0 / 256.0) + (double)(int32_t)r[i];  // Horner over the levels
+        }
+        if (c0 + 16 >= kT_N) {  // last column group read: the accumulators may be overwritten
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty);
+        }
+        const int y0 = nj * kT_N + c0;
+        if (x < p.n_red && y0 + 15 >= x) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int y = y0 + i;
+            if (y >= x && y < p.n_red)
+              atomicAdd(p.gram + (int64_t)x * p.n_red + y, ldexp(g[i], ex + __ldg(p.exps + y) - 14));
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+}
+
+// Frames the fixed-point pass declined: exact float64 rank-3 updates of the upper triangle.
+__global__ void __launch_bounds__(256) i8t_leftover_kernel(const float* __restrict__ forces, int n_sites,
+                                                           const int32_t* __restrict__ col_ptr,
+                                                           const int32_t* __restrict__ col_sites, int n_red,
+                                                           const int32_t* __restrict__ count,
+                                                           const int32_t* __restrict__ frames, double* __restrict__ gram) {
+  extern __shared__ double lv[];  // [3][n_red]
+  const int n = *count;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    const float* fr = forces + (int64_t)frames[i] * (int64_t)n_sites * 3;
+    __syncthreads();
+    for (int x = threadIdx.x; x < n_red; x += blockDim.x) {
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+      for (int m = col_ptr[x]; m < col_ptr[x + 1]; ++m) {
+        const float* q = fr + 3 * col_sites[m];
+        s0 += (double)q[0];
+        s1 += (double)q[1];
+        s2 += (double)q[2];
+      }
+      lv[x] = s0;
+      lv[n_red + x] = s1;
+      lv[2 * n_red + x] = s2;
+    }
+    __syncthreads();
+    for (int64_t e = threadIdx.x; e < (int64_t)n_red * n_red; e += blockDim.x) {
+      const int x = (int)(e / n_red), y = (int)(e - (int64_t)x * n_red);
+      if (y >= x) atomicAdd(gram + e, lv[x] * lv[y] + lv[n_red + x] * lv[n_red + y] + lv[2 * n_red + x] * lv[2 * n_red + y]);
+    }
+  }
+}
+
+struct I8tLayout {
+  size_t colmax, exps, scales, count, leftover, digits, total;
+  int64_t slab;
+};
+
+static I8tLayout i8t_layout(int n_red, int64_t n_frames) {
+  I8tLayout L;
+  const size_t n_pad = (size_t)i8t_pad(n_red);
+  auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  L.colmax = 0;
+  L.exps = up(n_pad * 8);
+  L.scales = L.exps + up(n_pad * 4);
+  L.count = L.scales + up(n_pad * 8);
+  L.leftover = L.count + 1024;
+  L.digits = L.leftover + up((size_t)n_frames * 4);
+  const int64_t rounded = (n_frames + kT_ChunkFrames - 1) / kT_ChunkFrames * kT_ChunkFrames;
+  L.slab = rounded < kT_SlabFrames ? rounded : kT_SlabFrames;
+  L.total = L.digits + (size_t)(L.slab / kT_ChunkFrames) * 3 * kT_Slices * (n_pad / 16) * kT_XbBytes;
+  return L;
+}
+
+}  // namespace agf
+
+extern "C" size_t agf_gram_linear_i8t_workspace_bytes(int32_t n_sites, int32_t n_red, int64_t n_frames) {
+  using namespace agf;
+  if (n_sites < 1 || n_red <= 97 || n_red > kT_MaxRed || n_frames < 1 || n_frames >= ((int64_t)1 << 31)) return 0;
+  return i8t_layout(n_red, n_frames).total;
+}
+
+extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_frames, int32_t n_sites, const int32_t* col_ptr,
+                                   const int32_t* col_sites, int32_t n_red, double* gram, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  using namespace agf;
+  AGF_REQUIRE(forces && col_ptr && col_sites && gram && workspace, "agf_gram_linear_i8t: null pointer");
+  AGF_REQUIRE(dtype == AGF_F32, "agf_gram_linear_i8t: float32 forces only (float64 input takes agf_gram_linear_ws)");
+  const size_t need = agf_gram_linear_i8t_workspace_bytes(n_sites, n_red, n_frames);
+  AGF_REQUIRE(need != 0, "agf_gram_linear_i8t: needs 97 < n_red <= %d and 1 <= n_frames < 2^31 (got %d, %lld)", kT_MaxRed,
+              n_red, (long long)n_frames);
+  AGF_REQUIRE(workspace_bytes >= need, "agf_gram_linear_i8t: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+  AGF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) % 16) == 0, "agf_gram_linear_i8t: workspace must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const I8tLayout L = i8t_layout(n_red, n_frames);
+  char* ws = reinterpret_cast<char*>(workspace);
+  unsigned long long* colmax = reinterpret_cast<unsigned long long*>(ws + L.colmax);
+  int32_t* exps = reinterpret_cast<int32_t*>(ws + L.exps);
+  double* scales = reinterpret_cast<double*>(ws + L.scales);
+  int32_t* count = reinterpret_cast<int32_t*>(ws + L.count);
+  int32_t* leftover = reinterpret_cast<int32_t*>(ws + L.leftover);
+  unsigned char* digits = reinterpret_cast<unsigned char*>(ws + L.digits);
+  const float* f = reinterpret_cast<const float*>(forces);
+  const int n_pad = i8t_pad(n_red), n_xb = n_pad / 16;
+  AGF_CUDA_TRY(cudaMemsetAsync(ws, 0, L.leftover, s));
+  {
+    const int64_t stride = n_frames > kT_SampleFrames ? n_frames / kT_SampleFrames : 1;
+    const int64_t n_sample = (n_frames + stride - 1) / stride;
+    const int rows = (int)(n_sample < 64 ? n_sample : 64);
+    i8t_sample_kernel<<<dim3((n_red + 127) / 128, rows), 128, 0, s>>>(f, n_frames, stride, n_sites, col_ptr, col_sites, n_red,
+                                                                     colmax);
+    AGF_CUDA_TRY(cudaGetLastError());
+    i8t_scale_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(colmax, n_red, n_pad, exps, scales);
+    AGF_CUDA_TRY(cudaGetLastError());
+  }
+  const size_t syrk_smem = (size_t)kT_Stages * kT_StageBytes + (2 * kT_Stages + 2) * sizeof(uint64_t) + 16;
+  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT_TileBytes));
+  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
+  const int sms = sm_count();
+  I8tSyrkParams q;
+  memset(&q, 0, sizeof(q));
+  q.digits = digits;
+  q.n_red = n_red;
+  q.n_xb = n_xb;
+  q.n_mb = (n_red + kT_M - 1) / kT_M;
+  q.n_nb = (n_red + kT_N - 1) / kT_N;
+  q.n_tiles = 0;
+  for (int mi = 0; mi < q.n_mb; ++mi) q.n_tiles += q.n_nb - (kT_M * mi) / kT_N;
+  q.exps = exps;
+  q.gram = gram;
+  for (int64_t f0 = 0; f0 < n_frames; f0 += L.slab) {
+    I8tDigitsParams d;
+    memset(&d, 0, sizeof(d));
+    d.n_frames = n_frames - f0 < L.slab ? n_frames - f0 : L.slab;
+    d.forces = f + f0 * (int64_t)n_sites * 3;
+    d.frame0 = f0;
+    d.n_sites = n_sites;
+    d.n_red = n_red;
+    d.n_xb = n_xb;
+    d.col_ptr = col_ptr;
+    d.col_sites = col_sites;
+    d.scales = scales;
+    d.digits = digits;
+    d.leftover_count = count;
+    d.leftover = leftover;
+    const int n_fb = (int)((d.n_frames + kT_ChunkFrames - 1) / kT_ChunkFrames);
+    i8t_digits_kernel<<<n_fb, 256, kT_TileBytes, s>>>(d);
+    AGF_CUDA_TRY(cudaGetLastError());
+    q.n_chunks = 3 * n_fb;
+    q.n_slices = (q.n_chunks + kT_SliceChunks - 1) / kT_SliceChunks;
+    const int64_t units = (int64_t)q.n_slices * q.n_tiles;
+    i8t_syrk_kernel<<<(int)(units < sms ? units : sms), kT_SyrkThreads, syrk_smem, s>>>(q);
+    AGF_CUDA_TRY(cudaGetLastError());
+  }
+  const size_t lsmem = (size_t)3 * n_red * sizeof(double);
+  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_leftover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+  i8t_leftover_kernel<<<sms, 256, lsmem, s>>>(f, n_sites, col_ptr, col_sites, n_red, count, leftover, gram);
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}

@@ -95,6 +95,21 @@ int agf_gram_linear_i8(const void* forces, int dtype, int64_t n_frames, int32_t 
                        int32_t max_group, uint32_t slot_members, double* gram, void* workspace,
                        size_t workspace_bytes, void* stream);
 
+/* The tensor-core Gram for LARGE reduced problems (97 < n_red <= 8192, float32 forces, groups of any size):
+ * the same digit scheme as agf_gram_linear_i8, tiled.  Per slab of 16 384 frames one kernel writes the five
+ * digit planes of the group sums to `workspace` in the shared-memory layout of the tensor core (chunks of 32
+ * frames of one xyz component, 16-column blocks: every operand plane of a tile is one contiguous span, moved
+ * by 1-D TMA bulk copies), and a persistent kernel accumulates 128 x 96 tiles of the upper block-triangle
+ * (tcgen05.mma kind::i8, five int32 accumulators per tile in TMEM, 4 096 contraction rows per work unit,
+ * float64 recombination, atomic adds into gram).  Replaces agf_gram_linear_ws (FP64 DMMA) for float32 input:
+ * same contract -- gram (+=) holds the element-wise upper triangle, call agf_symmetrize() afterwards.
+ *   workspace   device, agf_gram_linear_i8t_workspace_bytes(...) bytes (0: shape not supported), 16-byte aligned
+ */
+size_t agf_gram_linear_i8t_workspace_bytes(int32_t n_sites, int32_t n_red, int64_t n_frames);
+int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_frames, int32_t n_sites,
+                        const int32_t* col_ptr, const int32_t* col_sites, int32_t n_red, double* gram,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* gram[j, i] = gram[i, j] for i < j (device f64 [n, n]). */
 int agf_symmetrize(double* gram, int32_t n, void* stream);
 
