@@ -27,7 +27,7 @@
 
 namespace agf {
 
-constexpr int kT_M = 128, kT_N = 96, kT_K = 32;
+constexpr int kT_M = 128, kT_N = 96;  // one tile; K = 32 contraction rows per MMA
 constexpr int kT_Slices = 5;
 constexpr int kT_ChunkFrames = 32;                       // one chunk = one MMA k-block
 constexpr int kT_XbBytes = (kT_ChunkFrames / 8) * 128;   // x-block of one chunk and plane: 512 B
@@ -40,11 +40,11 @@ constexpr int kT_SlabFrames = 16384;    // frames whose digits are resident at a
 constexpr int kT_SyrkThreads = 192;     // load warp, MMA warp, four epilogue warps
 constexpr int kT_MaxRed = 8192;
 constexpr int kT_SampleFrames = 1024;
-constexpr uint32_t kT_Idesc = umma_idesc_i8(kT_M, kT_N);
 
-constexpr int kT_PanelCols = 128;                        // digits kernel: columns per pass
-constexpr int kT_TileXb = kT_XbBytes + 16;               // padded x-block stride in the staging tile (bank spread)
-constexpr int kT_TileBytes = 3 * kT_Slices * (kT_PanelCols / 16) * kT_TileXb;  // 63 360
+constexpr int kT_PanelCols = 128;                        // digits kernel: columns per work item
+constexpr int kT_ItemFrames = 8;                         // ... and frames (one k-group, one warp each)
+constexpr int kT_TileXb = kT_ItemFrames * 16 + 16;       // padded x-block stride in the staging tile (bank spread)
+constexpr int kT_TileBytes = 3 * kT_Slices * (kT_PanelCols / 16) * kT_TileXb;  // 17 280, two of them per CTA
 
 __host__ __device__ inline int i8t_pad(int n_red) {
   const int a = (n_red + kT_M - 1) / kT_M * kT_M, b = (n_red + kT_N - 1) / kT_N * kT_N;
@@ -89,103 +89,124 @@ __global__ void i8t_scale_kernel(const unsigned long long* __restrict__ colmax_b
 struct I8tDigitsParams {
   const float* forces;   // first frame of the slab
   int64_t n_frames;      // frames in the slab
-  int64_t frame0;        // index of forces[0] in the call's array (leftover list)
   int32_t n_sites, n_red, n_xb;
+  int32_t n_groups;      // groups of kT_ItemFrames frames, rounded up to whole chunks
   const int32_t* col_ptr;
   const int32_t* col_sites;
   const double* scales;  // [n_pad]
   unsigned char* digits;
-  int32_t* leftover_count;
-  int32_t* leftover;
+  int32_t* flags;        // [n_groups * kT_ItemFrames]: frame holds a value outside the fixed-point range
 };
 
-// CTA = 32 frames (three chunks) x all columns, 128 columns per pass: warp w owns frames w, w + 8, w + 16,
-// w + 24, lane q the column quad 4 q .. 4 q + 3 of the pass, so the four digits of a plane form one word.
+// Work item = (column pass of 128 columns, group of 8 frames); the items are dealt to the CTAs in equal
+// contiguous ranges, pass-major, so a CTA keeps its columns' member lists while it walks over frame groups.
+// Warp = frame, lane q = column quad 4 q .. 4 q + 3 of the pass: the four digits of a plane form one word.
+// The digits go through a double-buffered staging tile and leave as 128-byte rows (one k-group of one x-block).
 __global__ void __launch_bounds__(256) i8t_digits_kernel(const __grid_constant__ I8tDigitsParams p) {
-  extern __shared__ __align__(16) unsigned char tile[];  // [xyz][plane][x-block of the pass][kT_TileXb]
+  extern __shared__ __align__(16) unsigned char tiles[];  // 2 x [xyz][plane][x-block of the pass][kT_TileXb]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t fb = blockIdx.x;
-  const int64_t f0 = fb * kT_ChunkFrames;
   const int64_t frame_elems = (int64_t)p.n_sites * 3;
-  const uint32_t tbase = smem_u32(tile);
   const int n_pass = (p.n_xb * 16 + kT_PanelCols - 1) / kT_PanelCols;
-  uint32_t bad[4] = {0u, 0u, 0u, 0u};
-  for (int pass = 0; pass < n_pass; ++pass) {
-    const int x0 = pass * kT_PanelCols + 4 * lane;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f = warp + 8 * i;
-      const int64_t gf = f0 + f;
-      const bool live = gf < p.n_frames;
-      const float* fr = p.forces + (live ? gf : p.n_frames - 1) * frame_elems;
-      uint32_t lo[3][4], hi[3][4];
-      uint32_t range = 0;
+  const int64_t n_items = (int64_t)n_pass * p.n_groups;
+  const int64_t lo = n_items * blockIdx.x / gridDim.x, hi = n_items * (blockIdx.x + 1) / gridDim.x;
+  int cur_pass = -1, buf = 0;
+  int cb[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0};
+  double csc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int64_t item = lo; item < hi; ++item, buf ^= 1) {
+    const int pass = (int)(item / p.n_groups), fg = (int)(item - (int64_t)pass * p.n_groups);
+    if (pass != cur_pass) {
+      cur_pass = pass;
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
-        const int x = x0 + cc;
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, sc = 0.0;
+        const int x = pass * kT_PanelCols + 4 * lane + cc;
+        cb[cc] = cn[cc] = 0;
+        csc[cc] = 0.0;
         if (x < p.n_red) {
-          const int b = __ldg(p.col_ptr + x), e = __ldg(p.col_ptr + x + 1);
-          for (int m = b; m < e; ++m) {
-            const float* q = fr + 3 * __ldg(p.col_sites + m);
-            v0 += (double)__ldg(q);
-            v1 += (double)__ldg(q + 1);
-            v2 += (double)__ldg(q + 2);
-          }
-          sc = live ? __ldg(p.scales + x) : 0.0;
+          cb[cc] = __ldg(p.col_ptr + x);
+          cn[cc] = __ldg(p.col_ptr + x + 1) - cb[cc];
+          csc[cc] = __ldg(p.scales + x);
         }
-        const double t0 = fma(v0, sc, kI8Magic), t1 = fma(v1, sc, kI8Magic), t2 = fma(v2, sc, kI8Magic);
-        lo[0][cc] = (uint32_t)__double2loint(t0);
-        hi[0][cc] = (uint32_t)__double2hiint(t0);
-        lo[1][cc] = (uint32_t)__double2loint(t1);
-        hi[1][cc] = (uint32_t)__double2hiint(t1);
-        lo[2][cc] = (uint32_t)__double2loint(t2);
-        hi[2][cc] = (uint32_t)__double2hiint(t2);
-        range |= (hi[0][cc] ^ kI8HiExpect) | (hi[1][cc] ^ kI8HiExpect) | (hi[2][cc] ^ kI8HiExpect);
-      }
-      bad[i] |= range & 0xFFFFFF00u;
-      const uint32_t in_xb = (uint32_t)((f >> 3) * 128 + (f & 7) * 16 + (lane & 3) * 4);
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        const uint32_t dst = tbase + (uint32_t)((d * kT_Slices) * (kT_PanelCols / 16) + (lane >> 2)) * kT_TileXb + in_xb;
-        constexpr uint32_t ps = (kT_PanelCols / 16) * kT_TileXb;  // plane stride inside the tile
-        sts_u32(dst + 0 * ps, gather_bytes(hi[d][0], hi[d][1], hi[d][2], hi[d][3], 0) ^ 0x80808080u);
-        sts_u32(dst + 1 * ps, gather_bytes(lo[d][0], lo[d][1], lo[d][2], lo[d][3], 3) ^ 0x80808080u);
-        sts_u32(dst + 2 * ps, gather_bytes(lo[d][0], lo[d][1], lo[d][2], lo[d][3], 2) ^ 0x80808080u);
-        sts_u32(dst + 3 * ps, gather_bytes(lo[d][0], lo[d][1], lo[d][2], lo[d][3], 1) ^ 0x80808080u);
-        sts_u32(dst + 4 * ps, gather_bytes(lo[d][0], lo[d][1], lo[d][2], lo[d][3], 0) ^ 0x80808080u);
       }
     }
-    __syncthreads();
-    // tile -> workspace: per (xyz, plane) the pass's x-blocks are one contiguous span
-    for (int idx = threadIdx.x; idx < 3 * kT_Slices * (kT_PanelCols / 16) * (kT_XbBytes / 16); idx += blockDim.x) {
-      const int q = idx & (kT_XbBytes / 16 - 1);
-      const int r = idx / (kT_XbBytes / 16);
-      const int xb = r & (kT_PanelCols / 16 - 1), ds = r / (kT_PanelCols / 16);
+    const int64_t gf = (int64_t)fg * kT_ItemFrames + warp;
+    const bool live = gf < p.n_frames;
+    const float* fr = p.forces + (live ? gf : p.n_frames - 1) * frame_elems;
+    uint32_t lo_w[3][4], hi_w[3][4];
+    uint32_t range = 0;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      for (int m = 0; m < cn[cc]; ++m) {
+        const float* q = fr + 3 * __ldg(p.col_sites + cb[cc] + m);
+        v0 += (double)__ldg(q);
+        v1 += (double)__ldg(q + 1);
+        v2 += (double)__ldg(q + 2);
+      }
+      const double sc = live ? csc[cc] : 0.0;
+      const double t0 = fma(v0, sc, kI8Magic), t1 = fma(v1, sc, kI8Magic), t2 = fma(v2, sc, kI8Magic);
+      lo_w[0][cc] = (uint32_t)__double2loint(t0);
+      hi_w[0][cc] = (uint32_t)__double2hiint(t0);
+      lo_w[1][cc] = (uint32_t)__double2loint(t1);
+      hi_w[1][cc] = (uint32_t)__double2hiint(t1);
+      lo_w[2][cc] = (uint32_t)__double2loint(t2);
+      hi_w[2][cc] = (uint32_t)__double2hiint(t2);
+      range |= (hi_w[0][cc] ^ kI8HiExpect) | (hi_w[1][cc] ^ kI8HiExpect) | (hi_w[2][cc] ^ kI8HiExpect);
+    }
+    if (__any_sync(0xffffffffu, (range & 0xFFFFFF00u) != 0) && lane == 0) p.flags[gf] = 1;
+    const uint32_t tbase = smem_u32(tiles) + (uint32_t)buf * kT_TileBytes;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const uint32_t dst = tbase + (uint32_t)((d * kT_Slices) * (kT_PanelCols / 16) + (lane >> 2)) * kT_TileXb +
+                           (uint32_t)(warp * 16 + (lane & 3) * 4);
+      constexpr uint32_t ps = (kT_PanelCols / 16) * kT_TileXb;  // plane stride inside the tile
+      sts_u32(dst + 0 * ps, gather_bytes(hi_w[d][0], hi_w[d][1], hi_w[d][2], hi_w[d][3], 0) ^ 0x80808080u);
+      sts_u32(dst + 1 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 3) ^ 0x80808080u);
+      sts_u32(dst + 2 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 2) ^ 0x80808080u);
+      sts_u32(dst + 3 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 1) ^ 0x80808080u);
+      sts_u32(dst + 4 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 0) ^ 0x80808080u);
+    }
+    __syncthreads();  // also: everyone has left the copy-out of the item before the previous one (same buffer)
+    // tile -> workspace: rows of 128 bytes (k-group fg % 4 of x-block gxb, chunk (fg / 4, xyz), plane)
+    const unsigned char* tile = tiles + (size_t)buf * kT_TileBytes;
+    const int fb = fg >> 2, kg = fg & 3;
+    for (int idx = threadIdx.x; idx < 3 * kT_Slices * (kT_PanelCols / 16) * kT_ItemFrames; idx += blockDim.x) {
+      const int q = idx & (kT_ItemFrames - 1);
+      const int xb = (idx >> 3) & (kT_PanelCols / 16 - 1), ds = idx >> 6;
       const int gxb = pass * (kT_PanelCols / 16) + xb;
       if (gxb >= p.n_xb) continue;
       const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)(ds * (kT_PanelCols / 16) + xb) * kT_TileXb + q * 16);
       const int d = ds / kT_Slices, s = ds - d * kT_Slices;
-      unsigned char* dst = p.digits + (((size_t)(fb * 3 + d) * kT_Slices + s) * p.n_xb + gxb) * kT_XbBytes + q * 16;
+      unsigned char* dst =
+          p.digits + (((size_t)(fb * 3 + d) * kT_Slices + s) * p.n_xb + gxb) * kT_XbBytes + kg * 128 + q * 16;
       *reinterpret_cast<uint4*>(dst) = v;
     }
-    __syncthreads();
   }
-  // frames with a value out of range: clear their rows again (the float64 pass adds them), list the live ones
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (!__any_sync(0xffffffffu, bad[i] != 0)) continue;
-    const int f = warp + 8 * i;
-    const size_t in_xb = (size_t)((f >> 3) * 128 + (f & 7) * 16);
-    for (int idx = lane; idx < 3 * kT_Slices * p.n_xb; idx += 32) {
-      const int gxb = idx % p.n_xb, ds = idx / p.n_xb;
-      const int d = ds / kT_Slices, s = ds - d * kT_Slices;
-      unsigned char* dst = p.digits + (((size_t)(fb * 3 + d) * kT_Slices + s) * p.n_xb + gxb) * kT_XbBytes + in_xb;
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-    }
-    if (lane == 0 && f0 + f < p.n_frames) {
-      const int slot = atomicAdd(p.leftover_count, 1);
-      p.leftover[slot] = (int32_t)(p.frame0 + f0 + f);
+}
+
+// Flagged frames: clear their rows in every plane (the float64 pass adds them), list the ones that exist.
+__global__ void __launch_bounds__(256) i8t_scrub_kernel(const int32_t* __restrict__ flags, int n_flags, int64_t n_frames,
+                                                        int64_t frame0, int n_xb, unsigned char* __restrict__ digits,
+                                                        int32_t* __restrict__ leftover_count, int32_t* __restrict__ leftover) {
+  const int lane = threadIdx.x & 31;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n_flags; base += n_warps * 32) {
+    const int mine = base + lane < n_flags ? flags[base + lane] : 0;
+    uint32_t mask = __ballot_sync(0xffffffffu, mine != 0);
+    while (mask) {
+      const int f = base + __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int fb = f / kT_ChunkFrames, r = f - fb * kT_ChunkFrames;
+      const size_t in_xb = (size_t)((r >> 3) * 128 + (r & 7) * 16);
+      for (int idx = lane; idx < 3 * kT_Slices * n_xb; idx += 32) {
+        const int gxb = idx % n_xb, ds = idx / n_xb;
+        const int d = ds / kT_Slices, s = ds - d * kT_Slices;
+        unsigned char* dst = digits + (((size_t)(fb * 3 + d) * kT_Slices + s) * n_xb + gxb) * kT_XbBytes + in_xb;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      }
+      if (lane == 0 && f < n_frames) {
+        const int slot = atomicAdd(leftover_count, 1);
+        leftover[slot] = (int32_t)(frame0 + f);
+      }
     }
   }
 }
@@ -298,16 +319,25 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a0 = sbase + (uint32_t)stage * kT_StageBytes;
           const uint32_t b0 = a0 + kT_Slices * kT_APlane;
-          uint32_t started = c > c0 ? 0x1Fu : 0u;  // bit l: accumulator l already holds a product of this unit
+          // A_s against the STACK of column planes B_0 .. B_{4-s} (contiguous in the stage, 6 x-blocks each): one
+          // MMA of N = 96 (5 - s) writes the accumulators of the levels s .. 4, which are adjacent in TMEM.
+          // N <= 256: the three widest are issued as two halves.  8 MMAs instead of 15 per chunk -- the operand
+          // reads from shared memory drop from 105 KB to 77 KB (the kernel is bound by them, not by the math).
+          const uint32_t fresh = c > c0 ? 1u : 0u;
 #pragma unroll
           for (int s = 0; s < kT_Slices; ++s) {
-#pragma unroll
-            for (int t = 0; t < kT_Slices - s; ++t) {
-              const int l = s + t;
-              const uint64_t da = umma_desc_mn_i8(a0 + s * kT_APlane, 128, kT_XbBytes);
-              const uint64_t db = umma_desc_mn_i8(b0 + t * kT_BPlane, 128, kT_XbBytes);
-              umma_i8_issue(tmem_base + (uint32_t)(l * kT_N), da, db, kT_Idesc, (started >> l) & 1u);
-              started |= 1u << l;
+            const uint64_t da = umma_desc_mn_i8(a0 + s * kT_APlane, 128, kT_XbBytes);
+            const int width = kT_N * (kT_Slices - s);
+            const uint32_t acc = s == 0 ? fresh : 1u;  // s = 0 touches every level first
+            if (width > 256) {
+              const int half = width / 2;
+              umma_i8_issue(tmem_base + (uint32_t)(s * kT_N), da, umma_desc_mn_i8(b0, 128, kT_XbBytes),
+                            umma_idesc_i8(kT_M, half), acc);
+              umma_i8_issue(tmem_base + (uint32_t)(s * kT_N + half), da,
+                            umma_desc_mn_i8(b0 + (half / 16) * kT_XbBytes, 128, kT_XbBytes), umma_idesc_i8(kT_M, half), acc);
+            } else {
+              umma_i8_issue(tmem_base + (uint32_t)(s * kT_N), da, umma_desc_mn_i8(b0, 128, kT_XbBytes),
+                            umma_idesc_i8(kT_M, width), acc);
             }
           }
           umma_commit(&empty[stage]);  // arrives when the tensor core has finished reading the stage
@@ -404,7 +434,7 @@ __global__ void __launch_bounds__(256) i8t_leftover_kernel(const float* __restri
 }
 
 struct I8tLayout {
-  size_t colmax, exps, scales, count, leftover, digits, total;
+  size_t colmax, exps, scales, count, leftover, flags, digits, total;
   int64_t slab;
 };
 
@@ -417,9 +447,10 @@ static I8tLayout i8t_layout(int n_red, int64_t n_frames) {
   L.scales = L.exps + up(n_pad * 4);
   L.count = L.scales + up(n_pad * 8);
   L.leftover = L.count + 1024;
-  L.digits = L.leftover + up((size_t)n_frames * 4);
   const int64_t rounded = (n_frames + kT_ChunkFrames - 1) / kT_ChunkFrames * kT_ChunkFrames;
   L.slab = rounded < kT_SlabFrames ? rounded : kT_SlabFrames;
+  L.flags = L.leftover + up((size_t)n_frames * 4);
+  L.digits = L.flags + up((size_t)L.slab * 4);
   L.total = L.digits + (size_t)(L.slab / kT_ChunkFrames) * 3 * kT_Slices * (n_pad / 16) * kT_XbBytes;
   return L;
 }
@@ -451,6 +482,7 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
   double* scales = reinterpret_cast<double*>(ws + L.scales);
   int32_t* count = reinterpret_cast<int32_t*>(ws + L.count);
   int32_t* leftover = reinterpret_cast<int32_t*>(ws + L.leftover);
+  int32_t* flags = reinterpret_cast<int32_t*>(ws + L.flags);
   unsigned char* digits = reinterpret_cast<unsigned char*>(ws + L.digits);
   const float* f = reinterpret_cast<const float*>(forces);
   const int n_pad = i8t_pad(n_red), n_xb = n_pad / 16;
@@ -466,9 +498,12 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
     AGF_CUDA_TRY(cudaGetLastError());
   }
   const size_t syrk_smem = (size_t)kT_Stages * kT_StageBytes + (2 * kT_Stages + 2) * sizeof(uint64_t) + 16;
-  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kT_TileBytes));
+  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kT_TileBytes));
   AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
   const int sms = sm_count();
+  int digit_ctas_per_sm = 1;
+  AGF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&digit_ctas_per_sm, i8t_digits_kernel, 256, 2 * kT_TileBytes));
+  if (digit_ctas_per_sm < 1) digit_ctas_per_sm = 1;
   I8tSyrkParams q;
   memset(&q, 0, sizeof(q));
   q.digits = digits;
@@ -485,18 +520,24 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
     memset(&d, 0, sizeof(d));
     d.n_frames = n_frames - f0 < L.slab ? n_frames - f0 : L.slab;
     d.forces = f + f0 * (int64_t)n_sites * 3;
-    d.frame0 = f0;
     d.n_sites = n_sites;
     d.n_red = n_red;
     d.n_xb = n_xb;
+    const int n_fb = (int)((d.n_frames + kT_ChunkFrames - 1) / kT_ChunkFrames);
+    d.n_groups = n_fb * (kT_ChunkFrames / kT_ItemFrames);
     d.col_ptr = col_ptr;
     d.col_sites = col_sites;
     d.scales = scales;
     d.digits = digits;
-    d.leftover_count = count;
-    d.leftover = leftover;
-    const int n_fb = (int)((d.n_frames + kT_ChunkFrames - 1) / kT_ChunkFrames);
-    i8t_digits_kernel<<<n_fb, 256, kT_TileBytes, s>>>(d);
+    d.flags = flags;
+    const int n_flags = n_fb * kT_ChunkFrames;
+    AGF_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)n_flags * 4, s));
+    const int64_t n_items = (int64_t)((n_xb * 16 + kT_PanelCols - 1) / kT_PanelCols) * d.n_groups;
+    const int64_t want = (int64_t)sms * digit_ctas_per_sm;  // all resident at once: equal item ranges = equal work
+    i8t_digits_kernel<<<(int)(n_items < want ? n_items : want), 256, 2 * kT_TileBytes, s>>>(d);
+    AGF_CUDA_TRY(cudaGetLastError());
+    i8t_scrub_kernel<<<(n_flags + 255) / 256 < sms ? (n_flags + 255) / 256 : sms, 256, 0, s>>>(flags, n_flags, d.n_frames, f0, n_xb,
+                                                                                            digits, count, leftover);
     AGF_CUDA_TRY(cudaGetLastError());
     q.n_chunks = 3 * n_fb;
     q.n_slices = (q.n_chunks + kT_SliceChunks - 1) / kT_SliceChunks;

@@ -6,7 +6,7 @@
 namespace agf {
 
 // Instruction descriptor: D int32, A and B signed 8-bit, both MN-major, dense.
-constexpr uint32_t umma_idesc_i8(int m, int n) {
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int m, int n) {
   return (2u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
 }
