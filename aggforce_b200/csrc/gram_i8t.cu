@@ -12,7 +12,7 @@
 //      x-block = 16 reduced columns, k-group = 8 frames: one x-block of a chunk and plane is 512 contiguous
 //      bytes = four 8 x 16 core matrices of the canonical MN-major no-swizzle UMMA layout, and any window of
 //      x-blocks is one contiguous span -> one 1-D TMA bulk copy per operand plane, no tensor map.
-//   2. i8t_syrk_kernel (persistent, one CTA per SM): work unit = (slice of <= kT_SliceChunks chunks, tile of
+//   2. i8t_syrk_kernel (persistent, one CTA per SM): work unit = (slice of <= p.slice_chunks chunks, tile of
 //      128 x 96 Gram elements on or above the diagonal).  Warp 0 streams the unit's operand planes through a
 //      6-stage ring (per chunk: 5 x 4 KB for the 128 rows, 5 x 3 KB for the 96 columns), warp 1 issues
 //      tcgen05.mma.kind::i8 (M 128, N 96, K 32): the 15 plane products with s + t <= 4, accumulated EXACTLY
@@ -23,6 +23,8 @@
 //      running at one time read the same ~50 MB of digits: the operands come from L2, not HBM.
 // Frames holding a value outside the fixed-point range (or a non-finite one) are left out of the planes and
 // added in float64 by i8t_leftover_kernel, so the result does not depend on the scale sample.
+#include <stdlib.h>
+
 #include "i8.cuh"
 
 namespace agf {
@@ -35,7 +37,7 @@ constexpr int kT_APlane = (kT_M / 16) * kT_XbBytes;      // 4096
 constexpr int kT_BPlane = (kT_N / 16) * kT_XbBytes;      // 3072
 constexpr int kT_StageBytes = kT_Slices * (kT_APlane + kT_BPlane);  // 35 840
 constexpr int kT_Stages = 6;
-constexpr int kT_SliceChunks = 128;     // 4 096 contraction rows per unit (int32 headroom allows 768)
+constexpr int kT_SliceChunks = 256;     // 8 192 contraction rows per unit (int32 headroom allows 768 chunks)
 constexpr int kT_SlabFrames = 16384;    // frames whose digits are resident at a time
 constexpr int kT_SyrkThreads = 192;     // load warp, MMA warp, four epilogue warps
 constexpr int kT_MaxRed = 8192;
@@ -77,12 +79,13 @@ __global__ void __launch_bounds__(128) i8t_sample_kernel(const float* __restrict
 }
 
 __global__ void i8t_scale_kernel(const unsigned long long* __restrict__ colmax_bits, int n_red, int n_pad,
-                                 int32_t* __restrict__ exps, double* __restrict__ scales) {
+                                 int32_t* __restrict__ exps, double* __restrict__ scales, double* __restrict__ pow2) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= n_pad) return;
   const int e = x < n_red ? column_exponent(colmax_bits[x]) : 0;
   exps[x] = e;
   scales[x] = x < n_red ? ldexp(1.0, 39 - e) : 0.0;
+  pow2[x] = ldexp(1.0, e - 7);  // G[x][y] = pow2[x] pow2[y] sum_l 2^(-8 l) acc_l[x][y]
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -110,7 +113,7 @@ __global__ void __launch_bounds__(256) i8t_digits_kernel(const __grid_constant__
   const int64_t n_items = (int64_t)n_pass * p.n_groups;
   const int64_t lo = n_items * blockIdx.x / gridDim.x, hi = n_items * (blockIdx.x + 1) / gridDim.x;
   int cur_pass = -1, buf = 0;
-  int cb[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0};
+  int cb[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0}, cs0[4] = {0, 0, 0, 0}, cs1[4] = {0, 0, 0, 0};
   double csc[4] = {0.0, 0.0, 0.0, 0.0};
   for (int64_t item = lo; item < hi; ++item, buf ^= 1) {
     const int pass = (int)(item / p.n_groups), fg = (int)(item - (int64_t)pass * p.n_groups);
@@ -119,11 +122,13 @@ __global__ void __launch_bounds__(256) i8t_digits_kernel(const __grid_constant__
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const int x = pass * kT_PanelCols + 4 * lane + cc;
-        cb[cc] = cn[cc] = 0;
+        cb[cc] = cn[cc] = cs0[cc] = cs1[cc] = 0;
         csc[cc] = 0.0;
         if (x < p.n_red) {
           cb[cc] = __ldg(p.col_ptr + x);
           cn[cc] = __ldg(p.col_ptr + x + 1) - cb[cc];
+          if (cn[cc] > 0) cs0[cc] = 3 * __ldg(p.col_sites + cb[cc]);
+          if (cn[cc] > 1) cs1[cc] = 3 * __ldg(p.col_sites + cb[cc] + 1);
           csc[cc] = __ldg(p.scales + x);
         }
       }
@@ -131,12 +136,25 @@ __global__ void __launch_bounds__(256) i8t_digits_kernel(const __grid_constant__
     const int64_t gf = (int64_t)fg * kT_ItemFrames + warp;
     const bool live = gf < p.n_frames;
     const float* fr = p.forces + (live ? gf : p.n_frames - 1) * frame_elems;
+    // the first two members of the lane's four columns: 24 independent loads in flight at once (member lists
+    // walked one after the other would be as many dependent round trips to DRAM)
+    float a[4][3], b[4][3];
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const bool h0 = cn[cc] > 0, h1 = cn[cc] > 1;
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        a[cc][d] = h0 ? __ldg(fr + cs0[cc] + d) : 0.f;
+        b[cc][d] = h1 ? __ldg(fr + cs1[cc] + d) : 0.f;
+      }
+    }
     uint32_t lo_w[3][4], hi_w[3][4];
     uint32_t range = 0;
 #pragma unroll
     for (int cc = 0; cc < 4; ++cc) {
-      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-      for (int m = 0; m < cn[cc]; ++m) {
+      double v0 = (double)a[cc][0] + (double)b[cc][0], v1 = (double)a[cc][1] + (double)b[cc][1],
+             v2 = (double)a[cc][2] + (double)b[cc][2];
+      for (int m = 2; m < cn[cc]; ++m) {
         const float* q = fr + 3 * __ldg(p.col_sites + cb[cc] + m);
         v0 += (double)__ldg(q);
         v1 += (double)__ldg(q + 1);
@@ -215,8 +233,8 @@ __global__ void __launch_bounds__(256) i8t_scrub_kernel(const int32_t* __restric
 struct I8tSyrkParams {
   const unsigned char* digits;
   int32_t n_chunks;  // chunks of the slab (3 per 32 frames)
-  int32_t n_red, n_xb, n_mb, n_nb, n_tiles, n_slices;
-  const int32_t* exps;
+  int32_t n_red, n_xb, n_mb, n_nb, n_tiles, n_slices, slice_chunks;
+  const double* pow2;  // [n_pad] 2^(E_x - 7)
   double* gram;
 };
 
@@ -275,8 +293,8 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
         const int ks = u / p.n_tiles;
         int mi, nj;
         i8t_tile(u - ks * p.n_tiles, p.n_nb, mi, nj);
-        const int c0 = ks * kT_SliceChunks;
-        const int c1 = c0 + kT_SliceChunks < p.n_chunks ? c0 + kT_SliceChunks : p.n_chunks;
+        const int c0 = ks * p.slice_chunks;
+        const int c1 = c0 + p.slice_chunks < p.n_chunks ? c0 + p.slice_chunks : p.n_chunks;
         const unsigned char* a_src = p.digits + (size_t)c0 * kT_Slices * plane_bytes + (size_t)mi * (kT_M / 16) * kT_XbBytes;
         const unsigned char* b_src = p.digits + (size_t)c0 * kT_Slices * plane_bytes + (size_t)nj * (kT_N / 16) * kT_XbBytes;
         for (int c = c0; c < c1; ++c) {
@@ -306,8 +324,8 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
       bool first_unit = true;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
         const int ks = u / p.n_tiles;
-        const int c0 = ks * kT_SliceChunks;
-        const int c1 = c0 + kT_SliceChunks < p.n_chunks ? c0 + kT_SliceChunks : p.n_chunks;
+        const int c0 = ks * p.slice_chunks;
+        const int c1 = c0 + p.slice_chunks < p.n_chunks ? c0 + p.slice_chunks : p.n_chunks;
         if (!first_unit) {  // the epilogue warps have drained the accumulators of the previous unit
           mbar_wait(acc_empty, acc_phase);
           acc_phase ^= 1u;
@@ -352,13 +370,13 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
   } else {
     // ------------------------------------------------ epilogue warps: warp w may touch TMEM lanes 32 (w % 4) ...
     const int quarter = warp & 3;
+    double* patch = reinterpret_cast<double*>(smem + (size_t)kT_Stages * kT_StageBytes + 128) + quarter * 512;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int ks = u / p.n_tiles;
       int mi, nj;
       i8t_tile(u - ks * p.n_tiles, p.n_nb, mi, nj);
-      const int x = mi * kT_M + quarter * 32 + lane;
-      const int ex = x < p.n_red ? __ldg(p.exps + x) : 0;
+      const double px = __ldg(p.pow2 + mi * kT_M + quarter * 32 + lane);  // row < n_pad always
       mbar_wait(acc_full, acc_phase);
       acc_phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -386,13 +404,21 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
           if (lane == 0) mbar_arrive(acc_empty);
         }
         const int y0 = nj * kT_N + c0;
-        if (x < p.n_red && y0 + 15 >= x) {
+        if (y0 + 15 < mi * kT_M + quarter * 32 || y0 >= p.n_red) continue;  // warp-uniform: nothing on or above the diagonal
+        // A thread holds 16 columns of ONE row: adds straight from here would touch 32 sectors per warp
+        // instruction.  Scale, transpose through the warp's 32 x 16 patch of shared memory (xor-swizzled: no
+        // bank conflicts either way), then two rows x 16 columns per instruction = 8 sectors.
+        __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int y = y0 + i;
-            if (y >= x && y < p.n_red)
-              atomicAdd(p.gram + (int64_t)x * p.n_red + y, ldexp(g[i], ex + __ldg(p.exps + y) - 14));
-          }
+        for (int i = 0; i < 16; ++i) patch[lane * 16 + (i ^ (lane & 15))] = g[i] * px * __ldg(p.pow2 + y0 + i);
+        __syncwarp();
+        const int c = lane & 15, y = y0 + c;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int r = 2 * k + (lane >> 4);
+          const int xr = mi * kT_M + quarter * 32 + r;
+          if (y >= xr && y < p.n_red && xr < p.n_red)
+            atomicAdd(p.gram + (int64_t)xr * p.n_red + y, patch[r * 16 + (c ^ (r & 15))]);
         }
       }
     }
@@ -434,7 +460,7 @@ __global__ void __launch_bounds__(256) i8t_leftover_kernel(const float* __restri
 }
 
 struct I8tLayout {
-  size_t colmax, exps, scales, count, leftover, flags, digits, total;
+  size_t colmax, exps, scales, pow2, count, leftover, flags, digits, total;
   int64_t slab;
 };
 
@@ -445,7 +471,8 @@ static I8tLayout i8t_layout(int n_red, int64_t n_frames) {
   L.colmax = 0;
   L.exps = up(n_pad * 8);
   L.scales = L.exps + up(n_pad * 4);
-  L.count = L.scales + up(n_pad * 8);
+  L.pow2 = L.scales + up(n_pad * 8);
+  L.count = L.pow2 + up(n_pad * 8);
   L.leftover = L.count + 1024;
   const int64_t rounded = (n_frames + kT_ChunkFrames - 1) / kT_ChunkFrames * kT_ChunkFrames;
   L.slab = rounded < kT_SlabFrames ? rounded : kT_SlabFrames;
@@ -480,6 +507,7 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
   unsigned long long* colmax = reinterpret_cast<unsigned long long*>(ws + L.colmax);
   int32_t* exps = reinterpret_cast<int32_t*>(ws + L.exps);
   double* scales = reinterpret_cast<double*>(ws + L.scales);
+  double* pow2 = reinterpret_cast<double*>(ws + L.pow2);
   int32_t* count = reinterpret_cast<int32_t*>(ws + L.count);
   int32_t* leftover = reinterpret_cast<int32_t*>(ws + L.leftover);
   int32_t* flags = reinterpret_cast<int32_t*>(ws + L.flags);
@@ -494,10 +522,11 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
     i8t_sample_kernel<<<dim3((n_red + 127) / 128, rows), 128, 0, s>>>(f, n_frames, stride, n_sites, col_ptr, col_sites, n_red,
                                                                      colmax);
     AGF_CUDA_TRY(cudaGetLastError());
-    i8t_scale_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(colmax, n_red, n_pad, exps, scales);
+    i8t_scale_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(colmax, n_red, n_pad, exps, scales, pow2);
     AGF_CUDA_TRY(cudaGetLastError());
   }
-  const size_t syrk_smem = (size_t)kT_Stages * kT_StageBytes + (2 * kT_Stages + 2) * sizeof(uint64_t) + 16;
+  // stages, 128 bytes of barriers + TMEM address, four 32 x 16 float64 transposition patches
+  const size_t syrk_smem = (size_t)kT_Stages * kT_StageBytes + 128 + 4 * 512 * sizeof(double);
   AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kT_TileBytes));
   AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
   const int sms = sm_count();
@@ -513,7 +542,12 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
   q.n_nb = (n_red + kT_N - 1) / kT_N;
   q.n_tiles = 0;
   for (int mi = 0; mi < q.n_mb; ++mi) q.n_tiles += q.n_nb - (kT_M * mi) / kT_N;
-  q.exps = exps;
+  q.pow2 = pow2;
+  q.slice_chunks = kT_SliceChunks;
+  if (const char* e = getenv("AGF_I8T_SLICE_CHUNKS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 768) q.slice_chunks = v;  // 768 chunks = 24 576 rows: the int32 accumulators' limit
+  }
   q.gram = gram;
   for (int64_t f0 = 0; f0 < n_frames; f0 += L.slab) {
     I8tDigitsParams d;
@@ -540,7 +574,7 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
                                                                                             digits, count, leftover);
     AGF_CUDA_TRY(cudaGetLastError());
     q.n_chunks = 3 * n_fb;
-    q.n_slices = (q.n_chunks + kT_SliceChunks - 1) / kT_SliceChunks;
+    q.n_slices = (q.n_chunks + q.slice_chunks - 1) / q.slice_chunks;
     const int64_t units = (int64_t)q.n_slices * q.n_tiles;
     i8t_syrk_kernel<<<(int)(units < sms ? units : sms), kT_SyrkThreads, syrk_smem, s>>>(q);
     AGF_CUDA_TRY(cudaGetLastError());
