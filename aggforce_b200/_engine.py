@@ -827,6 +827,10 @@ class CompiledMap:
         self.out_f32, self.sparse, self.slice = False, False, False
         sizes = np.bincount(labels, minlength=n_labels)
         order = np.argsort(sizes, kind="stable")
+        if self.n_cg > 64:  # packed-panel GEMM path: unique columns follow their first site (see __init__)
+            first = np.full(n_labels, self.n_fg, dtype=np.int64)
+            np.minimum.at(first, labels, np.arange(self.n_fg))
+            order = np.argsort(first, kind="stable")
         rank = np.empty_like(order)
         rank[order] = np.arange(order.size)
         ptr_, sites = csr_from_labels(rank[labels], n_labels)

@@ -137,6 +137,8 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
             # collective): ONE message
             stat[2:3].copy_(_engine.dev_f64([n_elem]))
             _engine.allreduce_sum_max_(stat, 3)
+        if pend is not None and pend.buf is None:
+            pend = None  # a large device fit: checked when it was solved, downloaded only on request
         got = _engine.read_many([stat] + ([pend.buf] if pend is not None else []))
         st = got[0]
         if _engine.sharded():

@@ -128,6 +128,29 @@ class _DeviceFit:
         return self.expanded
 
 
+class _LargeDeviceFit:
+    """Result of the cuSOLVER path (n_red >= 512) that stays on the device: ``x_dev`` is the float64
+    ``(n_red, n_cg)`` solution, already checked (finite, equality rows met) when it was computed, so nothing
+    has to be read before the map is applied; ``matrix()`` downloads and expands it on first host access."""
+
+    buf = None  # no status to read: project_forces does not resolve this fit eagerly
+    fell_back = False
+
+    def __init__(self, x_dev, cols: np.ndarray) -> None:
+        self.x_dev, self.cols = x_dev, cols
+        self.expanded: Union[None, np.ndarray] = None
+
+    def matrix(self) -> np.ndarray:
+        if self.expanded is None:
+            reduced = _engine.to_host(self.x_dev).T
+            self.expanded = np.ascontiguousarray(reduced[:, self.cols])
+            self.x_dev = None
+        return self.expanded
+
+    def resolve(self, _host_buf=None) -> np.ndarray:
+        return self.matrix()
+
+
 def _equality_rows(coord_map: LinearMap, cols: np.ndarray, n_red: int) -> np.ndarray:
     """``A = coord_map @ C``: the coordinate-map columns of every group summed (qplinear.py:82)."""
     n_fg = coord_map.n_fg_sites
@@ -248,9 +271,16 @@ def qp_linear_map(
     if backend == "exact":
         sol = None
         if on_device:
-            sol = solve_equality_qp_device(qp_mat, a_mat, np.eye(coord_map.n_cg_sites))
-            if sol is None:  # not numerically positive definite: host path with its null-space fallback
-                qp_mat = _engine.to_host(qp_mat)
+            sol = solve_equality_qp_device(qp_mat, a_mat, np.eye(coord_map.n_cg_sites), keep_on_device=True)
+            if sol is not None:
+                # the solution is the coefficient operand of kernel (d) up to a row permutation: the fitted map
+                # is applied from the device, its 20 MB host form (500 x 5 000) only exists if somebody asks
+                structure, ucol_of_col = _engine.CompiledMap.from_labels(cols, n_cg, n_red)
+                pos = _engine._dev_cached(np.ascontiguousarray(np.argsort(ucol_of_col), dtype=np.int64))
+                compiled = structure.with_values(sol.index_select(0, pos).contiguous())
+                force_map = LinearMap.from_device_fit(_LargeDeviceFit(sol, cols), n_cg, cols, compiled)
+                return SeperableTMap(coord_map=coord_map, force_map=force_map)
+            qp_mat = _engine.to_host(qp_mat)  # not numerically positive definite: host path, null-space fallback
         if sol is None:
             sol = solve(qp_mat, a_mat, np.eye(coord_map.n_cg_sites), solver_args)
         if sol is None:

@@ -66,13 +66,15 @@ def solve_equality_qp(P, A, b) -> Optional[np.ndarray]:
     return x
 
 
-def solve_equality_qp_device(P, A, b) -> Optional[np.ndarray]:
+def solve_equality_qp_device(P, A, b, keep_on_device: bool = False):
     """Same closed form on the GPU for large problems: ``P`` is a float64 CUDA tensor
     (the Gram never leaves the device), one cuSOLVER Cholesky + multi-right-hand-side solves through
     ``torch.linalg``.  Returns ``None`` when ``P`` or the Schur complement is not numerically
     positive definite (or the solution misses the equality constraints) -- the caller then falls back
     to :func:`solve_equality_qp` on the host.  A singular Schur complement (redundant equality rows, as
-    the featurised fit produces) is handled like the host path: least squares on the small system."""
+    the featurised fit produces) is handled like the host path: least squares on the small system.
+    ``keep_on_device``: return the solution as a CUDA tensor (checked like the host copy) instead of
+    downloading it -- the fitted map of a large problem is applied from where it is."""
     import torch
 
     a = torch.as_tensor(np.asarray(A, dtype=np.float64), device=P.device)
@@ -95,6 +97,8 @@ def solve_equality_qp_device(P, A, b) -> Optional[np.ndarray]:
     resid = float((a @ x - rhs).abs().max().item()) if x.numel() else 0.0
     if not bool(torch.isfinite(x).all().item()) or resid > 1e-6 * max(1.0, float(rhs.abs().max().item())):
         return None
+    if keep_on_device:
+        return x[:, 0] if vec else x
     out = x.cpu().numpy()
     return out[:, 0] if vec else out
 
