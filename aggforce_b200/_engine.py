@@ -815,6 +815,7 @@ class CompiledMap:
         self.n_ucol, self.nnz = int(uniq.shape[0]), int(sites.size)
         self.ucol_ptr, self.ucol_sites = dev_i32(ptr_), dev_i32(sites)
         self.umat_t = dev_f64(uniq)  # [n_ucol, n_cg]
+        self._finite = bool(np.isfinite(uniq).all())
 
     @classmethod
     def from_labels(cls, column_labels: np.ndarray, n_cg: int, n_labels: int) -> Tuple["CompiledMap", np.ndarray]:
@@ -838,6 +839,12 @@ class CompiledMap:
         self.ucol_ptr, self.ucol_sites = dev_i32(ptr_), dev_i32(sites)
         self.umat_t = None  # filled per fit: see with_values
         return self, rank
+
+    def weights_finite(self) -> bool:
+        """The int8 application needs finite coefficients (a NaN / inf weight has no fixed-point digits; the
+        float64 kernels propagate it like numpy).  Host matrices are checked when compiled; a device fit is
+        checked when it is solved (``solve_equality_qp_device`` / ``agf_qp_equality_small`` decline otherwise)."""
+        return bool(getattr(self, "_finite", True))
 
     def with_values(self, umat_t: torch.Tensor) -> "CompiledMap":
         """A map sharing this one's (immutable) structure with its own coefficient operand."""
@@ -885,7 +892,18 @@ def map_apply(frames: Frames, cmap: CompiledMap, nan_mode: int, nan_atol: float,
         else:
             need = int(_lib.lib().agf_map_apply_workspace_bytes(dtype_code(piece), frames.n_sites, cmap.n_ucol,
                                                                 cmap.nnz, cmap.n_cg, piece.shape[0]))
-            if need > 0:  # too large for the shared-memory resident kernel: packed-panel DMMA GEMM
+            need_i8 = 0
+            if (need > 0 and _GRAM_I8[0] and piece.dtype == torch.float32 and cmap.n_cg > 64
+                    and piece.shape[0] >= _GRAM_I8T_MIN_FRAMES and cmap.weights_finite()):
+                need_i8 = int(_lib.lib().agf_map_apply_i8_workspace_bytes(frames.n_sites, cmap.n_ucol, cmap.n_cg,
+                                                                          piece.shape[0]))
+            if need_i8 > 0:  # int8 digit planes on tcgen05 (csrc/apply_i8.cu)
+                ws = workspace(need_i8)
+                _lib.call("agf_map_apply_i8", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites,
+                          ptr(cmap.ucol_ptr), ptr(cmap.ucol_sites), cmap.n_ucol, ptr(cmap.umat_t), cmap.n_cg, ptr(o),
+                          dtype_code(o), ptr(sumsq), nan_mode, float(nan_atol), ptr(flags), ptr(ws),
+                          C.c_size_t(ws.numel()), stream_ptr())
+            elif need > 0:  # too large for the shared-memory resident kernel: packed-panel DMMA GEMM
                 ws = workspace(need)
                 _lib.call("agf_map_apply_ws", ptr(piece), dtype_code(piece), piece.shape[0], frames.n_sites,
                           ptr(cmap.ucol_ptr), ptr(cmap.ucol_sites), cmap.n_ucol, cmap.nnz, ptr(cmap.umat_t),

@@ -29,6 +29,8 @@ SIGNATURES = {
                       _vp, _vp],
     "agf_map_apply_ws": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _i32, _vp, C.c_int, _vp, C.c_int, _dbl,
                          _vp, _vp, C.c_size_t, _vp],
+    "agf_map_apply_i8": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _vp, _i32, _vp, C.c_int, _vp, C.c_int, _dbl, _vp, _vp,
+                         C.c_size_t, _vp],
     "agf_map_apply_sparse": [_vp, C.c_int, _i64, _i32, _vp, _vp, _vp, _i32, _vp, C.c_int, _vp, C.c_int, _dbl, _vp,
                              _vp],
     "agf_map_apply_slice": [_vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _vp, C.c_int, _vp, C.c_int, _dbl, _vp, _vp],
@@ -59,6 +61,7 @@ PLAIN = {"agf_version": (C.c_int, []), "agf_peer_buffer_bytes": (C.c_size_t, [_i
          "agf_gram_linear_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64]),
          "agf_gram_linear_i8_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64]),
          "agf_gram_linear_i8t_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64]),
+         "agf_map_apply_i8_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i64]),
          "agf_map_apply_workspace_bytes": (C.c_size_t, [C.c_int, _i32, _i32, _i32, _i32, _i64]),
          "agf_gram_feat_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i64])}
 

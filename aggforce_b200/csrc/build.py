@@ -9,8 +9,8 @@ import sys
 from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent
-SOURCES = ["common.cu", "gram.cu", "apply.cu", "pairs.cu", "featgram.cu", "synth.cu", "augment.cu", "mapval.cu", "peak.cu", "qp.cu", "peer.cu", "gram_i8.cu", "gram_i8t.cu"]
-HEADERS = ["common.cuh", "i8.cuh", "frame_pipe.cuh", "panel.cuh", "philox.cuh", "../../include/agf_b200.h"]
+SOURCES = ["common.cu", "gram.cu", "apply.cu", "pairs.cu", "featgram.cu", "synth.cu", "augment.cu", "mapval.cu", "peak.cu", "qp.cu", "peer.cu", "gram_i8.cu", "gram_i8t.cu", "apply_i8.cu"]
+HEADERS = ["common.cuh", "i8.cuh", "i8_digits.cuh", "frame_pipe.cuh", "panel.cuh", "philox.cuh", "../../include/agf_b200.h"]
 LIB = CSRC / "libagf_b200.so"
 STAMP = CSRC / ".libagf_b200.stamp"
 

@@ -25,208 +25,22 @@
 // added in float64 by i8t_leftover_kernel, so the result does not depend on the scale sample.
 #include <stdlib.h>
 
-#include "i8.cuh"
+#include "i8_digits.cuh"
 
 namespace agf {
 
 constexpr int kT_M = 128, kT_N = 96;  // one tile; K = 32 contraction rows per MMA
-constexpr int kT_Slices = 5;
-constexpr int kT_ChunkFrames = 32;                       // one chunk = one MMA k-block
-constexpr int kT_XbBytes = (kT_ChunkFrames / 8) * 128;   // x-block of one chunk and plane: 512 B
 constexpr int kT_APlane = (kT_M / 16) * kT_XbBytes;      // 4096
 constexpr int kT_BPlane = (kT_N / 16) * kT_XbBytes;      // 3072
 constexpr int kT_StageBytes = kT_Slices * (kT_APlane + kT_BPlane);  // 35 840
 constexpr int kT_Stages = 6;
 constexpr int kT_SliceChunks = 256;     // 8 192 contraction rows per unit (int32 headroom allows 768 chunks)
-constexpr int kT_SlabFrames = 16384;    // frames whose digits are resident at a time
 constexpr int kT_SyrkThreads = 192;     // load warp, MMA warp, four epilogue warps
 constexpr int kT_MaxRed = 8192;
-constexpr int kT_SampleFrames = 1024;
-
-constexpr int kT_PanelCols = 128;                        // digits kernel: columns per work item
-constexpr int kT_ItemFrames = 8;                         // ... and frames (one k-group, one warp each)
-constexpr int kT_TileXb = kT_ItemFrames * 16 + 16;       // padded x-block stride in the staging tile (bank spread)
-constexpr int kT_TileBytes = 3 * kT_Slices * (kT_PanelCols / 16) * kT_TileXb;  // 17 280, two of them per CTA
 
 __host__ __device__ inline int i8t_pad(int n_red) {
   const int a = (n_red + kT_M - 1) / kT_M * kT_M, b = (n_red + kT_N - 1) / kT_N * kT_N;
   return a > b ? a : b;
-}
-
-// ------------------------------------------------------------------------------------------------
-// column scales from a strided sample of the frames: thread = column, block row = frame group
-__global__ void __launch_bounds__(128) i8t_sample_kernel(const float* __restrict__ forces, int64_t n_frames, int64_t stride,
-                                                         int n_sites, const int32_t* __restrict__ col_ptr,
-                                                         const int32_t* __restrict__ col_sites, int n_red,
-                                                         unsigned long long* __restrict__ colmax_bits) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= n_red) return;
-  const int b = __ldg(col_ptr + x), e = __ldg(col_ptr + x + 1);
-  double best = 0.0;
-  for (int64_t t = (int64_t)blockIdx.y * stride; t < n_frames; t += (int64_t)gridDim.y * stride) {
-    const float* fr = forces + t * (int64_t)n_sites * 3;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int m = b; m < e; ++m) {
-      const float* q = fr + 3 * __ldg(col_sites + m);
-      s0 += (double)__ldg(q);
-      s1 += (double)__ldg(q + 1);
-      s2 += (double)__ldg(q + 2);
-    }
-    const double m = fmax(fabs(s0), fmax(fabs(s1), fabs(s2)));
-    if (m < 1.0e300) best = fmax(best, m);
-  }
-  atomicMax(colmax_bits + x, (unsigned long long)__double_as_longlong(best));  // bits of x >= 0 order like x
-}
-
-__global__ void i8t_scale_kernel(const unsigned long long* __restrict__ colmax_bits, int n_red, int n_pad,
-                                 int32_t* __restrict__ exps, double* __restrict__ scales, double* __restrict__ pow2) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= n_pad) return;
-  const int e = x < n_red ? column_exponent(colmax_bits[x]) : 0;
-  exps[x] = e;
-  scales[x] = x < n_red ? ldexp(1.0, 39 - e) : 0.0;
-  pow2[x] = ldexp(1.0, e - 7);  // G[x][y] = pow2[x] pow2[y] sum_l 2^(-8 l) acc_l[x][y]
-}
-
-// ------------------------------------------------------------------------------------------------
-struct I8tDigitsParams {
-  const float* forces;   // first frame of the slab
-  int64_t n_frames;      // frames in the slab
-  int32_t n_sites, n_red, n_xb;
-  int32_t n_groups;      // groups of kT_ItemFrames frames, rounded up to whole chunks
-  const int32_t* col_ptr;
-  const int32_t* col_sites;
-  const double* scales;  // [n_pad]
-  unsigned char* digits;
-  int32_t* flags;        // [n_groups * kT_ItemFrames]: frame holds a value outside the fixed-point range
-};
-
-// Work item = (column pass of 128 columns, group of 8 frames); the items are dealt to the CTAs in equal
-// contiguous ranges, pass-major, so a CTA keeps its columns' member lists while it walks over frame groups.
-// Warp = frame, lane q = column quad 4 q .. 4 q + 3 of the pass: the four digits of a plane form one word.
-// The digits go through a double-buffered staging tile and leave as 128-byte rows (one k-group of one x-block).
-__global__ void __launch_bounds__(256) i8t_digits_kernel(const __grid_constant__ I8tDigitsParams p) {
-  extern __shared__ __align__(16) unsigned char tiles[];  // 2 x [xyz][plane][x-block of the pass][kT_TileXb]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t frame_elems = (int64_t)p.n_sites * 3;
-  const int n_pass = (p.n_xb * 16 + kT_PanelCols - 1) / kT_PanelCols;
-  const int64_t n_items = (int64_t)n_pass * p.n_groups;
-  const int64_t lo = n_items * blockIdx.x / gridDim.x, hi = n_items * (blockIdx.x + 1) / gridDim.x;
-  int cur_pass = -1, buf = 0;
-  int cb[4] = {0, 0, 0, 0}, cn[4] = {0, 0, 0, 0}, cs0[4] = {0, 0, 0, 0}, cs1[4] = {0, 0, 0, 0};
-  double csc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int64_t item = lo; item < hi; ++item, buf ^= 1) {
-    const int pass = (int)(item / p.n_groups), fg = (int)(item - (int64_t)pass * p.n_groups);
-    if (pass != cur_pass) {
-      cur_pass = pass;
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int x = pass * kT_PanelCols + 4 * lane + cc;
-        cb[cc] = cn[cc] = cs0[cc] = cs1[cc] = 0;
-        csc[cc] = 0.0;
-        if (x < p.n_red) {
-          cb[cc] = __ldg(p.col_ptr + x);
-          cn[cc] = __ldg(p.col_ptr + x + 1) - cb[cc];
-          if (cn[cc] > 0) cs0[cc] = 3 * __ldg(p.col_sites + cb[cc]);
-          if (cn[cc] > 1) cs1[cc] = 3 * __ldg(p.col_sites + cb[cc] + 1);
-          csc[cc] = __ldg(p.scales + x);
-        }
-      }
-    }
-    const int64_t gf = (int64_t)fg * kT_ItemFrames + warp;
-    const bool live = gf < p.n_frames;
-    const float* fr = p.forces + (live ? gf : p.n_frames - 1) * frame_elems;
-    // the first two members of the lane's four columns: 24 independent loads in flight at once (member lists
-    // walked one after the other would be as many dependent round trips to DRAM)
-    float a[4][3], b[4][3];
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      const bool h0 = cn[cc] > 0, h1 = cn[cc] > 1;
-#pragma unroll
-      for (int d = 0; d < 3; ++d) {
-        a[cc][d] = h0 ? __ldg(fr + cs0[cc] + d) : 0.f;
-        b[cc][d] = h1 ? __ldg(fr + cs1[cc] + d) : 0.f;
-      }
-    }
-    uint32_t lo_w[3][4], hi_w[3][4];
-    uint32_t range = 0;
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-      double v0 = (double)a[cc][0] + (double)b[cc][0], v1 = (double)a[cc][1] + (double)b[cc][1],
-             v2 = (double)a[cc][2] + (double)b[cc][2];
-      for (int m = 2; m < cn[cc]; ++m) {
-        const float* q = fr + 3 * __ldg(p.col_sites + cb[cc] + m);
-        v0 += (double)__ldg(q);
-        v1 += (double)__ldg(q + 1);
-        v2 += (double)__ldg(q + 2);
-      }
-      const double sc = live ? csc[cc] : 0.0;
-      const double t0 = fma(v0, sc, kI8Magic), t1 = fma(v1, sc, kI8Magic), t2 = fma(v2, sc, kI8Magic);
-      lo_w[0][cc] = (uint32_t)__double2loint(t0);
-      hi_w[0][cc] = (uint32_t)__double2hiint(t0);
-      lo_w[1][cc] = (uint32_t)__double2loint(t1);
-      hi_w[1][cc] = (uint32_t)__double2hiint(t1);
-      lo_w[2][cc] = (uint32_t)__double2loint(t2);
-      hi_w[2][cc] = (uint32_t)__double2hiint(t2);
-      range |= (hi_w[0][cc] ^ kI8HiExpect) | (hi_w[1][cc] ^ kI8HiExpect) | (hi_w[2][cc] ^ kI8HiExpect);
-    }
-    if (__any_sync(0xffffffffu, (range & 0xFFFFFF00u) != 0) && lane == 0) p.flags[gf] = 1;
-    const uint32_t tbase = smem_u32(tiles) + (uint32_t)buf * kT_TileBytes;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const uint32_t dst = tbase + (uint32_t)((d * kT_Slices) * (kT_PanelCols / 16) + (lane >> 2)) * kT_TileXb +
-                           (uint32_t)(warp * 16 + (lane & 3) * 4);
-      constexpr uint32_t ps = (kT_PanelCols / 16) * kT_TileXb;  // plane stride inside the tile
-      sts_u32(dst + 0 * ps, gather_bytes(hi_w[d][0], hi_w[d][1], hi_w[d][2], hi_w[d][3], 0) ^ 0x80808080u);
-      sts_u32(dst + 1 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 3) ^ 0x80808080u);
-      sts_u32(dst + 2 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 2) ^ 0x80808080u);
-      sts_u32(dst + 3 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 1) ^ 0x80808080u);
-      sts_u32(dst + 4 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 0) ^ 0x80808080u);
-    }
-    __syncthreads();  // also: everyone has left the copy-out of the item before the previous one (same buffer)
-    // tile -> workspace: rows of 128 bytes (k-group fg % 4 of x-block gxb, chunk (fg / 4, xyz), plane)
-    const unsigned char* tile = tiles + (size_t)buf * kT_TileBytes;
-    const int fb = fg >> 2, kg = fg & 3;
-    for (int idx = threadIdx.x; idx < 3 * kT_Slices * (kT_PanelCols / 16) * kT_ItemFrames; idx += blockDim.x) {
-      const int q = idx & (kT_ItemFrames - 1);
-      const int xb = (idx >> 3) & (kT_PanelCols / 16 - 1), ds = idx >> 6;
-      const int gxb = pass * (kT_PanelCols / 16) + xb;
-      if (gxb >= p.n_xb) continue;
-      const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)(ds * (kT_PanelCols / 16) + xb) * kT_TileXb + q * 16);
-      const int d = ds / kT_Slices, s = ds - d * kT_Slices;
-      unsigned char* dst =
-          p.digits + (((size_t)(fb * 3 + d) * kT_Slices + s) * p.n_xb + gxb) * kT_XbBytes + kg * 128 + q * 16;
-      *reinterpret_cast<uint4*>(dst) = v;
-    }
-  }
-}
-
-// Flagged frames: clear their rows in every plane (the float64 pass adds them), list the ones that exist.
-__global__ void __launch_bounds__(256) i8t_scrub_kernel(const int32_t* __restrict__ flags, int n_flags, int64_t n_frames,
-                                                        int64_t frame0, int n_xb, unsigned char* __restrict__ digits,
-                                                        int32_t* __restrict__ leftover_count, int32_t* __restrict__ leftover) {
-  const int lane = threadIdx.x & 31;
-  const int n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n_flags; base += n_warps * 32) {
-    const int mine = base + lane < n_flags ? flags[base + lane] : 0;
-    uint32_t mask = __ballot_sync(0xffffffffu, mine != 0);
-    while (mask) {
-      const int f = base + __ffs(mask) - 1;
-      mask &= mask - 1;
-      const int fb = f / kT_ChunkFrames, r = f - fb * kT_ChunkFrames;
-      const size_t in_xb = (size_t)((r >> 3) * 128 + (r & 7) * 16);
-      for (int idx = lane; idx < 3 * kT_Slices * n_xb; idx += 32) {
-        const int gxb = idx % n_xb, ds = idx / n_xb;
-        const int d = ds / kT_Slices, s = ds - d * kT_Slices;
-        unsigned char* dst = digits + (((size_t)(fb * 3 + d) * kT_Slices + s) * n_xb + gxb) * kT_XbBytes + in_xb;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-      }
-      if (lane == 0 && f < n_frames) {
-        const int slot = atomicAdd(leftover_count, 1);
-        leftover[slot] = (int32_t)(frame0 + f);
-      }
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -516,22 +330,21 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
   const int n_pad = i8t_pad(n_red), n_xb = n_pad / 16;
   AGF_CUDA_TRY(cudaMemsetAsync(ws, 0, L.leftover, s));
   {
-    const int64_t stride = n_frames > kT_SampleFrames ? n_frames / kT_SampleFrames : 1;
-    const int64_t n_sample = (n_frames + stride - 1) / stride;
-    const int rows = (int)(n_sample < 64 ? n_sample : 64);
-    i8t_sample_kernel<<<dim3((n_red + 127) / 128, rows), 128, 0, s>>>(f, n_frames, stride, n_sites, col_ptr, col_sites, n_red,
-                                                                     colmax);
+    const I8tSamplePlan sp = i8t_sample_plan(n_frames);
+    AGF_CUDA_TRY(cudaMemsetAsync(colmax, 0x7F, (size_t)n_pad * 8, s));
+    i8t_sample_kernel<<<dim3((n_red + 127) / 128, sp.groups), 128, 0, s>>>(f, n_frames, sp.stride, n_sites, col_ptr, col_sites,
+                                                                          n_red, colmax);
     AGF_CUDA_TRY(cudaGetLastError());
     i8t_scale_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(colmax, n_red, n_pad, exps, scales, pow2);
     AGF_CUDA_TRY(cudaGetLastError());
   }
   // stages, 128 bytes of barriers + TMEM address, four 32 x 16 float64 transposition patches
   const size_t syrk_smem = (size_t)kT_Stages * kT_StageBytes + 128 + 4 * 512 * sizeof(double);
-  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kT_TileBytes));
+  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_digits_kernel<kGramLayout>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kT_TileBytes));
   AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
   const int sms = sm_count();
   int digit_ctas_per_sm = 1;
-  AGF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&digit_ctas_per_sm, i8t_digits_kernel, 256, 2 * kT_TileBytes));
+  AGF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&digit_ctas_per_sm, i8t_digits_kernel<kGramLayout>, 256, 2 * kT_TileBytes));
   if (digit_ctas_per_sm < 1) digit_ctas_per_sm = 1;
   I8tSyrkParams q;
   memset(&q, 0, sizeof(q));
@@ -568,9 +381,9 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
     AGF_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)n_flags * 4, s));
     const int64_t n_items = (int64_t)((n_xb * 16 + kT_PanelCols - 1) / kT_PanelCols) * d.n_groups;
     const int64_t want = (int64_t)sms * digit_ctas_per_sm;  // all resident at once: equal item ranges = equal work
-    i8t_digits_kernel<<<(int)(n_items < want ? n_items : want), 256, 2 * kT_TileBytes, s>>>(d);
+    i8t_digits_kernel<kGramLayout><<<(int)(n_items < want ? n_items : want), 256, 2 * kT_TileBytes, s>>>(d);
     AGF_CUDA_TRY(cudaGetLastError());
-    i8t_scrub_kernel<<<(n_flags + 255) / 256 < sms ? (n_flags + 255) / 256 : sms, 256, 0, s>>>(flags, n_flags, d.n_frames, f0, n_xb,
+    i8t_scrub_kernel<kGramLayout><<<(n_flags + 255) / 256 < sms ? (n_flags + 255) / 256 : sms, 256, 0, s>>>(flags, n_flags, d.n_frames, f0, n_xb,
                                                                                             digits, count, leftover);
     AGF_CUDA_TRY(cudaGetLastError());
     q.n_chunks = 3 * n_fb;

@@ -550,6 +550,7 @@ def config_probes(agf, _engine, _lib, torch, dist, rank, world, peaks, hbm_peak,
         "agf_gram_linear_ws": ("tensor", (3 * n_red4 * (n_red4 + 1) + 3 * n4) * T4),
         "agf_gram_linear_i8t": ("tensor", (3 * n_red4 * (n_red4 + 1) + 3 * n4) * T4),
         "agf_map_apply_ws": ("tensor", 6 * 500 * n_red4 * T4),
+        "agf_map_apply_i8": ("tensor", 6 * 500 * n_red4 * T4),
         "agf_pair_moments": ("hbm", 12 * n4 * T4),
     }
     out["cfg4_shape"] = {
@@ -587,6 +588,7 @@ def config_probes(agf, _engine, _lib, torch, dist, rank, world, peaks, hbm_peak,
               "agf_gram_linear_i8t": ("tensor", (3 * n_red5 * (n_red5 + 1) + 3 * (n5 + ncg5)) * T5),
               "agf_gauss_augment": ("hbm", aug_bytes)}
     algo5a = {"agf_map_apply_ws": ("tensor", 6 * ncg5 * n_red5 * T5),
+              "agf_map_apply_i8": ("tensor", 6 * ncg5 * n_red5 * T5),
               "agf_gauss_augment": ("hbm", 2 * aug_bytes)}
     out["cfg5_shape"] = {
         "workload": f"synthetic {n5}-atom system, {ncg5} beads (+{ncg5} noise sites), n_red {n_red5}, {T5} frames per "

@@ -155,6 +155,24 @@ int agf_map_apply_ws(const void* points, int in_dtype, int64_t n_frames, int32_t
                      int nan_mode, double nan_atol, int32_t* nan_flags, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* The large dense application on the 5th-generation tensor cores (float32 input, finite weights, n_ucol <= 8192):
+ * same outputs and NaN semantics as agf_map_apply_ws.  The sums of every unique column are scaled per column by
+ * a power of two taken from a sample of the frames, rounded to 39-bit fixed point and split into five signed
+ * 8-bit digit planes (columns = contraction dimension, K-major core matrices, one frame block x 32 columns per
+ * TMA bulk copy); the weights, multiplied by the column scales, get a power-of-two scale per bead and the same
+ * five digits.  A persistent kernel accumulates the 15 plane products with s + t <= 4 exactly in int32
+ * (tcgen05.mma kind::i8, TMEM accumulators) per (32 frames x 128 beads) tile and recombines them in float64.
+ * Frames holding a non-finite or out-of-range value are computed in float64 by a second kernel, which also
+ * carries the NaN protocol (nan_mode 1: NaN counts as 0, nan_flags as for agf_map_apply).
+ *   workspace   device, agf_map_apply_i8_workspace_bytes(...) bytes (0: shape not supported), 16-byte aligned
+ */
+size_t agf_map_apply_i8_workspace_bytes(int32_t n_sites, int32_t n_ucol, int32_t n_cg, int64_t n_frames);
+int agf_map_apply_i8(const void* points, int in_dtype, int64_t n_frames, int32_t n_sites,
+                     const int32_t* ucol_ptr, const int32_t* ucol_sites, int32_t n_ucol,
+                     const double* umat_t, int32_t n_cg, void* out, int out_dtype, double* sumsq,
+                     int nan_mode, double nan_atol, int32_t* nan_flags, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
 /* Sparse-row form for slice / uniform maps (a few non-zeros per bead): CSR rows
  *   row_ptr device int32 [n_cg + 1], row_sites device int32 [nnz], row_weights device f64 [nnz].
  * Only the referenced sites are read.  Same outputs / NaN semantics as agf_map_apply with
