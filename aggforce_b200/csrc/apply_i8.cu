@@ -19,6 +19,8 @@
 //     i8a_leftover_kernel in float64 with the reference's NaN protocol (map/core.py:219-240), after the GEMM.
 // Error: the dropped products (s + t >= 5) and the two roundings are below 2^-38 of (largest |W'| of the bead)
 // x (column scale) per term -- about 1e-11 of the result for maps without catastrophic cancellation (bar 1e-6).
+#include <stdlib.h>
+
 #include "i8_digits.cuh"
 
 namespace agf {
@@ -422,11 +424,12 @@ static int i8a_run(const float* x, int64_t n_frames, int32_t n_sites, const int3
     AGF_CUDA_TRY(cudaGetLastError());
   }
   const size_t gemm_smem = (size_t)kA_Stages * kA_StageBytes + 128;
-  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_digits_kernel<kApplyLayout>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kT_TileBytes));
+  void (*digits_kernel)(I8tDigitsParams) = i8t_digits_kernel<kApplyLayout>;  // 3 CTAs per SM (2 and 4 measured the same)
+  AGF_CUDA_TRY(cudaFuncSetAttribute(digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kT_TileBytes));
   AGF_CUDA_TRY(cudaFuncSetAttribute(i8a_gemm_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
   const int sms = sm_count();
   int digit_ctas_per_sm = 1;
-  AGF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&digit_ctas_per_sm, i8t_digits_kernel<kApplyLayout>, 256,
+  AGF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&digit_ctas_per_sm, digits_kernel, 256,
                                                              2 * kT_TileBytes));
   if (digit_ctas_per_sm < 1) digit_ctas_per_sm = 1;
   for (int64_t f0 = 0; f0 < n_frames; f0 += L.slab) {
@@ -448,7 +451,7 @@ static int i8a_run(const float* x, int64_t n_frames, int32_t n_sites, const int3
     AGF_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)n_flags * 4, s));
     const int64_t n_items = (int64_t)(n_xb * 16 / kT_PanelCols) * d.n_groups;
     const int64_t want = (int64_t)sms * digit_ctas_per_sm;
-    i8t_digits_kernel<kApplyLayout><<<(int)(n_items < want ? n_items : want), 256, 2 * kT_TileBytes, s>>>(d);
+    digits_kernel<<<(int)(n_items < want ? n_items : want), 256, 2 * kT_TileBytes, s>>>(d);
     AGF_CUDA_TRY(cudaGetLastError());
     i8t_scrub_kernel<kApplyLayout><<<(n_flags + 255) / 256 < sms ? (n_flags + 255) / 256 : sms, 256, 0, s>>>(
         flags, n_flags, d.n_frames, f0, n_xb, xdig, count, leftover);

@@ -340,11 +340,12 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
   }
   // stages, 128 bytes of barriers + TMEM address, four 32 x 16 float64 transposition patches
   const size_t syrk_smem = (size_t)kT_Stages * kT_StageBytes + 128 + 4 * 512 * sizeof(double);
-  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_digits_kernel<kGramLayout>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kT_TileBytes));
+  void (*digits_kernel)(I8tDigitsParams) = i8t_digits_kernel<kGramLayout>;  // 3 CTAs per SM (2 and 4 measured the same)
+  AGF_CUDA_TRY(cudaFuncSetAttribute(digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kT_TileBytes));
   AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
   const int sms = sm_count();
   int digit_ctas_per_sm = 1;
-  AGF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&digit_ctas_per_sm, i8t_digits_kernel<kGramLayout>, 256, 2 * kT_TileBytes));
+  AGF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&digit_ctas_per_sm, digits_kernel, 256, 2 * kT_TileBytes));
   if (digit_ctas_per_sm < 1) digit_ctas_per_sm = 1;
   I8tSyrkParams q;
   memset(&q, 0, sizeof(q));
@@ -381,7 +382,7 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
     AGF_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)n_flags * 4, s));
     const int64_t n_items = (int64_t)((n_xb * 16 + kT_PanelCols - 1) / kT_PanelCols) * d.n_groups;
     const int64_t want = (int64_t)sms * digit_ctas_per_sm;  // all resident at once: equal item ranges = equal work
-    i8t_digits_kernel<kGramLayout><<<(int)(n_items < want ? n_items : want), 256, 2 * kT_TileBytes, s>>>(d);
+    digits_kernel<<<(int)(n_items < want ? n_items : want), 256, 2 * kT_TileBytes, s>>>(d);
     AGF_CUDA_TRY(cudaGetLastError());
     i8t_scrub_kernel<kGramLayout><<<(n_flags + 255) / 256 < sms ? (n_flags + 255) / 256 : sms, 256, 0, s>>>(flags, n_flags, d.n_frames, f0, n_xb,
                                                                                             digits, count, leftover);

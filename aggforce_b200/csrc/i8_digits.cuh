@@ -118,7 +118,7 @@ __device__ __forceinline__ size_t i8t_row_offset(int n_xb, int fb, int d, int s,
 }
 
 template <int LAYOUT>
-__global__ void __launch_bounds__(256) i8t_digits_kernel(const __grid_constant__ I8tDigitsParams p) {
+__global__ void __launch_bounds__(256, 3) i8t_digits_kernel(const __grid_constant__ I8tDigitsParams p) {
   extern __shared__ __align__(16) unsigned char tiles[];  // 2 x [xyz][plane][x-block of the pass][kT_TileXb]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t frame_elems = (int64_t)p.n_sites * 3;
