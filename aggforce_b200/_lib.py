@@ -42,6 +42,8 @@ SIGNATURES = {
                       _dbl, _vp, _vp],
     "agf_gram_feat_ws": [_vp, _vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _dbl,
                          _dbl, _dbl, _vp, _vp, C.c_size_t, _vp],
+    "agf_gram_feat_i8": [_vp, _vp, C.c_int, _i64, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32, _dbl,
+                         _dbl, _dbl, _vp, _vp, C.c_size_t, _vp],
     "agf_symmetrize_batch": [_vp, _i32, _i32, _vp],
     "agf_feat_rows": [_vp, C.c_int, _i32, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _vp, _i32,
                       _dbl, _dbl, _vp, _vp],
@@ -63,6 +65,7 @@ PLAIN = {"agf_version": (C.c_int, []), "agf_peer_buffer_bytes": (C.c_size_t, [_i
          "agf_gram_linear_i8t_workspace_bytes": (C.c_size_t, [_i32, _i32, _i64]),
          "agf_map_apply_i8_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i64]),
          "agf_map_apply_workspace_bytes": (C.c_size_t, [C.c_int, _i32, _i32, _i32, _i32, _i64]),
+         "agf_gram_feat_i8_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i64]),
          "agf_gram_feat_workspace_bytes": (C.c_size_t, [_i32, _i32, _i32, _i32, _i64])}
 
 

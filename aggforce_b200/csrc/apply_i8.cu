@@ -376,7 +376,7 @@ static I8aLayout i8a_layout(int n_ucol, int n_cg, int64_t n_frames) {
   L.n_mb = (n_cg + kA_M - 1) / kA_M;
   const size_t np = (size_t)L.n_kpad, mp = (size_t)L.n_mb * kA_M;
   L.colmax = 0;
-  L.exps = up(np * 8);
+  L.exps = up(np * 8 * kT_MaxSampleGroups);
   L.scales = L.exps + up(np * 4);
   L.pow2 = L.scales + up(np * 8);
   L.rowmax = L.pow2 + up(np * 8);
@@ -397,7 +397,7 @@ static int i8a_run(const float* x, int64_t n_frames, int32_t n_sites, const int3
                    int32_t n_ucol, const double* umat_t, int32_t n_cg, TO* out, double* sumsq, int nan_mode, double nan_atol,
                    int32_t* nan_flags, char* ws, cudaStream_t s) {
   const I8aLayout L = i8a_layout(n_ucol, n_cg, n_frames);
-  unsigned long long* colmax = reinterpret_cast<unsigned long long*>(ws + L.colmax);
+  double* gmax = reinterpret_cast<double*>(ws + L.colmax);  // [sample groups][padded columns]
   int32_t* exps = reinterpret_cast<int32_t*>(ws + L.exps);
   double* scales = reinterpret_cast<double*>(ws + L.scales);
   double* pow2 = reinterpret_cast<double*>(ws + L.pow2);
@@ -412,11 +412,10 @@ static int i8a_run(const float* x, int64_t n_frames, int32_t n_sites, const int3
   AGF_CUDA_TRY(cudaMemsetAsync(ws, 0, L.leftover, s));
   {
     const I8tSamplePlan sp = i8t_sample_plan(n_frames);
-    AGF_CUDA_TRY(cudaMemsetAsync(colmax, 0x7F, (size_t)L.n_kpad * 8, s));
     i8t_sample_kernel<<<dim3((n_ucol + 127) / 128, sp.groups), 128, 0, s>>>(x, n_frames, sp.stride, n_sites, ucol_ptr, ucol_sites,
-                                                                          n_ucol, colmax);
+                                                                          n_ucol, L.n_kpad, gmax);
     AGF_CUDA_TRY(cudaGetLastError());
-    i8t_scale_kernel<<<(L.n_kpad + 255) / 256, 256, 0, s>>>(colmax, n_ucol, L.n_kpad, exps, scales, pow2);
+    i8t_scale_kernel<<<(L.n_kpad + 7) / 8, 256, 0, s>>>(gmax, sp.groups, n_ucol, L.n_kpad, L.n_kpad, exps, scales, pow2);
     AGF_CUDA_TRY(cudaGetLastError());
     i8a_rowmax_kernel<<<dim3((n_cg + 127) / 128, 32), 128, 0, s>>>(umat_t, n_ucol, n_cg, exps, rowmax);
     AGF_CUDA_TRY(cudaGetLastError());

@@ -19,6 +19,7 @@
 // handful of frames) and agf_feat_apply (application of the fitted map, featlinearmap.py:
 // 512-520 + map/core.py:428-430, without materialising per-frame weights).
 #include "common.cuh"
+#include "i8_digits.cuh"
 #include "panel.cuh"
 
 namespace agf {
@@ -420,6 +421,294 @@ __global__ void __launch_bounds__(256) feat_apply_kernel(const FeatParams p, con
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Featurised Gram on the Blackwell tensor cores (agf_gram_feat_i8): the regression rows v (one set of n_feat
+// columns per bead) go through the same int8 digit planes as the linear Gram (i8_digits.cuh, gram_i8t.cu) and the
+// tiled SYRK runs batched over the beads.  feat_digits_kernel evaluates the rows exactly like feat_pack_kernel
+// (float64, per-frame group records in shared memory) and either records the column maxima of a sample of frame
+// groups (SAMPLE) or writes the digits.
+struct FeatDigits {
+  int64_t n_frames;       // frames of the slab (digits) or of the whole call (sample)
+  int64_t group_stride;   // SAMPLE: frame groups between consecutive sampled groups
+  int32_t n_xb;           // 16-column blocks per bead
+  const double* scales;   // [n_cg][n_xb * 16]
+  unsigned char* digits;  // bead-major buffers, bead_stride bytes apart
+  int64_t bead_stride;
+  int32_t* flags;         // [frames of the slab, rounded up to 32]
+  double* gmax;           // SAMPLE: [sample group][n_cg * n_xb * 16]
+};
+
+template <typename T, bool SAMPLE>
+__global__ void __launch_bounds__(256) feat_digits_kernel(const __grid_constant__ FeatParams p, const __grid_constant__ FeatDigits q) {
+  extern __shared__ __align__(16) unsigned char fd_smem[];
+  __shared__ double bead_pos[kPanelKF][3];
+  __shared__ unsigned long long s_max[kT_PanelCols];
+  unsigned char* tiles = fd_smem;                                             // 2 staging tiles (digits only)
+  double* s_grp = reinterpret_cast<double*>(fd_smem + (SAMPLE ? 0 : 2 * kT_TileBytes));  // [8][G][8]: f[3], dist, m*u[3], pad
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bead = blockIdx.y;
+  const int64_t fg = SAMPLE ? (int64_t)blockIdx.x * q.group_stride : (int64_t)blockIdx.x;
+  const int64_t t0 = fg * kT_ItemFrames;
+  const int nf = (int)max((int64_t)0, min((int64_t)kT_ItemFrames, q.n_frames - t0));
+  const T* coords = reinterpret_cast<const T*>(p.coords);
+  const T* forces = reinterpret_cast<const T*>(p.forces);
+  const int64_t fstride = (int64_t)p.n_sites * 3;
+  const int n_pad = q.n_xb * 16;
+  bead_positions<T>(p, coords, t0, nf, bead, bead_pos);
+  __syncthreads();
+  const int G = p.n_groups, nb = p.nb;
+  for (int item = threadIdx.x; item < nf * G; item += blockDim.x) {
+    const int t = item / G, g = item - t * G;
+    double f[3], m;
+    group_sum<T>(forces + (t0 + t) * fstride, p.grp_ptr, p.grp_sites, g, f, m);
+    double* rec = s_grp + (size_t)item * 8;
+    rec[0] = f[0];
+    rec[1] = f[1];
+    rec[2] = f[2];
+    if (g < p.n_channels) {
+      double pos[3];
+      group_sum<T>(coords + (t0 + t) * fstride, p.grp_ptr, p.grp_sites, g, pos, m);
+      const double dx = pos[0] / m - bead_pos[t][0], dy = pos[1] / m - bead_pos[t][1],
+                   dz = pos[2] / m - bead_pos[t][2];
+      const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+      rec[3] = dist;
+      rec[4] = m * (dx / dist);  // NaN at dist == 0
+      rec[5] = m * (dy / dist);
+      rec[6] = m * (dz / dist);
+    }
+  }
+  __syncthreads();
+  const bool live = warp < nf;  // warp = frame of the group
+  const int fb = (int)(fg >> 2), kg = (int)(fg & 3);
+  int buf = 0;
+  for (int pass = 0; pass < n_pad / kT_PanelCols; ++pass, buf ^= 1) {
+    if (SAMPLE) {
+      if (threadIdx.x < kT_PanelCols) s_max[threadIdx.x] = 0ull;
+      __syncthreads();
+    }
+    uint32_t lo_w[3][4], hi_w[3][4];
+    uint32_t range = 0;
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int col = pass * kT_PanelCols + 4 * lane + cc;
+      double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+      if (live && col < p.n_feat) {
+        if (col < G) {
+          const double* rec = s_grp + (size_t)(warp * G + col) * 8;
+          v0 = rec[0];
+          v1 = rec[1];
+          v2 = rec[2];
+        } else {
+          const int ch = (col - G) / nb, k = (col - G) - ch * nb;
+          const double* rec = s_grp + (size_t)(warp * G + ch) * 8;
+          double gk, gp;
+          clipped_gauss(rec[3], __ldg(p.centers + k), p.inv_width, p.clip, p.ln_inv_clip, gk, gp);
+          const double c = p.kbt * gp;
+          v0 = gk * rec[0] + c * rec[4];
+          v1 = gk * rec[1] + c * rec[5];
+          v2 = gk * rec[2] + c * rec[6];
+        }
+      }
+      if (SAMPLE) {
+        const double m = fmax(fabs(v0), fmax(fabs(v1), fabs(v2)));
+        if (m > 0.0 && m < 1.0e300) atomicMax(&s_max[4 * lane + cc], (unsigned long long)__double_as_longlong(m));
+      } else {
+        const double sc = (live && col < p.n_feat) ? __ldg(q.scales + (size_t)bead * n_pad + col) : 0.0;
+        const double t0d = fma(v0, sc, kI8Magic), t1d = fma(v1, sc, kI8Magic), t2d = fma(v2, sc, kI8Magic);
+        lo_w[0][cc] = (uint32_t)__double2loint(t0d);
+        hi_w[0][cc] = (uint32_t)__double2hiint(t0d);
+        lo_w[1][cc] = (uint32_t)__double2loint(t1d);
+        hi_w[1][cc] = (uint32_t)__double2hiint(t1d);
+        lo_w[2][cc] = (uint32_t)__double2loint(t2d);
+        hi_w[2][cc] = (uint32_t)__double2hiint(t2d);
+        range |= (hi_w[0][cc] ^ kI8HiExpect) | (hi_w[1][cc] ^ kI8HiExpect) | (hi_w[2][cc] ^ kI8HiExpect);
+      }
+    }
+    if (SAMPLE) {
+      __syncthreads();
+      if (threadIdx.x < kT_PanelCols)
+        q.gmax[(size_t)blockIdx.x * p.n_cg * n_pad + (size_t)bead * n_pad + pass * kT_PanelCols + threadIdx.x] =
+            __longlong_as_double((long long)s_max[threadIdx.x]);
+      __syncthreads();
+      continue;
+    }
+    if (__any_sync(0xffffffffu, (range & 0xFFFFFF00u) != 0) && lane == 0) q.flags[t0 + warp] = 1;
+    const uint32_t tbase = smem_u32(tiles) + (uint32_t)buf * kT_TileBytes;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const uint32_t dst = tbase + (uint32_t)((d * kT_Slices) * (kT_PanelCols / 16) + (lane >> 2)) * kT_TileXb +
+                           (uint32_t)(warp * 16 + (lane & 3) * 4);
+      constexpr uint32_t ps = (kT_PanelCols / 16) * kT_TileXb;  // plane stride inside the tile
+      sts_u32(dst + 0 * ps, gather_bytes(hi_w[d][0], hi_w[d][1], hi_w[d][2], hi_w[d][3], 0) ^ 0x80808080u);
+      sts_u32(dst + 1 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 3) ^ 0x80808080u);
+      sts_u32(dst + 2 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 2) ^ 0x80808080u);
+      sts_u32(dst + 3 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 1) ^ 0x80808080u);
+      sts_u32(dst + 4 * ps, gather_bytes(lo_w[d][0], lo_w[d][1], lo_w[d][2], lo_w[d][3], 0) ^ 0x80808080u);
+    }
+    __syncthreads();  // also: everyone has left the copy-out of the pass before the previous one (same buffer)
+    const unsigned char* tile = tiles + (size_t)buf * kT_TileBytes;
+    unsigned char* out = q.digits + (size_t)bead * q.bead_stride;
+    for (int idx = threadIdx.x; idx < 3 * kT_Slices * (kT_PanelCols / 16) * kT_ItemFrames; idx += blockDim.x) {
+      const int qq = idx & (kT_ItemFrames - 1);
+      const int xb = (idx >> 3) & (kT_PanelCols / 16 - 1), ds = idx >> 6;
+      const int gxb = pass * (kT_PanelCols / 16) + xb;
+      const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)(ds * (kT_PanelCols / 16) + xb) * kT_TileXb + qq * 16);
+      const int d = ds / kT_Slices, s = ds - d * kT_Slices;
+      *reinterpret_cast<uint4*>(out + i8t_row_offset<kGramLayout>(q.n_xb, fb, d, s, gxb, kg) + qq * 16) = v;
+    }
+  }
+}
+
+// Column scales of the featurised rows.  id columns (group forces): the robust upper quartile of the sampled
+// group maxima, as for the linear Gram.  gb columns  v = g_k F + kbt m g_k' u  are heavy-tailed (a distance
+// wandering through the flank of a Gaussian bin changes g_k by orders of magnitude), so a quantile would send most
+// frames to the float64 pass: they take the sample MAXIMUM with 64-128x headroom instead, capped by the a-priori
+// bound  |v| <= |F| + kbt m max|g'|  (|g_k| < 1, max|g'| = sqrt(2/e) / width) evaluated at the id column's range --
+// a frame whose group forces are in range is then in range in every gb column, and a stray huge force in the
+// sample cannot coarsen a gb column beyond that bound.  Columns that barely leave the clip in the sample (maximum
+// below 2^-19 of the bound) get a floor of 2^-12 of the bound: their absolute error stays 2^-51 of the bound, below
+// the rounding of the live columns, and without the floor any frame that leaves the clip a little further (g - clip
+// starts from zero there, the ratio to the sampled maximum is unbounded) would overflow them.
+__global__ void feat_scale_kernel(const double* __restrict__ gmax, int n_groups, FeatParams p, int n_pad,
+                                  int32_t* __restrict__ exps, double* __restrict__ scales, double* __restrict__ pow2) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp = column
+  const int lane = threadIdx.x & 31;
+  const int cols = p.n_cg * n_pad;
+  if (x >= cols) return;
+  const int bead = x / n_pad, col = x - bead * n_pad;
+  int e = 0;
+  const bool live = col < p.n_feat;
+  if (live) {
+    const int G = p.n_groups;
+    const int g = col < G ? col : (col - G) / p.nb;
+    const int e_id = column_exponent_robust(i8t_group_quartile(gmax, n_groups, cols, bead * n_pad + g));
+    if (col < G) {
+      e = e_id;
+    } else {
+      const double m = (double)(__ldg(p.grp_ptr + g + 1) - __ldg(p.grp_ptr + g));
+      const double bound = ldexp(1.0, e_id - 1) + p.kbt * m * 0.8577638849607068 * p.inv_width;
+      const int e_cap = ilogb(bound) + 2;
+      double best = 0.0;
+      for (int sg = lane; sg < n_groups; sg += 32) best = fmax(best, gmax[(size_t)sg * cols + x]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+      e = (best > 0.0 && best < 1.0e300) ? max(min(ilogb(best) + 7, e_cap), e_cap - 12) : e_cap;
+      e = e < -900 ? -900 : (e > 900 ? 900 : e);
+    }
+  }
+  if (lane != 0) return;
+  exps[x] = e;
+  scales[x] = live ? ldexp(1.0, 39 - e) : 0.0;
+  pow2[x] = ldexp(1.0, e - 7);
+}
+
+// Flagged frames of the featurised fit: clear their rows in every bead's planes, list the ones that exist.
+__global__ void __launch_bounds__(256) feat_scrub_kernel(const int32_t* __restrict__ flags, int n_flags, int64_t n_frames,
+                                                         int64_t frame0, int n_xb, int n_cg, unsigned char* __restrict__ digits,
+                                                         int64_t bead_stride, int32_t* __restrict__ leftover_count,
+                                                         int32_t* __restrict__ leftover) {
+  const int lane = threadIdx.x & 31;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; base < n_flags; base += n_warps * 32) {
+    const int mine = base + lane < n_flags ? flags[base + lane] : 0;
+    uint32_t mask = __ballot_sync(0xffffffffu, mine != 0);
+    while (mask) {
+      const int f = base + __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int fb = f / kT_ChunkFrames, r = f - fb * kT_ChunkFrames;
+      for (int idx = lane; idx < n_cg * 3 * kT_Slices * n_xb; idx += 32) {
+        const int gxb = idx % n_xb, rest = idx / n_xb;
+        const int ds = rest % (3 * kT_Slices), bead = rest / (3 * kT_Slices);
+        const int d = ds / kT_Slices, s = ds - d * kT_Slices;
+        unsigned char* dst = digits + (size_t)bead * bead_stride + i8t_row_offset<kGramLayout>(n_xb, fb, d, s, gxb, r >> 3) + (r & 7) * 16;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+      }
+      if (lane == 0 && f < n_frames) {
+        const int slot = atomicAdd(leftover_count, 1);
+        leftover[slot] = (int32_t)(frame0 + f);
+      }
+    }
+  }
+}
+
+// Frames the fixed-point pass declined, in float64: CTA = (listed frame, bead), rank-3 update of the upper triangle.
+template <typename T>
+__global__ void __launch_bounds__(256) feat_leftover_kernel(const __grid_constant__ FeatParams p, const int32_t* __restrict__ count,
+                                                            const int32_t* __restrict__ frames) {
+  extern __shared__ double fl_v[];  // [3][n_feat]
+  __shared__ double bead_pos[kPanelKF][3];
+  const T* coords = reinterpret_cast<const T*>(p.coords);
+  const T* forces = reinterpret_cast<const T*>(p.forces);
+  const int64_t fstride = (int64_t)p.n_sites * 3;
+  const int G = p.n_groups, nb = p.nb, n = *count;
+  for (int item = blockIdx.x; item < n * p.n_cg; item += gridDim.x) {
+    const int64_t t = frames[item / p.n_cg];
+    const int bead = item % p.n_cg;
+    __syncthreads();
+    bead_positions<T>(p, coords, t, 1, bead, bead_pos);
+    __syncthreads();
+    for (int col = threadIdx.x; col < p.n_feat; col += blockDim.x) {
+      const int g = col < G ? col : (col - G) / nb;
+      double f[3], m, v0, v1, v2;
+      group_sum<T>(forces + t * fstride, p.grp_ptr, p.grp_sites, g, f, m);
+      if (col < G) {
+        v0 = f[0];
+        v1 = f[1];
+        v2 = f[2];
+      } else {
+        double pos[3];
+        group_sum<T>(coords + t * fstride, p.grp_ptr, p.grp_sites, g, pos, m);
+        const double dx = pos[0] / m - bead_pos[0][0], dy = pos[1] / m - bead_pos[0][1], dz = pos[2] / m - bead_pos[0][2];
+        const double dist = sqrt(dx * dx + dy * dy + dz * dz);
+        double gk, gp;
+        clipped_gauss(dist, __ldg(p.centers + (col - G - g * nb)), p.inv_width, p.clip, p.ln_inv_clip, gk, gp);
+        const double c = p.kbt * gp * m;
+        v0 = gk * f[0] + c * (dx / dist);
+        v1 = gk * f[1] + c * (dy / dist);
+        v2 = gk * f[2] + c * (dz / dist);
+      }
+      fl_v[col] = v0;
+      fl_v[p.n_feat + col] = v1;
+      fl_v[2 * p.n_feat + col] = v2;
+    }
+    __syncthreads();
+    double* gram = p.gram + (int64_t)bead * p.n_feat * p.n_feat;
+    for (int64_t e = threadIdx.x; e < (int64_t)p.n_feat * p.n_feat; e += blockDim.x) {
+      const int x = (int)(e / p.n_feat), y = (int)(e - (int64_t)x * p.n_feat);
+      if (y >= x)
+        atomicAdd(gram + e, fl_v[x] * fl_v[y] + fl_v[p.n_feat + x] * fl_v[p.n_feat + y] +
+                                fl_v[2 * p.n_feat + x] * fl_v[2 * p.n_feat + y]);
+    }
+  }
+}
+
+struct FeatI8Layout {
+  size_t gmax, exps, scales, pow2, count, leftover, flags, digits, total;
+  int64_t slab, bead_stride;
+  int n_pad;
+};
+
+static FeatI8Layout feat_i8_layout(int n_feat, int n_cg, int64_t n_frames) {
+  FeatI8Layout L;
+  auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+  L.n_pad = i8t_pad(n_feat);
+  const size_t cols = (size_t)n_cg * L.n_pad;
+  L.gmax = 0;
+  L.exps = up(cols * 8 * kT_MaxSampleGroups);
+  L.scales = L.exps + up(cols * 4);
+  L.pow2 = L.scales + up(cols * 8);
+  L.count = L.pow2 + up(cols * 8);
+  L.leftover = L.count + 1024;
+  const int64_t rounded = (n_frames + kT_ChunkFrames - 1) / kT_ChunkFrames * kT_ChunkFrames;
+  L.slab = rounded < kT_SlabFrames ? rounded : kT_SlabFrames;
+  L.flags = L.leftover + up((size_t)n_frames * 4);
+  L.digits = L.flags + up((size_t)L.slab * 4);
+  L.bead_stride = (int64_t)(L.slab / kT_ChunkFrames) * 3 * kT_Slices * (L.n_pad / 16) * kT_XbBytes;
+  L.total = L.digits + (size_t)n_cg * L.bead_stride;
+  return L;
+}
+
 static int fill_params(FeatParams& p, const void* coords, const void* forces, int64_t n_frames, int32_t n_sites,
                        const int32_t* grp_ptr, const int32_t* grp_sites, int32_t n_groups, int32_t n_channels,
                        const int32_t* bead_ptr, const int32_t* bead_sites, const double* bead_w, int32_t n_cg,
@@ -549,6 +838,118 @@ extern "C" int agf_gram_feat_ws(const void* coords, const void* forces, int dtyp
     rc = launch_panel_syrk(reinterpret_cast<const double*>(workspace), chunks, p.n_feat, n_cg, gram, s);
     if (rc) return rc;
   }
+  return AGF_OK;
+}
+
+extern "C" size_t agf_gram_feat_i8_workspace_bytes(int32_t n_groups, int32_t n_channels, int32_t nb, int32_t n_cg,
+                                                   int64_t n_frames) {
+  using namespace agf;
+  if (n_groups <= 0 || n_channels < 0 || nb <= 0 || n_cg <= 0 || n_frames <= 0 || n_frames >= ((int64_t)1 << 31)) return 0;
+  const int64_t n_feat = (int64_t)n_groups + (int64_t)nb * n_channels;
+  if (n_feat > 8192 || (size_t)kPanelKF * n_groups * 64 + 2 * kT_TileBytes > (size_t)200 * 1024) return 0;
+  return feat_i8_layout((int)n_feat, n_cg, n_frames).total;
+}
+
+extern "C" int agf_gram_feat_i8(const void* coords, const void* forces, int dtype, int64_t n_frames, int32_t n_sites,
+                                const int32_t* grp_ptr, const int32_t* grp_sites, int32_t n_groups, int32_t n_channels,
+                                const int32_t* bead_ptr, const int32_t* bead_sites, const double* bead_w, int32_t n_cg,
+                                const double* centers, int32_t nb, double width, double clip, double kbt, double* gram,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace agf;
+  FeatParams p;
+  int rc = fill_params(p, coords, forces, n_frames, n_sites, grp_ptr, grp_sites, n_groups, n_channels, bead_ptr,
+                       bead_sites, bead_w, n_cg, centers, nb, width, clip, kbt);
+  if (rc) return rc;
+  AGF_REQUIRE(forces && gram && workspace, "agf_gram_feat_i8: null pointer");
+  AGF_REQUIRE(dtype == AGF_F32 || dtype == AGF_F64, "agf_gram_feat_i8: bad dtype");
+  const size_t need = agf_gram_feat_i8_workspace_bytes(n_groups, n_channels, nb, n_cg, n_frames);
+  AGF_REQUIRE(need != 0 && workspace_bytes >= need, "agf_gram_feat_i8: shape not supported or workspace too small");
+  AGF_REQUIRE((reinterpret_cast<uintptr_t>(workspace) % 16) == 0, "agf_gram_feat_i8: workspace must be 16-byte aligned");
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  p.gram = gram;
+  const FeatI8Layout L = feat_i8_layout(p.n_feat, n_cg, n_frames);
+  char* ws = reinterpret_cast<char*>(workspace);
+  double* gmax = reinterpret_cast<double*>(ws + L.gmax);
+  int32_t* exps = reinterpret_cast<int32_t*>(ws + L.exps);
+  double* scales = reinterpret_cast<double*>(ws + L.scales);
+  double* pow2 = reinterpret_cast<double*>(ws + L.pow2);
+  int32_t* count = reinterpret_cast<int32_t*>(ws + L.count);
+  int32_t* leftover = reinterpret_cast<int32_t*>(ws + L.leftover);
+  int32_t* flags = reinterpret_cast<int32_t*>(ws + L.flags);
+  unsigned char* digits = reinterpret_cast<unsigned char*>(ws + L.digits);
+  const int n_xb = L.n_pad / 16, cols = n_cg * L.n_pad;
+  const size_t elem = dtype == AGF_F32 ? 4 : 8;
+  const size_t frame_bytes = (size_t)n_sites * 3 * elem;
+  const size_t grp_smem = (size_t)kPanelKF * n_groups * 8 * sizeof(double);
+  AGF_CUDA_TRY(cudaMemsetAsync(ws, 0, L.leftover, s));
+  FeatDigits q;
+  memset(&q, 0, sizeof(q));
+  q.n_xb = n_xb;
+  q.scales = scales;
+  q.digits = digits;
+  q.bead_stride = L.bead_stride;
+  q.flags = flags;
+  q.gmax = gmax;
+#define AGF_FEAT_DIGITS(SAMPLE, grid, smem)                                                                       \
+  do {                                                                                                            \
+    if (dtype == AGF_F32) {                                                                                       \
+      AGF_CUDA_TRY(cudaFuncSetAttribute(feat_digits_kernel<float, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+      feat_digits_kernel<float, SAMPLE><<<grid, 256, smem, s>>>(p, q);                                          \
+    } else {                                                                                                      \
+      AGF_CUDA_TRY(cudaFuncSetAttribute(feat_digits_kernel<double, SAMPLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smem))); \
+      feat_digits_kernel<double, SAMPLE><<<grid, 256, smem, s>>>(p, q);                                         \
+    }                                                                                                             \
+    AGF_CUDA_TRY(cudaGetLastError());                                                                             \
+  } while (0)
+  {  // column scales: up to 64 groups of 8 frames spread over the call's frames
+    const int64_t all_groups = (n_frames + kT_ItemFrames - 1) / kT_ItemFrames;
+    const int n_sg = (int)(all_groups < kT_MaxSampleGroups ? all_groups : kT_MaxSampleGroups);
+    q.n_frames = n_frames;
+    q.group_stride = all_groups / n_sg;
+    AGF_FEAT_DIGITS(true, dim3(n_sg, n_cg), grp_smem);
+    feat_scale_kernel<<<(cols + 7) / 8, 256, 0, s>>>(gmax, n_sg, p, L.n_pad, exps, scales, pow2);
+    AGF_CUDA_TRY(cudaGetLastError());
+  }
+  const int sms = sm_count();
+  for (int64_t f0 = 0; f0 < n_frames; f0 += L.slab) {
+    const int64_t nf = n_frames - f0 < L.slab ? n_frames - f0 : L.slab;
+    const int n_fb = (int)((nf + kT_ChunkFrames - 1) / kT_ChunkFrames);
+    const int n_flags = n_fb * kT_ChunkFrames;
+    p.coords = reinterpret_cast<const char*>(coords) + (size_t)f0 * frame_bytes;
+    p.forces = reinterpret_cast<const char*>(forces) + (size_t)f0 * frame_bytes;
+    p.n_frames = nf;
+    q.n_frames = nf;
+    AGF_CUDA_TRY(cudaMemsetAsync(flags, 0, (size_t)n_flags * 4, s));
+    AGF_FEAT_DIGITS(false, dim3(n_fb * (kT_ChunkFrames / kT_ItemFrames), n_cg), grp_smem + 2 * kT_TileBytes);
+    feat_scrub_kernel<<<(n_flags + 255) / 256 < sms ? (n_flags + 255) / 256 : sms, 256, 0, s>>>(
+        flags, n_flags, nf, f0, n_xb, n_cg, digits, L.bead_stride, count, leftover);
+    AGF_CUDA_TRY(cudaGetLastError());
+    I8tSyrkLaunch l;
+    l.digits = digits;
+    l.n_chunks = 3 * n_fb;
+    l.n_red = p.n_feat;
+    l.slice_chunks = 64;  // 10 beads x 37 tiles share a slice: keep the slice of all beads inside L2
+    l.n_batch = n_cg;
+    l.digits_batch_stride = L.bead_stride;
+    l.pow2 = pow2;
+    l.gram = gram;
+    l.gram_batch_stride = (int64_t)p.n_feat * p.n_feat;
+    rc = i8t_launch_syrk(l, s);
+    if (rc) return rc;
+  }
+#undef AGF_FEAT_DIGITS
+  p.coords = coords;
+  p.forces = forces;
+  p.n_frames = n_frames;
+  const size_t lsmem = (size_t)3 * p.n_feat * sizeof(double);
+  if (dtype == AGF_F32) {
+    AGF_CUDA_TRY(cudaFuncSetAttribute(feat_leftover_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+    feat_leftover_kernel<float><<<sms, 256, lsmem, s>>>(p, count, leftover);
+  } else {
+    AGF_CUDA_TRY(cudaFuncSetAttribute(feat_leftover_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+    feat_leftover_kernel<double><<<sms, 256, lsmem, s>>>(p, count, leftover);
+  }
+  AGF_CUDA_TRY(cudaGetLastError());
   return AGF_OK;
 }
 

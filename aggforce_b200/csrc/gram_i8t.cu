@@ -38,7 +38,7 @@ constexpr int kT_SliceChunks = 256;     // 8 192 contraction rows per unit (int3
 constexpr int kT_SyrkThreads = 192;     // load warp, MMA warp, four epilogue warps
 constexpr int kT_MaxRed = 8192;
 
-__host__ __device__ inline int i8t_pad(int n_red) {
+int i8t_pad(int n_red) {
   const int a = (n_red + kT_M - 1) / kT_M * kT_M, b = (n_red + kT_N - 1) / kT_N * kT_N;
   return a > b ? a : b;
 }
@@ -48,6 +48,9 @@ struct I8tSyrkParams {
   const unsigned char* digits;
   int32_t n_chunks;  // chunks of the slab (3 per 32 frames)
   int32_t n_red, n_xb, n_mb, n_nb, n_tiles, n_slices, slice_chunks;
+  int32_t n_batch;              // independent Grams over the same frames (beads of a featurised fit), 1 otherwise
+  int64_t digits_batch_stride;  // bytes between the digit buffers of consecutive batch members
+  int64_t gram_batch_stride;    // doubles between their Grams; pow2 is [n_batch][n_xb * 16]
   const double* pow2;  // [n_pad] 2^(E_x - 7)
   double* gram;
 };
@@ -66,6 +69,15 @@ __device__ __forceinline__ void i8t_tile(int t, int n_nb, int& mi, int& nj) {
     t -= cnt;
     ++mi;
   }
+}
+
+// unit -> (slice, batch member, tile): slice-major, so that the CTAs running at one time share a slice of the digits
+__device__ __forceinline__ void i8t_unit(const I8tSyrkParams& p, int u, int& ks, int& bm, int& mi, int& nj) {
+  const int per_slice = p.n_tiles * p.n_batch;
+  ks = u / per_slice;
+  const int r = u - ks * per_slice;
+  bm = r / p.n_tiles;
+  i8t_tile(r - bm * p.n_tiles, p.n_nb, mi, nj);
 }
 
 __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __grid_constant__ I8tSyrkParams p) {
@@ -95,7 +107,7 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
-  const int n_units = p.n_slices * p.n_tiles;
+  const int n_units = p.n_slices * p.n_tiles * p.n_batch;
 
   if (warp == 0) {
     // ------------------------------------------------ load warp: one thread, ten bulk copies per chunk
@@ -104,13 +116,13 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
       uint32_t phase = 0;
       const size_t plane_bytes = (size_t)p.n_xb * kT_XbBytes;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int ks = u / p.n_tiles;
-        int mi, nj;
-        i8t_tile(u - ks * p.n_tiles, p.n_nb, mi, nj);
+        int ks, bm, mi, nj;
+        i8t_unit(p, u, ks, bm, mi, nj);
         const int c0 = ks * p.slice_chunks;
         const int c1 = c0 + p.slice_chunks < p.n_chunks ? c0 + p.slice_chunks : p.n_chunks;
-        const unsigned char* a_src = p.digits + (size_t)c0 * kT_Slices * plane_bytes + (size_t)mi * (kT_M / 16) * kT_XbBytes;
-        const unsigned char* b_src = p.digits + (size_t)c0 * kT_Slices * plane_bytes + (size_t)nj * (kT_N / 16) * kT_XbBytes;
+        const unsigned char* base = p.digits + (size_t)bm * p.digits_batch_stride + (size_t)c0 * kT_Slices * plane_bytes;
+        const unsigned char* a_src = base + (size_t)mi * (kT_M / 16) * kT_XbBytes;
+        const unsigned char* b_src = base + (size_t)nj * (kT_N / 16) * kT_XbBytes;
         for (int c = c0; c < c1; ++c) {
           mbar_wait(&empty[stage], phase ^ 1u);
           unsigned char* dst = stages + (size_t)stage * kT_StageBytes;
@@ -137,7 +149,7 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
       const uint32_t sbase = smem_u32(stages);
       bool first_unit = true;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-        const int ks = u / p.n_tiles;
+        const int ks = u / (p.n_tiles * p.n_batch);
         const int c0 = ks * p.slice_chunks;
         const int c1 = c0 + p.slice_chunks < p.n_chunks ? c0 + p.slice_chunks : p.n_chunks;
         if (!first_unit) {  // the epilogue warps have drained the accumulators of the previous unit
@@ -187,10 +199,11 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
     double* patch = reinterpret_cast<double*>(smem + (size_t)kT_Stages * kT_StageBytes + 128) + quarter * 512;
     uint32_t acc_phase = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-      const int ks = u / p.n_tiles;
-      int mi, nj;
-      i8t_tile(u - ks * p.n_tiles, p.n_nb, mi, nj);
-      const double px = __ldg(p.pow2 + mi * kT_M + quarter * 32 + lane);  // row < n_pad always
+      int ks, bm, mi, nj;
+      i8t_unit(p, u, ks, bm, mi, nj);
+      const double* pow2 = p.pow2 + (size_t)bm * p.n_xb * 16;
+      double* gram = p.gram + (int64_t)bm * p.gram_batch_stride;
+      const double px = __ldg(pow2 + mi * kT_M + quarter * 32 + lane);  // row < n_pad always
       mbar_wait(acc_full, acc_phase);
       acc_phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -224,7 +237,7 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
         // bank conflicts either way), then two rows x 16 columns per instruction = 8 sectors.
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) patch[lane * 16 + (i ^ (lane & 15))] = g[i] * px * __ldg(p.pow2 + y0 + i);
+        for (int i = 0; i < 16; ++i) patch[lane * 16 + (i ^ (lane & 15))] = g[i] * px * __ldg(pow2 + y0 + i);
         __syncwarp();
         const int c = lane & 15, y = y0 + c;
 #pragma unroll
@@ -232,7 +245,7 @@ __global__ void __launch_bounds__(kT_SyrkThreads, 1) i8t_syrk_kernel(const __gri
           const int r = 2 * k + (lane >> 4);
           const int xr = mi * kT_M + quarter * 32 + r;
           if (y >= xr && y < p.n_red && xr < p.n_red)
-            atomicAdd(p.gram + (int64_t)xr * p.n_red + y, patch[r * 16 + (c ^ (r & 15))]);
+            atomicAdd(gram + (int64_t)xr * p.n_red + y, patch[r * 16 + (c ^ (r & 15))]);
         }
       }
     }
@@ -273,6 +286,39 @@ __global__ void __launch_bounds__(256) i8t_leftover_kernel(const float* __restri
   }
 }
 
+int i8t_launch_syrk(const I8tSyrkLaunch& l, cudaStream_t s) {
+  // stages, 128 bytes of barriers + TMEM address, four 32 x 16 float64 transposition patches
+  const size_t smem = (size_t)kT_Stages * kT_StageBytes + 128 + 4 * 512 * sizeof(double);
+  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  I8tSyrkParams q;
+  memset(&q, 0, sizeof(q));
+  q.digits = l.digits;
+  q.n_chunks = l.n_chunks;
+  q.n_red = l.n_red;
+  q.n_xb = i8t_pad(l.n_red) / 16;
+  q.n_mb = (l.n_red + kT_M - 1) / kT_M;
+  q.n_nb = (l.n_red + kT_N - 1) / kT_N;
+  for (int mi = 0; mi < q.n_mb; ++mi) q.n_tiles += q.n_nb - (kT_M * mi) / kT_N;
+  q.n_batch = l.n_batch;
+  q.digits_batch_stride = l.digits_batch_stride;
+  q.gram_batch_stride = l.gram_batch_stride;
+  q.pow2 = l.pow2;
+  q.gram = l.gram;
+  q.slice_chunks = l.slice_chunks >= 1 && l.slice_chunks <= 768 ? l.slice_chunks : kT_SliceChunks;
+  if (const char* e = getenv("AGF_I8T_SLICE_CHUNKS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= 768) q.slice_chunks = v;  // 768 chunks = 24 576 rows: the int32 accumulators' limit
+  }
+  q.n_slices = (q.n_chunks + q.slice_chunks - 1) / q.slice_chunks;
+  const int64_t units = (int64_t)q.n_slices * q.n_tiles * q.n_batch;
+  if (units == 0) return AGF_OK;
+  AGF_REQUIRE(units < ((int64_t)1 << 31), "tiled Gram: too many work units");
+  const int sms = sm_count();
+  i8t_syrk_kernel<<<(int)(units < sms ? units : sms), kT_SyrkThreads, smem, s>>>(q);
+  AGF_CUDA_TRY(cudaGetLastError());
+  return AGF_OK;
+}
+
 struct I8tLayout {
   size_t colmax, exps, scales, pow2, count, leftover, flags, digits, total;
   int64_t slab;
@@ -283,7 +329,7 @@ static I8tLayout i8t_layout(int n_red, int64_t n_frames) {
   const size_t n_pad = (size_t)i8t_pad(n_red);
   auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
   L.colmax = 0;
-  L.exps = up(n_pad * 8);
+  L.exps = up(n_pad * 8 * kT_MaxSampleGroups);
   L.scales = L.exps + up(n_pad * 4);
   L.pow2 = L.scales + up(n_pad * 8);
   L.count = L.pow2 + up(n_pad * 8);
@@ -318,7 +364,7 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const I8tLayout L = i8t_layout(n_red, n_frames);
   char* ws = reinterpret_cast<char*>(workspace);
-  unsigned long long* colmax = reinterpret_cast<unsigned long long*>(ws + L.colmax);
+  double* gmax = reinterpret_cast<double*>(ws + L.colmax);  // [sample groups][padded columns]
   int32_t* exps = reinterpret_cast<int32_t*>(ws + L.exps);
   double* scales = reinterpret_cast<double*>(ws + L.scales);
   double* pow2 = reinterpret_cast<double*>(ws + L.pow2);
@@ -331,38 +377,18 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
   AGF_CUDA_TRY(cudaMemsetAsync(ws, 0, L.leftover, s));
   {
     const I8tSamplePlan sp = i8t_sample_plan(n_frames);
-    AGF_CUDA_TRY(cudaMemsetAsync(colmax, 0x7F, (size_t)n_pad * 8, s));
     i8t_sample_kernel<<<dim3((n_red + 127) / 128, sp.groups), 128, 0, s>>>(f, n_frames, sp.stride, n_sites, col_ptr, col_sites,
-                                                                          n_red, colmax);
+                                                                          n_red, n_pad, gmax);
     AGF_CUDA_TRY(cudaGetLastError());
-    i8t_scale_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(colmax, n_red, n_pad, exps, scales, pow2);
+    i8t_scale_kernel<<<(n_pad + 7) / 8, 256, 0, s>>>(gmax, sp.groups, n_red, n_pad, n_pad, exps, scales, pow2);
     AGF_CUDA_TRY(cudaGetLastError());
   }
-  // stages, 128 bytes of barriers + TMEM address, four 32 x 16 float64 transposition patches
-  const size_t syrk_smem = (size_t)kT_Stages * kT_StageBytes + 128 + 4 * 512 * sizeof(double);
   void (*digits_kernel)(I8tDigitsParams) = i8t_digits_kernel<kGramLayout>;  // 3 CTAs per SM (2 and 4 measured the same)
   AGF_CUDA_TRY(cudaFuncSetAttribute(digits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * kT_TileBytes));
-  AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)syrk_smem));
   const int sms = sm_count();
   int digit_ctas_per_sm = 1;
   AGF_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&digit_ctas_per_sm, digits_kernel, 256, 2 * kT_TileBytes));
   if (digit_ctas_per_sm < 1) digit_ctas_per_sm = 1;
-  I8tSyrkParams q;
-  memset(&q, 0, sizeof(q));
-  q.digits = digits;
-  q.n_red = n_red;
-  q.n_xb = n_xb;
-  q.n_mb = (n_red + kT_M - 1) / kT_M;
-  q.n_nb = (n_red + kT_N - 1) / kT_N;
-  q.n_tiles = 0;
-  for (int mi = 0; mi < q.n_mb; ++mi) q.n_tiles += q.n_nb - (kT_M * mi) / kT_N;
-  q.pow2 = pow2;
-  q.slice_chunks = kT_SliceChunks;
-  if (const char* e = getenv("AGF_I8T_SLICE_CHUNKS")) {
-    const int v = atoi(e);
-    if (v >= 1 && v <= 768) q.slice_chunks = v;  // 768 chunks = 24 576 rows: the int32 accumulators' limit
-  }
-  q.gram = gram;
   for (int64_t f0 = 0; f0 < n_frames; f0 += L.slab) {
     I8tDigitsParams d;
     memset(&d, 0, sizeof(d));
@@ -387,11 +413,18 @@ extern "C" int agf_gram_linear_i8t(const void* forces, int dtype, int64_t n_fram
     i8t_scrub_kernel<kGramLayout><<<(n_flags + 255) / 256 < sms ? (n_flags + 255) / 256 : sms, 256, 0, s>>>(flags, n_flags, d.n_frames, f0, n_xb,
                                                                                             digits, count, leftover);
     AGF_CUDA_TRY(cudaGetLastError());
+    I8tSyrkLaunch q;
+    q.digits = digits;
     q.n_chunks = 3 * n_fb;
-    q.n_slices = (q.n_chunks + q.slice_chunks - 1) / q.slice_chunks;
-    const int64_t units = (int64_t)q.n_slices * q.n_tiles;
-    i8t_syrk_kernel<<<(int)(units < sms ? units : sms), kT_SyrkThreads, syrk_smem, s>>>(q);
-    AGF_CUDA_TRY(cudaGetLastError());
+    q.n_red = n_red;
+    q.slice_chunks = 0;
+    q.n_batch = 1;
+    q.digits_batch_stride = 0;
+    q.pow2 = pow2;
+    q.gram = gram;
+    q.gram_batch_stride = 0;
+    const int rc = i8t_launch_syrk(q, s);
+    if (rc) return rc;
   }
   const size_t lsmem = (size_t)3 * n_red * sizeof(double);
   AGF_CUDA_TRY(cudaFuncSetAttribute(i8t_leftover_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));

@@ -20,15 +20,18 @@ constexpr int kT_TileBytes = 3 * kT_Slices * (kT_PanelCols / 16) * kT_TileXb;  /
 
 
 // ------------------------------------------------------------------------------------------------
-// Column scales from a strided sample of the frames: thread = column, block row = one GROUP of sampled frames
-// (strided over the whole array).  The scale of a column comes from the SMALLEST positive group maximum: a stray
-// huge value in the sample raises only its own group's maximum and so cannot coarsen the fixed point of the
-// column (its frame simply goes to the float64 pass like any other out-of-range frame).
-// colmin_bits must be preset to 0x7F7F... (a huge finite double: "no positive value seen").
+// Column scales from a strided sample of the frames.  Thread = column, block row = one GROUP of sampled frames
+// (strided over the whole array); every group leaves its maximum |group sum| per column in gmax[group][column].
+// The scale of a column is taken from the UPPER QUARTILE of its positive group maxima (i8t_scale_kernel): a few
+// stray huge values raise only their own groups' maxima and cannot coarsen the fixed point of the column (their
+// frames go to the float64 pass like any other out-of-range frame), and a column that is active in part of the
+// trajectory only is scaled by its active groups.
+constexpr int kT_MaxSampleGroups = 64;
+
 static __global__ void __launch_bounds__(128) i8t_sample_kernel(const float* __restrict__ forces, int64_t n_frames, int64_t stride,
                                                                 int n_sites, const int32_t* __restrict__ col_ptr,
-                                                                const int32_t* __restrict__ col_sites, int n_red,
-                                                                unsigned long long* __restrict__ colmin_bits) {
+                                                                const int32_t* __restrict__ col_sites, int n_red, int n_pad,
+                                                                double* __restrict__ gmax) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= n_red) return;
   const int b = __ldg(col_ptr + x), e = __ldg(col_ptr + x + 1);
@@ -45,26 +48,65 @@ static __global__ void __launch_bounds__(128) i8t_sample_kernel(const float* __r
     const double m = fmax(fabs(s0), fmax(fabs(s1), fabs(s2)));
     if (m < 1.0e300) best = fmax(best, m);
   }
-  if (best > 0.0) atomicMin(colmin_bits + x, (unsigned long long)__double_as_longlong(best));  // bits of x >= 0 order like x
+  gmax[(size_t)blockIdx.y * n_pad + x] = best;
 }
 
-// Group maxima of a few sampled frames sit near 2 sigma for bell-shaped data: values below 8-16x the smallest of
-// them (2^(E-1) with E = ilogb + 4, i.e. beyond 13 sigma) fit the 39-bit fixed point, whose step is then about
-// 1e-10 of a typical value.
-__device__ __forceinline__ int column_exponent_robust(unsigned long long min_bits) {
-  const double m = __longlong_as_double((long long)min_bits);
-  if (!(m > 0.0) || !(m < 1.0e300)) return -900;  // nothing but zeros (or nothing finite) in the sample
-  int e = ilogb(m) + 4;
+// Upper quartile of the positive entries of gmax[0 .. n_groups)[x]; 0 when there is none.  Whole warp: lane l
+// holds groups l and l + 32, ranks them against all others with shuffles (ties broken by group index).
+__device__ __forceinline__ double i8t_group_quartile(const double* __restrict__ gmax, int n_groups, int n_pad, int x) {
+  const int lane = threadIdx.x & 31;
+  double v[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int g = lane + 32 * h;
+    const double m = g < n_groups ? gmax[(size_t)g * n_pad + x] : 0.0;
+    v[h] = m > 0.0 ? m : 0.0;  // NaN and negatives count as "no positive maximum"
+  }
+  const int n = __popc(__ballot_sync(0xffffffffu, v[0] > 0.0)) + __popc(__ballot_sync(0xffffffffu, v[1] > 0.0));
+  if (n == 0) return 0.0;
+  int rank[2] = {0, 0};  // number of positive entries ordered before mine
+#pragma unroll
+  for (int oh = 0; oh < 2; ++oh) {
+    for (int ol = 0; ol < 32; ++ol) {
+      const double o = __shfl_sync(0xffffffffu, v[oh], ol);
+      const int og = ol + 32 * oh;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        rank[h] += (o > 0.0 && (o < v[h] || (o == v[h] && og < lane + 32 * h))) ? 1 : 0;
+    }
+  }
+  const int want = (3 * (n - 1) + 2) / 4;
+  double pick = 0.0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (v[h] > 0.0 && rank[h] == want) pick = v[h];
+  // exactly one lane holds the wanted rank
+  const uint32_t who = __ballot_sync(0xffffffffu, pick > 0.0);
+  return __shfl_sync(0xffffffffu, pick, __ffs(who) - 1);
+}
+
+// Group maxima of 8-16 sampled frames sit between 2 and 3 sigma for bell-shaped data: values below 4-8x their
+// upper quartile (2^(E-1) with E = ilogb + 4, i.e. beyond 10 sigma) fit the 39-bit fixed point, whose step is then
+// about 1e-10 of a typical value.  (One bit less headroom puts the limit at 5-9 sigma: a frame in a thousand of a
+// 5 000-atom system would take the float64 pass.)
+__device__ __forceinline__ int column_exponent_robust(double q) {
+  if (!(q > 0.0) || !(q < 1.0e300)) return -900;  // nothing but zeros (or nothing finite) in the sample
+  int e = ilogb(q) + 4;
   return e < -900 ? -900 : (e > 900 ? 900 : e);
 }
 
-static __global__ void i8t_scale_kernel(const unsigned long long* __restrict__ colmin_bits, int n_red, int n_pad,
-                                        int32_t* __restrict__ exps, double* __restrict__ scales, double* __restrict__ pow2) {
-  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+// n_pad: columns per row of gmax / exps / scales / pow2; a column x is live when x % n_period < n_red (batched
+// column sets -- the beads of a featurised fit -- repeat with period n_period; n_period = n_pad otherwise).
+static __global__ void __launch_bounds__(256) i8t_scale_kernel(const double* __restrict__ gmax, int n_groups, int n_red, int n_pad,
+                                                               int n_period, int32_t* __restrict__ exps,
+                                                               double* __restrict__ scales, double* __restrict__ pow2) {
+  const int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp = column
   if (x >= n_pad) return;
-  const int e = x < n_red ? column_exponent_robust(colmin_bits[x]) : 0;
+  const bool live = x % n_period < n_red;
+  const int e = live ? column_exponent_robust(i8t_group_quartile(gmax, n_groups, n_pad, x)) : 0;
+  if ((threadIdx.x & 31) != 0) return;
   exps[x] = e;
-  scales[x] = x < n_red ? ldexp(1.0, 39 - e) : 0.0;
+  scales[x] = live ? ldexp(1.0, 39 - e) : 0.0;
   pow2[x] = ldexp(1.0, e - 7);  // G[x][y] = pow2[x] pow2[y] sum_l 2^(-8 l) acc_l[x][y]
 }
 
@@ -78,7 +120,7 @@ static inline I8tSamplePlan i8t_sample_plan(int64_t n_frames) {
   sp.stride = n_frames > kT_SampleFrames ? n_frames / kT_SampleFrames : 1;
   const int64_t n_sample = (n_frames + sp.stride - 1) / sp.stride;
   int64_t g = n_sample / 8;
-  sp.groups = (int)(g < 1 ? 1 : (g > 64 ? 64 : g));
+  sp.groups = (int)(g < 1 ? 1 : (g > kT_MaxSampleGroups ? kT_MaxSampleGroups : g));
   return sp;
 }
 
@@ -239,5 +281,22 @@ __global__ void __launch_bounds__(256) i8t_scrub_kernel(const int32_t* __restric
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// The tiled SYRK over digit planes in kGramLayout (defined in gram_i8t.cu): gram[bm] (+=, upper triangle) for
+// n_batch independent column sets of n_red columns each, whose digit buffers lie digits_batch_stride bytes apart.
+struct I8tSyrkLaunch {
+  const unsigned char* digits;
+  int32_t n_chunks;            // chunks (32 frames of one xyz component) in the buffer
+  int32_t n_red;
+  int32_t slice_chunks;        // chunks per work unit, 0 = default (256; at most 768)
+  int32_t n_batch;
+  int64_t digits_batch_stride;
+  const double* pow2;          // [n_batch][i8t_pad(n_red)]: 2^(E - 7) per column
+  double* gram;                // [n_batch][n_red][n_red]
+  int64_t gram_batch_stride;   // doubles
+};
+int i8t_launch_syrk(const I8tSyrkLaunch& l, cudaStream_t s);
+int i8t_pad(int n_red);  // columns per buffer row: whole 128-column row blocks and whole 96-column blocks
 
 }  // namespace agf

@@ -275,6 +275,16 @@ class _FusedContext:
         for _, c, f in _engine.paired_pieces(coords, forces):
             if c.dtype != f.dtype:
                 c, f = c.to(torch.float64), f.to(torch.float64)
+            need_i8 = 0
+            if _engine._GRAM_I8[0] and nf > 97 and c.shape[0] >= _engine._GRAM_I8T_MIN_FRAMES:
+                need_i8 = int(_lib.lib().agf_gram_feat_i8_workspace_bytes(self.n_groups, self.n_channels, self.nb,
+                                                                          self.n_cg, c.shape[0]))
+            if need_i8 > 0:  # regression rows -> int8 digit planes -> batched tcgen05 SYRK (csrc/featgram.cu)
+                ws = _engine.workspace(need_i8)
+                _lib.call("agf_gram_feat_i8", _engine.ptr(c), _engine.ptr(f), _engine.dtype_code(c), c.shape[0],
+                          self.n_fg, *self._common(), float(kbt), _engine.ptr(gram), _engine.ptr(ws),
+                          C.c_size_t(ws.numel()), _engine.stream_ptr())
+                continue
             need = int(_lib.lib().agf_gram_feat_workspace_bytes(self.n_groups, self.n_channels, self.nb, self.n_cg,
                                                                 c.shape[0]))
             ws = _engine.workspace(need)

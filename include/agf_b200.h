@@ -276,6 +276,24 @@ int agf_gram_feat_ws(const void* coords, const void* forces, int dtype, int64_t 
                      const double* centers, int32_t nb, double width, double clip, double kbt,
                      double* gram, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The featurised Gram on the 5th-generation tensor cores (n_feat > 97; float32 or float64 input): same contract and
+ * arguments as agf_gram_feat_ws.  The regression rows are evaluated in float64 exactly as there, scaled per
+ * (bead, feature column) by a power of two taken from a sample of frame groups, rounded to 39-bit fixed point
+ * and split into five signed 8-bit digit planes; the tiled tcgen05 int8 SYRK of agf_gram_linear_i8t runs batched
+ * over the beads (128 x 96 tiles of every bead's upper block-triangle).  Frames with a non-finite or out-of-range
+ * row value are added in float64 by a second kernel.
+ *   workspace   device, agf_gram_feat_i8_workspace_bytes(...) bytes (0: shape not supported -- use
+ *               agf_gram_feat_ws), 16-byte aligned
+ */
+size_t agf_gram_feat_i8_workspace_bytes(int32_t n_groups, int32_t n_channels, int32_t nb, int32_t n_cg,
+                                        int64_t n_frames);
+int agf_gram_feat_i8(const void* coords, const void* forces, int dtype, int64_t n_frames, int32_t n_sites,
+                     const int32_t* grp_ptr, const int32_t* grp_sites, int32_t n_groups,
+                     int32_t n_channels, const int32_t* bead_ptr, const int32_t* bead_sites,
+                     const double* bead_w, int32_t n_cg, const double* centers, int32_t nb, double width,
+                     double clip, double kbt, double* gram, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
 int agf_symmetrize_batch(double* gram, int32_t n, int32_t batch, void* stream);
 
 /* ------------------------------------------------------------------------------------

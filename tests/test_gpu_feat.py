@@ -312,3 +312,62 @@ def test_project_forces_with_gaussian_methods(topo, data):
         assert abs((res["mapped_coords"] - x_cg).var() / 0.2 - 1) < 0.2
         assert abs(res["residual"] - np.mean(res["mapped_forces"] ** 2)) < 1e-9 * res["residual"]
         assert res["constraints"] == cons
+
+
+# --------------------------------------------------------------------------------------
+# featurised Gram on the tensor cores (agf_gram_feat_i8: int8 digit planes, batched tcgen05 SYRK)
+# --------------------------------------------------------------------------------------
+def _feat_grams(coords, forces, topo, use_i8, min_frames=None):
+    from aggforce_b200 import _engine, _lib
+    from aggforce_b200.qp.featlinearmap import _FusedContext, _fusable
+
+    ctx = _FusedContext(_cmap(topo), topo.xh_constraints, _fusable(_featurizer()))
+    old = (_engine._GRAM_I8[0], _engine._GRAM_I8T_MIN_FRAMES)
+    _engine._GRAM_I8[0] = use_i8
+    if min_frames is not None:
+        _engine._GRAM_I8T_MIN_FRAMES = min_frames
+    try:
+        _lib.timing(True)
+        grams = ctx.grams(_engine.Frames(coords), _engine.Frames(forces), KBT)
+        names = {n for n, _ in _lib.timing_records()}
+        _lib.timing(False)
+    finally:
+        _engine._GRAM_I8[0], _engine._GRAM_I8T_MIN_FRAMES = old
+    assert ("agf_gram_feat_i8" in names) == use_i8 and ("agf_gram_feat_ws" in names) != use_i8
+    return grams, ctx
+
+
+def test_feat_gram_i8_matches_oracle(topo, data):
+    """40 frames through the int8 path (its frame threshold lowered) against the float64 oracle: the north-star bar."""
+    coords, forces = data
+    grams, ctx = _feat_grams(coords, forces, topo, True, min_frames=1)
+    cmap = _cmap(topo)
+    for bead in (0, 5, 9):
+        feats, divs = _oracle_features(coords, cmap.standard_matrix, topo.xh_constraints, ctx.labels, bead)
+        ref = oracle.feat_gram(forces, feats, divs, KBT)
+        assert rel_fro(grams[bead], ref) < 1e-9
+        assert np.array_equal(grams[bead], grams[bead].T)
+
+
+def test_feat_gram_i8_agrees_with_the_dmma_kernel(topo):
+    """3 001 frames (ragged chunk, several slices), float32 and float64 input, an out-of-range frame and a NaN."""
+    from aggforce_b200.synth import synth_trajectory_host
+
+    coords, forces = synth_trajectory_host(topo, 3001, seed=78)
+    want, _ = _feat_grams(coords, forces, topo, False)
+    got, _ = _feat_grams(coords, forces, topo, True)
+    for bead in range(10):
+        assert rel_fro(got[bead], want[bead]) < 1e-9
+    got64, _ = _feat_grams(coords.astype(np.float64), forces.astype(np.float64), topo, True)
+    assert rel_fro(got64, want) < 1e-9
+    forces = forces.copy()
+    forces[1500, 20, 1] = 4.0e8  # far outside the sampled scale: float64 pass
+    want, _ = _feat_grams(coords, forces, topo, False)
+    got, _ = _feat_grams(coords, forces, topo, True)
+    assert rel_fro(got, want) < 1e-12  # the huge frame dominates and is exact
+    mask = np.abs(want) < 1e-6 * np.abs(want).max()
+    assert np.abs(got - want)[mask].max() < 1e-9 * np.abs(want[mask]).max()
+    forces[2000, 3, 0] = np.nan
+    want, _ = _feat_grams(coords, forces, topo, False)
+    got, _ = _feat_grams(coords, forces, topo, True)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(got).any()
