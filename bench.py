@@ -275,14 +275,14 @@ def kernel_table(per_kernel: dict, algo: dict, peaks: dict, hbm_peak: float, tra
 INT8_NOMINAL_TOPS = 4500.0  # dense int8 tensor peak of one B200 (datasheet; no int8 probe runs inside the bench)
 
 
-def tiled_gram_note(entry: dict, n_red: int, n_frames: int) -> None:
+def tiled_gram_note(entry: dict, n_red: int, n_frames: int, batch: int = 1) -> None:
     """agf_gram_linear_i8t: `achieved` stays the float64-EQUIVALENT rate against the FP64 DMMA peak (the roof
     of the formulation it replaces); the kernel's own roof is the int8 tensor pipe, reported next to it."""
     if not entry or entry.get("ms_total", 0) <= 0:
         return
     n_mb, n_nb = -(-n_red // 128), -(-n_red // 96)
     tiles = sum(n_nb - (128 * mi) // 96 for mi in range(n_mb))
-    ops = 2.0 * 15 * tiles * 128 * 96 * 3 * n_frames  # n_frames: all frames of the call, over all its launches
+    ops = 2.0 * 15 * batch * tiles * 128 * 96 * 3 * n_frames  # n_frames: all frames of the call, over all its launches
     entry["int8_tops"] = ops / (entry["ms_total"] * 1e-3) / 1e12
     entry["int8_peak_tops"] = INT8_NOMINAL_TOPS
     entry["int8_frac"] = entry["int8_tops"] / INT8_NOMINAL_TOPS
@@ -338,8 +338,21 @@ def main() -> None:
         # the sampler runs across warm-up AND the timed steps: the timed region alone lasts tens of
         # milliseconds, less than one nvidia-smi sampling period
         sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None  # one nvidia-smi poller per box
-        for _ in range(warmup):
+        done, t_w = 0, time.perf_counter()
+        # at least `warmup` steps, and the same load kept up until the poller has delivered its first sample
+        # (nvidia-smi needs ~0.1-0.3 s to start), so that the samples bracket the timed steps under load;
+        # rank 0 (the one with the poller) decides for everybody: the steps carry collectives
+        while True:
+            more = done < warmup or (sampler is not None and sampler.proc is not None and not sampler.rows
+                                     and time.perf_counter() - t_w < 3.0)
+            if world > 1:
+                flag = torch.tensor([1 if more else 0], device="cuda", dtype=torch.int32)
+                dist.broadcast(flag, 0)
+                more = bool(flag.item())
+            if not more:
+                break
             fn()
+            done += 1
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = _lib.LAUNCHES["count"]
@@ -352,7 +365,15 @@ def main() -> None:
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        clocks = sampler.stop() if sampler else None
+        clocks = None
+        if sampler is not None:
+            # the step function does not communicate outside frame_sharding(), so rank 0 may keep its GPU under
+            # the same load alone until two more samples have arrived (untimed; at most one second)
+            have, t_a = len(sampler.rows), time.perf_counter()
+            while (world == 1 and sampler.proc is not None and len(sampler.rows) < have + 2
+                   and time.perf_counter() - t_a < 1.0):
+                fn()
+            clocks = sampler.stop()
         return float(ms.item()) / steps, launches, clocks
 
     def kernel_times(fn):
@@ -519,7 +540,8 @@ def config_probes(agf, _engine, _lib, torch, dist, rank, world, peaks, hbm_peak,
     ms3, _ = wall(run3)
     per = kernel_times(run3)
     n_feat, n_cg = 97 + 7 * 96, 10
-    algo3 = {"agf_gram_feat_ws": ("tensor", n_cg * 3 * n_feat * (n_feat + 1) * T3)}
+    algo3 = {"agf_gram_feat_ws": ("tensor", n_cg * 3 * n_feat * (n_feat + 1) * T3),
+             "agf_gram_feat_i8": ("tensor", n_cg * 3 * n_feat * (n_feat + 1) * T3)}
     out["cfg3_featurised"] = {
         "workload": f"cln025, qp_feat_linear_map(Multifeaturize([id_feat, gb_feat(0,8,1,n_basis=7)]), l2=1e3), "
                     f"n_feat {n_feat}, {T3} frames per GPU: project_forces = featurised Gram + per-bead device solve "
@@ -527,6 +549,7 @@ def config_probes(agf, _engine, _lib, torch, dist, rank, world, peaks, hbm_peak,
         "frames_per_gpu": T3, "ms_project_forces": ms3, "frames_per_s": world * T3 / (ms3 * 1e-3),
         "kernels": kernel_table(per, algo3, peaks, hbm_peak, {}),
     }
+    tiled_gram_note(out["cfg3_featurised"]["kernels"].get("agf_gram_feat_i8"), n_feat, T3, batch=n_cg)
     del c3, f3
 
     # ---- config 4 shape: 5 000 atoms, 500 beads, n_red 2 600; Gram + constraint detection + apply
