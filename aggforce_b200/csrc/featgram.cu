@@ -436,7 +436,8 @@ struct FeatDigits {
   unsigned char* digits;  // bead-major buffers, bead_stride bytes apart
   int64_t bead_stride;
   int32_t* flags;         // [frames of the slab, rounded up to 32]
-  double* gmax;           // SAMPLE: [sample group][n_cg * n_xb * 16]
+  double* gmax;           // SAMPLE: [sample group][n_cg * n_xb * 16], or NULL: ...
+  unsigned long long* colmax_bits;  // ... maxima over ALL sampled groups (bits of a non-negative double), [n_cg * n_xb * 16]
 };
 
 template <typename T, bool SAMPLE>
@@ -527,9 +528,13 @@ __global__ void __launch_bounds__(256) feat_digits_kernel(const __grid_constant_
     }
     if (SAMPLE) {
       __syncthreads();
-      if (threadIdx.x < kT_PanelCols)
-        q.gmax[(size_t)blockIdx.x * p.n_cg * n_pad + (size_t)bead * n_pad + pass * kT_PanelCols + threadIdx.x] =
-            __longlong_as_double((long long)s_max[threadIdx.x]);
+      if (threadIdx.x < kT_PanelCols) {
+        const size_t x = (size_t)bead * n_pad + pass * kT_PanelCols + threadIdx.x;
+        if (q.gmax != nullptr)
+          q.gmax[(size_t)blockIdx.x * p.n_cg * n_pad + x] = __longlong_as_double((long long)s_max[threadIdx.x]);
+        else if (s_max[threadIdx.x] != 0ull)
+          atomicMax(q.colmax_bits + x, s_max[threadIdx.x]);
+      }
       __syncthreads();
       continue;
     }
@@ -560,17 +565,20 @@ __global__ void __launch_bounds__(256) feat_digits_kernel(const __grid_constant_
   }
 }
 
-// Column scales of the featurised rows.  id columns (group forces): the robust upper quartile of the sampled
+// Column scales of the featurised rows.  id columns (group forces): the robust upper quartile of 64 sampled
 // group maxima, as for the linear Gram.  gb columns  v = g_k F + kbt m g_k' u  are heavy-tailed (a distance
-// wandering through the flank of a Gaussian bin changes g_k by orders of magnitude), so a quantile would send most
-// frames to the float64 pass: they take the sample MAXIMUM with 64-128x headroom instead, capped by the a-priori
-// bound  |v| <= |F| + kbt m max|g'|  (|g_k| < 1, max|g'| = sqrt(2/e) / width) evaluated at the id column's range --
-// a frame whose group forces are in range is then in range in every gb column, and a stray huge force in the
-// sample cannot coarsen a gb column beyond that bound.  Columns that barely leave the clip in the sample (maximum
-// below 2^-19 of the bound) get a floor of 2^-12 of the bound: their absolute error stays 2^-51 of the bound, below
-// the rounding of the live columns, and without the floor any frame that leaves the clip a little further (g - clip
-// starts from zero there, the ratio to the sampled maximum is unbounded) would overflow them.
-__global__ void feat_scale_kernel(const double* __restrict__ gmax, int n_groups, FeatParams p, int n_pad,
+// wandering through the flank of a Gaussian bin changes g_k by orders of magnitude), so neither a quantile nor the
+// maximum of a few hundred frames predicts their range: too little headroom sends frames to the float64 pass by
+// the hundred, too much costs the gb x gb block of the Gram its precision (the dropped digit products are
+// relative to the SCALES; seven spare bits showed up as 1e-6 in the fitted coefficients of an ill-conditioned
+// featurised QP).  They take the maximum over EVERY FOURTH group of 8 frames (a second, denser sampling pass:
+// one more evaluation of a quarter of the rows) with 4-8x headroom, capped by the a-priori bound
+// |v| <= |F| + kbt m max|g'|  (|g_k| < 1, max|g'| = sqrt(2/e) / width) at the id column's range -- a frame whose
+// group forces are in range can then not overflow a capped column, and a stray huge force cannot coarsen a gb
+// column beyond that bound.  Columns that barely leave the clip (maximum below 2^-15 of the bound; g - clip starts
+// from zero there) get a floor of 2^-12 of the bound: their absolute error stays 2^-51 of the bound.
+__global__ void feat_scale_kernel(const double* __restrict__ gmax, int n_groups,
+                                  const unsigned long long* __restrict__ colmax_bits, FeatParams p, int n_pad,
                                   int32_t* __restrict__ exps, double* __restrict__ scales, double* __restrict__ pow2) {
   const int x = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // warp = column
   const int lane = threadIdx.x & 31;
@@ -589,11 +597,8 @@ __global__ void feat_scale_kernel(const double* __restrict__ gmax, int n_groups,
       const double m = (double)(__ldg(p.grp_ptr + g + 1) - __ldg(p.grp_ptr + g));
       const double bound = ldexp(1.0, e_id - 1) + p.kbt * m * 0.8577638849607068 * p.inv_width;
       const int e_cap = ilogb(bound) + 2;
-      double best = 0.0;
-      for (int sg = lane; sg < n_groups; sg += 32) best = fmax(best, gmax[(size_t)sg * cols + x]);
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
-      e = (best > 0.0 && best < 1.0e300) ? max(min(ilogb(best) + 7, e_cap), e_cap - 12) : e_cap;
+      const double best = __longlong_as_double((long long)colmax_bits[x]);  // over a quarter of all frames
+      e = (best > 0.0 && best < 1.0e300) ? max(min(ilogb(best) + 3, e_cap), e_cap - 12) : e_cap;
       e = e < -900 ? -900 : (e > 900 ? 900 : e);
     }
   }
@@ -684,7 +689,7 @@ __global__ void __launch_bounds__(256) feat_leftover_kernel(const __grid_constan
 }
 
 struct FeatI8Layout {
-  size_t gmax, exps, scales, pow2, count, leftover, flags, digits, total;
+  size_t gmax, colmax, exps, scales, pow2, count, leftover, flags, digits, total;
   int64_t slab, bead_stride;
   int n_pad;
 };
@@ -695,7 +700,8 @@ static FeatI8Layout feat_i8_layout(int n_feat, int n_cg, int64_t n_frames) {
   L.n_pad = i8t_pad(n_feat);
   const size_t cols = (size_t)n_cg * L.n_pad;
   L.gmax = 0;
-  L.exps = up(cols * 8 * kT_MaxSampleGroups);
+  L.colmax = up(cols * 8 * kT_MaxSampleGroups);
+  L.exps = L.colmax + up(cols * 8);
   L.scales = L.exps + up(cols * 4);
   L.pow2 = L.scales + up(cols * 8);
   L.count = L.pow2 + up(cols * 8);
@@ -870,6 +876,7 @@ extern "C" int agf_gram_feat_i8(const void* coords, const void* forces, int dtyp
   const FeatI8Layout L = feat_i8_layout(p.n_feat, n_cg, n_frames);
   char* ws = reinterpret_cast<char*>(workspace);
   double* gmax = reinterpret_cast<double*>(ws + L.gmax);
+  unsigned long long* colmax = reinterpret_cast<unsigned long long*>(ws + L.colmax);
   int32_t* exps = reinterpret_cast<int32_t*>(ws + L.exps);
   double* scales = reinterpret_cast<double*>(ws + L.scales);
   double* pow2 = reinterpret_cast<double*>(ws + L.pow2);
@@ -907,7 +914,14 @@ extern "C" int agf_gram_feat_i8(const void* coords, const void* forces, int dtyp
     q.n_frames = n_frames;
     q.group_stride = all_groups / n_sg;
     AGF_FEAT_DIGITS(true, dim3(n_sg, n_cg), grp_smem);
-    feat_scale_kernel<<<(cols + 7) / 8, 256, 0, s>>>(gmax, n_sg, p, L.n_pad, exps, scales, pow2);
+    // the denser pass for the gb columns: every fourth group, maxima merged with atomicMax (colmax is zeroed above)
+    const int64_t dense_stride = all_groups >= 8 ? 4 : 1;
+    q.gmax = nullptr;
+    q.colmax_bits = colmax;
+    q.group_stride = dense_stride;
+    AGF_FEAT_DIGITS(true, dim3((unsigned)((all_groups + dense_stride - 1) / dense_stride), n_cg), grp_smem);
+    q.gmax = gmax;
+    feat_scale_kernel<<<(cols + 7) / 8, 256, 0, s>>>(gmax, n_sg, colmax, p, L.n_pad, exps, scales, pow2);
     AGF_CUDA_TRY(cudaGetLastError());
   }
   const int sms = sm_count();

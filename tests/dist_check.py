@@ -66,14 +66,26 @@ def main() -> None:
     choice = np.random.default_rng(42100).choice(Tf, size=20, replace=False)
     kw = dict(coord_map=cmap, constrained_inds=topo.xh_constraints, method=qp_feat_linear_map, featurizer=feat,
               kbt=0.6955215, l2_regularization=1e3, constraint_frames=choice)
-    with agf.frame_sharding():
-        fres = agf.project_forces(coords=ac[flo:fhi].contiguous(), forces=af[flo:fhi].contiguous(), **kw)
-    fref = agf.project_forces(coords=ac[:Tf].contiguous(), forces=af[:Tf].contiguous(), **kw)
-    c0 = np.stack(fres["tmap"].force_map.tags["coef_list"])
-    c1 = np.stack(fref["tmap"].force_map.tags["coef_list"])
-    rel_c = np.linalg.norm(c0 - c1) / np.linalg.norm(c1)
-    rel_ff = float((fres["mapped_forces"] - fref["mapped_forces"][flo:fhi]).norm() / fref["mapped_forces"][flo:fhi].norm())
+    def feat_pair():
+        with agf.frame_sharding():
+            a = agf.project_forces(coords=ac[flo:fhi].contiguous(), forces=af[flo:fhi].contiguous(), **kw)
+        b = agf.project_forces(coords=ac[:Tf].contiguous(), forces=af[:Tf].contiguous(), **kw)
+        c0 = np.stack(a["tmap"].force_map.tags["coef_list"])
+        c1 = np.stack(b["tmap"].force_map.tags["coef_list"])
+        rc = np.linalg.norm(c0 - c1) / np.linalg.norm(c1)
+        rf = float((a["mapped_forces"] - b["mapped_forces"][flo:fhi]).norm() / b["mapped_forces"][flo:fhi].norm())
+        return rc, rf
+
+    # the sharding logic on ONE arithmetic (FP64 DMMA Grams on both sides): rounding-level agreement
+    _engine._GRAM_I8[0] = False
+    rel_c, rel_ff = feat_pair()
+    _engine._GRAM_I8[0] = True
     ok = ok and rel_c < 1e-8 and rel_ff < 1e-8
+    # default kernels: the 3 000-frame single-GPU fit takes the int8 tensor-core Gram, the 1 500-frame shards
+    # the DMMA one (both within 1e-9 of the float64 Gram); this small, ill-conditioned featurised QP amplifies
+    # the difference: the north-star bar (1e-6) on what the map does, the coefficients reported
+    rel_c8, rel_ff8 = feat_pair()
+    ok = ok and rel_ff8 < 1e-6 and rel_c8 < 1e-4
     with agf.frame_sharding():  # unseeded choice: still one choice for all ranks
         fres2 = agf.project_forces(coords=ac[flo:fhi].contiguous(), forces=af[flo:fhi].contiguous(),
                                    **dict(kw, constraint_frames=None))
@@ -110,6 +122,7 @@ def main() -> None:
     if rank == 0:
         print(f"dist_check world={world}: constraints={len(res['constraints'])} rel_w={rel_w:.2e} rel_f={rel_f:.2e} "
               f"residual={res['residual']:.6g} feat rel_coef={rel_c:.2e} rel_mapped={rel_ff:.2e} "
+              f"(int8 vs DMMA paths: {rel_c8:.2e} / {rel_ff8:.2e}) "
               f"peer exchange {peer} -> {'OK' if flag.item() else 'FAILED'}")
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
