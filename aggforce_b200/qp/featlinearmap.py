@@ -33,7 +33,8 @@ from ..map import CLAFTMap, CLAMap, LinearMap
 from ..trajectory import Trajectory
 from ..util import Curry
 from .gbfeat import GbSpec, gb_feat
-from .solver import DEFAULT_SOLVER_OPTIONS, SolverOptions, solve, solve_equality_qp_device, warn_if_solver_ignored
+from .solver import (DEFAULT_SOLVER_OPTIONS, SolverOptions, solve, solve_equality_qp_device,
+                     solve_equality_qp_device_batched, warn_if_solver_ignored)
 
 _DEVICE_SOLVE_MIN = 512  # feature counts from which the per-bead QP is solved on the device
 
@@ -301,8 +302,9 @@ class _FusedContext:
         host = _engine.to_host(gram)
         return host[:, self.columns][:, :, self.columns]
 
-    def constraint_rows(self, coords: _engine.Frames, bead: int, frame_indices: np.ndarray) -> np.ndarray:
-        """``(n_sel * n_cg, n_feat)`` equality rows of one bead (user feature order)."""
+    def constraint_rows(self, coords: _engine.Frames, bead: int, frame_indices: np.ndarray, on_device: bool = False):
+        """``(n_sel * n_cg, n_feat)`` equality rows of one bead (user feature order); numpy, or a CUDA tensor
+        with ``on_device`` (nothing synchronises then)."""
         idx = np.asarray(frame_indices, dtype=np.int64)
         n_sel = int(idx.size)
         picked = coords.gather(idx)
@@ -310,6 +312,11 @@ class _FusedContext:
         rows = torch.empty((n_sel, self.n_cg, self.n_feat_kernel), dtype=torch.float64, device=_engine.device())
         _lib.call("agf_feat_rows", _engine.ptr(picked), _engine.dtype_code(picked), self.n_fg, _engine.ptr(sel), n_sel,
                   int(bead), _engine.ptr(self.d_labels), *self._common(), _engine.ptr(rows), _engine.stream_ptr())
+        if on_device:
+            rows = rows.reshape(n_sel * self.n_cg, self.n_feat_kernel)
+            if np.array_equal(self.columns, np.arange(self.n_feat_kernel)):
+                return rows
+            return rows[:, _engine._dev_cached(np.ascontiguousarray(self.columns, dtype=np.int64))]
         return _engine.to_host(rows).reshape(n_sel * self.n_cg, self.n_feat_kernel)[:, self.columns]
 
     def apply(self, coords: _engine.Frames, forces: _engine.Frames, coefs: np.ndarray, want_sumsq: bool = False):
@@ -432,7 +439,26 @@ def _fit_fused(traj, coord_map, featurizer, plan, kbt, n_constraint_frames, cons
     n_feat = grams.shape[1]
     coefs = []
     chosen = _ConstraintFrames(coords.n_frames, coord_map.n_cg_sites, n_constraint_frames, constraint_frames)
-    for bead in range(coord_map.n_cg_sites):
+    n_cg = coord_map.n_cg_sites
+    if on_device:
+        # all beads at once: equality rows stay on the device (single GPU), one batched Cholesky / Schur solve,
+        # one read for the checks -- the per-bead loop below is the fallback when any bead's solve declines
+        dev_rows = not _engine.sharded()
+        a_all = [chosen.rows(b, lambda idx, b=b: ctx.constraint_rows(coords, b, idx, on_device=dev_rows), n_cg)
+                 for b in range(n_cg)]
+        if len({tuple(a.shape) for a in a_all}) == 1:
+            a_dev = torch.stack([a if isinstance(a, torch.Tensor) else torch.as_tensor(a, device=grams.device)
+                                 for a in a_all])
+            n_sel = a_dev.shape[1] // n_cg
+            rhs = torch.zeros((n_cg, n_sel, n_cg), dtype=torch.float64, device=grams.device)
+            rhs[torch.arange(n_cg), :, torch.arange(n_cg)] = 1.0
+            qp_all = grams.clone()
+            if l2_regularization > 0:
+                qp_all.diagonal(dim1=1, dim2=2).add_(l2_regularization)
+            sol = solve_equality_qp_device_batched(qp_all, a_dev, rhs.reshape(n_cg, n_sel * n_cg))
+            if sol is not None:
+                coefs = [sol[b] for b in range(n_cg)]
+    for bead in range(n_cg if not coefs else 0):
         frames = chosen.picks[bead]
         a_mat = chosen.rows(bead, lambda idx, b=bead: ctx.constraint_rows(coords, b, idx), coord_map.n_cg_sites)
         target = np.zeros((len(frames), coord_map.n_cg_sites))
