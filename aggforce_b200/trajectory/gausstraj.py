@@ -43,7 +43,10 @@ class SimpleCondNormal(Augmenter):
 
 
 class CondNormal(Augmenter):
-    """``y = premap(x) + N(0, cov)`` with a linear ``premap`` and scalar (isotropic) ``cov``.
+    """``y = premap(x) + N(0, cov)`` with a linear ``premap``.  ``cov``: a scalar (isotropic noise: the fused
+    kernel ``agf_gauss_augment``) or, as the reference's ``JCondNormal`` accepts, the full covariance matrix of
+    the flattened ``(n_new * 3)`` noise vector (sites major, xyz fastest: ``jaxgausstraj.py:331-346``), which
+    takes a dense device path (Cholesky factor for the draw, precision matrix for the log-gradients).
 
     ``premap`` is a ``LinearMap`` (or its bound ``flat_call``); ``None`` means identity.
     ``noise`` optionally injects the standard-normal draw ``(n_frames, n_new, 3)`` used by the
@@ -54,8 +57,14 @@ class CondNormal(Augmenter):
 
     def __init__(self, cov: float, premap=None, source_postmap=None, seed: Optional[int] = None,
                  dtype: Any = None, noise=None) -> None:
+        self._cov_matrix = None
         if not np.isscalar(cov):
-            raise NotImplementedError("only scalar (isotropic) covariances are supported")
+            mat = np.asarray(cov, dtype=np.float64)
+            if mat.ndim != 2 or mat.shape[0] != mat.shape[1] or mat.shape[0] % self.n_dim:
+                raise ValueError("cov must be a scalar or a square (n_new * 3, n_new * 3) matrix")
+            self._cov_matrix = mat
+            if dtype is None and isinstance(cov, np.ndarray) and cov.dtype in (np.float32, np.float64):
+                dtype = cov.dtype  # the reference takes the working dtype from the matrix
         owner = getattr(premap, "__self__", None)
         self.premap = owner if owner is not None else premap
         # linear map applied to the log-gradient w.r.t. the source sites (jaxgausstraj.py:263-284):
@@ -63,7 +72,7 @@ class CondNormal(Augmenter):
         # trajectory is the mapped back-projected noise force
         post_owner = getattr(source_postmap, "__self__", None)
         self.source_postmap = post_owner if post_owner is not None else source_postmap
-        self.cov = float(cov)
+        self.cov = float(cov) if self._cov_matrix is None else self._cov_matrix
         self.seed = int(np.random.default_rng().integers(0, 10**6)) if seed is None else int(seed)
         self.dtype = np.dtype(np.float32 if dtype is None else dtype)
         self._noise = noise
@@ -80,6 +89,75 @@ class CondNormal(Augmenter):
         out = eps if self.premap is None else self.premap.T(eps)
         return out if self.source_postmap is None else self.source_postmap(out)
 
+    # -- full covariance (dense device path)
+    def _factors(self):
+        """(Cholesky factor L, precision matrix) of the covariance as float64 device tensors, cached."""
+        cached = getattr(self, "_cov_factors", None)
+        if cached is None:
+            sigma = torch.as_tensor(self._cov_matrix, device=_engine.device())
+            chol, info = torch.linalg.cholesky_ex(sigma)
+            if int(info.item()) != 0:
+                raise ValueError("cov is not positive definite")
+            prec = torch.cholesky_solve(torch.eye(sigma.shape[0], dtype=torch.float64, device=sigma.device), chol)
+            cached = self._cov_factors = (chol, prec)
+        return cached
+
+    def _precision_times(self, resid: torch.Tensor) -> torch.Tensor:
+        """``cov^-1 r`` for every frame (float64 arithmetic, result in the working dtype)."""
+        _, prec = self._factors()
+        flat = resid.reshape(resid.shape[0], -1).to(torch.float64)
+        if flat.shape[1] != prec.shape[0]:
+            raise ValueError(f"cov is {tuple(prec.shape)} but the augmenting sites have {flat.shape[1]} coordinates")
+        return (flat @ prec).reshape(resid.shape).to(resid.dtype)
+
+    _NOISE_BLOCK = 4096
+
+    def _standard_normal(self, draw: "NoiseDraw", frame0: int, n_frames: int, n_new: int) -> torch.Tensor:
+        """Standard-normal draw for global frames ``frame0 .. frame0 + n_frames``: generated in fixed blocks of
+        frames, each from its own generator keyed by (seed, draw, block), so that any slab decomposition of the
+        same draw sees the same noise."""
+        dev = _engine.device()
+        first, last = frame0 // self._NOISE_BLOCK, (frame0 + n_frames - 1) // self._NOISE_BLOCK
+        parts = []
+        for blk in range(first, last + 1):
+            gen = torch.Generator(device=dev)
+            gen.manual_seed((self.seed * 1_000_003 + draw.index * 7919 + blk) % (2**63 - 1))
+            z = torch.randn((self._NOISE_BLOCK, n_new, self.n_dim), dtype=torch.float64, device=dev, generator=gen)
+            lo = max(frame0 - blk * self._NOISE_BLOCK, 0)
+            hi = min(frame0 + n_frames - blk * self._NOISE_BLOCK, self._NOISE_BLOCK)
+            parts.append(z[lo:hi])
+        return torch.cat(parts)
+
+    def _augment_full_cov(self, coords, forces, kbt: float, draw: "NoiseDraw", frame0: int):
+        td = self._tdtype()
+        ref = coords if coords is not None else forces
+        n_frames, n_sites = int(ref.shape[0]), int(ref.shape[1])
+        n_new = self.n_new_sites(n_sites)
+        chol, prec = self._factors()
+        if chol.shape[0] != n_new * self.n_dim:
+            raise ValueError(f"cov is {tuple(chol.shape)} but the augmenting sites have {n_new * self.n_dim} coordinates")
+        if draw.noise is not None:
+            z = draw.noise[frame0 : frame0 + n_frames].to(torch.float64)
+            if tuple(z.shape) != (n_frames, n_new, self.n_dim):
+                raise ValueError(f"injected noise has shape {tuple(draw.noise.shape)}; frames {frame0}.."
+                                 f"{frame0 + n_frames} of (n_frames, {n_new}, 3) are needed")
+        else:
+            z = self._standard_normal(draw, frame0, n_frames, n_new)
+        flat_z = z.reshape(n_frames, -1)
+        eps = (flat_z @ chol.T).reshape(n_frames, n_new, self.n_dim)           # cov-distributed noise
+        scaled = torch.linalg.solve_triangular(chol.T.contiguous(), flat_z.T.contiguous(), upper=True).T  # cov^-1 eps = L^-T z
+        scaled = scaled.reshape(n_frames, n_new, self.n_dim)
+        oc = of = None
+        if coords is not None:
+            x = coords.to(td)
+            mean = torch.as_tensor(self._mean(x)).to(device=x.device, dtype=torch.float64)
+            oc = torch.cat([x, (mean + eps).to(td)], dim=1)
+        if forces is not None:
+            f = forces.to(td)
+            back = torch.as_tensor(self._back(scaled)).to(device=f.device, dtype=torch.float64)
+            of = torch.cat([(f.to(torch.float64) + kbt * back).to(td), (-kbt * scaled).to(td)], dim=1)
+        return oc, of
+
     # -- Augmenter interface
     def sample(self, source):
         host = not (isinstance(source, torch.Tensor) and source.is_cuda)
@@ -93,8 +171,9 @@ class CondNormal(Augmenter):
         dev = _engine.device()
         mean = torch.as_tensor(self._mean(source)).to(device=dev, dtype=self._tdtype())
         resid = torch.as_tensor(generated).to(device=dev, dtype=self._tdtype()) - mean
-        wrt_generated = -resid / self.cov
-        wrt_source = torch.as_tensor(self._back(resid / self.cov)).to(device=dev, dtype=self._tdtype())
+        scaled = resid / self.cov if self._cov_matrix is None else self._precision_times(resid)
+        wrt_generated = -scaled
+        wrt_source = torch.as_tensor(self._back(scaled)).to(device=dev, dtype=self._tdtype())
         if host:
             return _engine.to_host(wrt_source), _engine.to_host(wrt_generated)
         return wrt_source, wrt_generated
@@ -147,6 +226,8 @@ class CondNormal(Augmenter):
         input may be ``None`` (its output is then ``None``)."""
         from .. import _lib
 
+        if self._cov_matrix is not None:
+            return self._augment_full_cov(coords, forces, kbt, draw, frame0)
         td = self._tdtype()
         ref = coords if coords is not None else forces
         n_frames, n_sites = int(ref.shape[0]), int(ref.shape[1])

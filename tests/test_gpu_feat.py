@@ -371,3 +371,52 @@ def test_feat_gram_i8_agrees_with_the_dmma_kernel(topo):
     want, _ = _feat_grams(coords, forces, topo, False)
     got, _ = _feat_grams(coords, forces, topo, True)
     assert np.array_equal(np.isnan(got), np.isnan(want)) and np.isnan(got).any()
+
+
+def test_condnormal_full_covariance(topo, data):
+    """``JCondNormal`` accepts the full covariance of the flattened noise vector (jaxgausstraj.py:148-150):
+    a diagonal matrix reproduces the scalar kernel for the same injected draw, a dense one follows the closed
+    form (eps = L z, gradients through cov^-1), and the draw does not depend on the slab decomposition."""
+    from aggforce_b200.trajectory import AugmentedTrajectory, CondNormal, Trajectory
+    from aggforce_b200.trajectory.gausstraj import NoiseDraw
+
+    coords, forces = data
+    cmap = _cmap(topo)
+    cm = cmap.standard_matrix
+    rng = np.random.default_rng(10)
+    noise = rng.standard_normal((len(coords), 10, 3))
+    diag = CondNormal(cov=0.4 * np.eye(30), premap=cmap, noise=noise, dtype=np.float64)
+    scal = CondNormal(cov=0.4, premap=cmap, noise=noise, dtype=np.float64)
+    traj = Trajectory(coords=coords, forces=forces)
+    a = AugmentedTrajectory.from_trajectory(traj, kbt=0.6, augmenter=diag)
+    b = AugmentedTrajectory.from_trajectory(traj, kbt=0.6, augmenter=scal)
+    assert rel_fro(a.coords, b.coords) < 1e-12 and rel_fro(a.forces, b.forces) < 1e-12
+    # dense covariance against numpy
+    q = rng.standard_normal((30, 30))
+    sigma = q @ q.T / 30 + 0.2 * np.eye(30)
+    chol = np.linalg.cholesky(sigma)
+    aug = CondNormal(cov=sigma, premap=cmap, noise=noise)  # float64 taken from the matrix
+    at = AugmentedTrajectory.from_trajectory(traj, kbt=0.6, augmenter=aug)
+    eps = (noise.reshape(-1, 30) @ chol.T).reshape(-1, 10, 3)
+    mean = oracle.apply_map(coords.astype(np.float64), cm)
+    scaled = np.linalg.solve(sigma, eps.reshape(-1, 30).T).T.reshape(-1, 10, 3)
+    want_c = np.concatenate([coords, mean + eps], axis=1)
+    back = np.einsum("cf,tcd->tfd", cm, scaled)
+    want_f = np.concatenate([forces + 0.6 * back, -0.6 * scaled], axis=1)
+    assert at.coords.dtype == np.float64 and rel_fro(at.coords, want_c) < 1e-12 and rel_fro(at.forces, want_f) < 1e-10
+    y = mean + eps
+    gx, gy = aug.log_gradient(coords, y)
+    assert rel_fro(gy, -scaled) < 1e-10 and rel_fro(gx, back) < 1e-10
+    # generated noise: independent of the slabs, and with the requested covariance
+    gen = CondNormal(cov=sigma, premap=cmap, seed=3)
+    dev = torch.as_tensor(coords, device="cuda")
+    whole = gen.augment_device(dev, None, 0.0, NoiseDraw(1, None))[0]
+    parts = torch.cat([gen.augment_device(dev[a0:a1], None, 0.0, NoiseDraw(1, None), frame0=a0)[0]
+                       for a0, a1 in [(0, 7), (7, 33), (33, len(coords))]])
+    assert float((whole - parts).abs().max()) < 1e-12 * float(whole.abs().max())  # same draw (GEMM shapes differ)
+    big = torch.zeros((20000, topo.n_sites, 3), dtype=torch.float64, device="cuda")
+    ys = gen.augment_device(big, None, 0.0, NoiseDraw(2, None))[0][:, topo.n_sites:].reshape(20000, 30)
+    emp = (ys.T @ ys / 20000).cpu().numpy()
+    assert np.abs(emp - sigma).max() < 0.05 * np.abs(sigma).max()
+    with pytest.raises(ValueError):
+        CondNormal(cov=np.eye(7), premap=cmap)
