@@ -50,7 +50,6 @@ constexpr int kI8MmaWarp = kI8FrameWarps + 1;         // TMEM allocation, MMA is
 constexpr int kI8Threads = (kI8FrameWarps + 2) * 32;
 constexpr int kI8MaxFramesPerCta = 8192;  // 5 products of at most 2^14 per row and level: 24 576 rows stay below 2^31
 constexpr int kI8SampleFrames = 4096;
-constexpr long long kI8Bias = 0x8080808080LL;
 constexpr uint32_t kI8Idesc = umma_idesc_i8(kI8M, kI8N);
 
 struct GramI8Params {
@@ -65,6 +64,8 @@ struct GramI8Params {
   const unsigned long long* colmax_bits;  // [n_red] max |group sum| of the sample, as double bits
   int32_t* leftover_count;
   int32_t* leftover;  // frame indices
+  long long* sums;    // [2][n_red][n_red] exact integer partial sums (see the epilogue), zeroed per call
+  double* side_slots; // [gridDim.x][kI8FrameWarps] partial sums of the (96, 96) element
   ChunkSchedule sch;
 };
 
@@ -322,11 +323,15 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int x = warp * 32 + lane;
       for (int c0 = 0; c0 < kI8N; c0 += 16) {
-        double g[16];
+        // The CTA's int32 accumulators are EXACT, and so are integer sums over CTAs and launches: the levels are
+        // packed into two int64 per element -- hi = 2^8 acc_0 + acc_1, lo = 2^16 acc_2 + 2^8 acc_3 + acc_4 -- and
+        // added with integer atomics, whose result does not depend on the order.  gram_i8_finalize_kernel turns
+        // them into float64 once per call: the Gram is bit-identical from run to run.
+        long long hi[16], lo[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) g[i] = 0.0;
+        for (int i = 0; i < 16; ++i) hi[i] = lo[i] = 0;
 #pragma unroll
-        for (int l = kI8Slices - 1; l >= 0; --l) {
+        for (int l = 0; l < kI8Slices; ++l) {
           uint32_t r[16];
           const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(l * kI8N + c0);
           asm volatile(
@@ -337,28 +342,57 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
               : "r"(taddr));
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 16; ++i) g[i] = g[i] * (1.0 / 256.0) + (double)(int32_t)r[i];  // Horner over the levels
+          for (int i = 0; i < 16; ++i) {
+            const long long a = (long long)(int32_t)r[i];
+            if (l < 2) hi[i] = hi[i] * 256 + a;
+            else lo[i] = lo[i] * 256 + a;
+          }
         }
         if (x < p.n_red) {
+          const int64_t nn = (int64_t)p.n_red * p.n_red;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int y = c0 + i;
             if (y >= p.n_red) continue;
-            const double v = ldexp(g[i], s_exp[x] + s_exp[y] - 14);
+            int64_t e;
             if (x < kI8N) {
-              if (y >= x) atomicAdd(p.gram + (int64_t)x * p.n_red + y, v);
+              if (y < x) continue;
+              e = (int64_t)x * p.n_red + y;
             } else {
-              atomicAdd(p.gram + (int64_t)y * p.n_red + x, v);  // row 96 of the operand = column 96 of the Gram
+              e = (int64_t)y * p.n_red + x;  // row 96 of the operand = column 96 of the Gram
             }
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.sums + e), (unsigned long long)hi[i]);
+            atomicAdd(reinterpret_cast<unsigned long long*>(p.sums + nn + e), (unsigned long long)lo[i]);
           }
         }
       }
     }
-    if (side_lane) atomicAdd(p.gram + (int64_t)kI8N * p.n_red + kI8N, ldexp(side, 2 * s_exp[kI8N] - 78));
+    if (side_lane) p.side_slots[blockIdx.x * kI8FrameWarps + warp] += side;  // this warp's slot: plain add
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == kI8MmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+}
+
+// Integer partial sums -> float64, once per call (thread = element of the upper triangle); the (96, 96) element
+// sums the per-warp side slots in a fixed order.
+__global__ void __launch_bounds__(256) gram_i8_finalize_kernel(const long long* __restrict__ sums,
+                                                               const double* __restrict__ side_slots, int n_slots,
+                                                               const unsigned long long* __restrict__ colmax_bits,
+                                                               int n_red, double* __restrict__ gram) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_red * n_red) return;
+  const int x = e / n_red, y = e - x * n_red;
+  if (y < x) return;
+  const int ex = column_exponent(colmax_bits[x]), ey = column_exponent(colmax_bits[y]);
+  if (x == kI8N && y == kI8N) {
+    double side = 0.0;
+    for (int i = 0; i < n_slots; ++i) side += side_slots[i];
+    gram[e] += ldexp(side, 2 * ex - 78);
+    return;
+  }
+  const double g = (double)sums[e] * (1.0 / 256.0) + (double)sums[(int64_t)n_red * n_red + e] * (1.0 / 4294967296.0);
+  gram[e] += ldexp(g, ex + ey - 14);
 }
 
 // Column maxima of the group sums over a sample of frames (thread = (frame, column)).
@@ -414,6 +448,9 @@ __global__ void __launch_bounds__(256) gram_leftover_kernel(const float* __restr
   }
 }
 
+constexpr int kI8SideSlots = 1024 * kI8FrameWarps;  // (CTA, frame warp) slots of the (96, 96) side sum: up to 1 024 SMs
+static size_t i8_ws_sums_offset(int64_t n_frames) { return (1024 + (size_t)n_frames * sizeof(int32_t) + 15) / 16 * 16; }
+
 static size_t gram_i8_smem(int n_sites, int n_red) {
   size_t off = (size_t)2 * kI8PanelBytes + 128 + 16 + kI8Cols * 4 + (size_t)(n_red + 1 + n_sites) * 4;
   off = (off + 127) / 128 * 128;
@@ -427,7 +464,7 @@ extern "C" size_t agf_gram_linear_i8_workspace_bytes(int32_t n_sites, int32_t n_
   using namespace agf;
   if (n_red < 1 || n_red > kI8N + 1 || n_frames < 1 || n_frames >= ((int64_t)1 << 31)) return 0;
   if (gram_i8_smem(n_sites, n_red) > (size_t)226 * 1024) return 0;
-  return 1024 + (size_t)n_frames * sizeof(int32_t);
+  return i8_ws_sums_offset(n_frames) + (size_t)2 * n_red * n_red * sizeof(long long) + kI8SideSlots * sizeof(double);
 }
 
 extern "C" int agf_gram_linear_i8(const void* forces, int dtype, int64_t n_frames, int32_t n_sites, const int32_t* col_ptr,
@@ -447,7 +484,11 @@ extern "C" int agf_gram_linear_i8(const void* forces, int dtype, int64_t n_frame
   unsigned long long* colmax = reinterpret_cast<unsigned long long*>(workspace);  // [128]
   int32_t* count = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + 1024 - 16);
   int32_t* leftover = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(workspace) + 1024);
+  long long* sums = reinterpret_cast<long long*>(reinterpret_cast<char*>(workspace) + i8_ws_sums_offset(n_frames));
+  double* side_slots = reinterpret_cast<double*>(sums + (size_t)2 * n_red * n_red);
   AGF_CUDA_TRY(cudaMemsetAsync(workspace, 0, 1024, s));
+  AGF_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)2 * n_red * n_red * sizeof(long long) +
+                                            (size_t)sm_count() * kI8FrameWarps * sizeof(double), s));
   const float* f = reinterpret_cast<const float*>(forces);
   const int64_t sample = n_frames < kI8SampleFrames ? n_frames : kI8SampleFrames;
   gram_i8_sample_kernel<<<(int)((sample * n_red + 255) / 256), 256, 0, s>>>(f, sample, n_sites, col_ptr, col_sites, n_red,
@@ -464,6 +505,7 @@ extern "C" int agf_gram_linear_i8(const void* forces, int dtype, int64_t n_frame
   else if (w0 >= 1 && w0 <= 2 && w1 >= 1 && w1 <= 2 && w2 >= 1 && w2 <= 2 && w3 >= 1 && w3 <= 2) kern = gram_i8_kernel<2, 2, 2, 2>;
   AGF_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int sms = sm_count();
+  AGF_REQUIRE(sms * kI8FrameWarps <= kI8SideSlots, "agf_gram_linear_i8: more SMs than side slots");
   const int64_t slab = (int64_t)sms * kI8MaxFramesPerCta;  // int32 accumulators: bounded rows per CTA and launch
   for (int64_t f0 = 0; f0 < n_frames; f0 += slab) {
     GramI8Params p;
@@ -479,12 +521,16 @@ extern "C" int agf_gram_linear_i8(const void* forces, int dtype, int64_t n_frame
     p.colmax_bits = colmax;
     p.leftover_count = count;
     p.leftover = leftover;
+    p.sums = sums;
+    p.side_slots = side_slots;
     p.sch = make_schedule(p.forces, p.n_frames, (int64_t)n_sites * 12, kI8SubFrames);
     const int64_t want = (p.sch.n_chunks + 1) / 2;
     const int ctas = (int)(want < sms ? (want < 1 ? 1 : want) : sms);
     kern<<<ctas, kI8Threads, smem, s>>>(p);
     AGF_CUDA_TRY(cudaGetLastError());
   }
+  gram_i8_finalize_kernel<<<(n_red * n_red + 255) / 256, 256, 0, s>>>(sums, side_slots, sms * kI8FrameWarps, colmax, n_red, gram);
+  AGF_CUDA_TRY(cudaGetLastError());
   gram_leftover_kernel<<<sms, 256, 0, s>>>(f, 0, n_sites, col_ptr, col_sites, n_red, count, leftover, gram);
   AGF_CUDA_TRY(cudaGetLastError());
   return AGF_OK;

@@ -163,6 +163,31 @@ def _equality_rows(coord_map: LinearMap, cols: np.ndarray, n_red: int) -> np.nda
     return np.asarray((onehot.T @ cmat.T).T)
 
 
+_EQ_ROWS_CACHE: dict = {}
+
+
+def _equality_rows_cached(coord_map: LinearMap, cols: np.ndarray, n_red: int, want_device: bool):
+    """``(A, A on the device or None)`` for large fits: building ``A = cmap C`` (a sparse product over a 500 x 5 000
+    map) and uploading its 10 MB cost 8 ms per call at the config-4 shape; both are functions of the coordinate
+    map's content and the column table only.  The key reuses the content digest the map's own compile step took
+    a moment ago (``LinearMap._compile``), so an edited map misses."""
+    compiled = getattr(coord_map, "_compiled", None)
+    digest = compiled[0] if compiled is not None and isinstance(compiled[0], bytes) and compiled[0] != b"device-fit" else None
+    if digest is None or not isinstance(coord_map, LinearMap):
+        a_mat = _equality_rows(coord_map, cols, n_red)
+        return a_mat, (_engine.dev_f64(a_mat) if want_device else None)
+    key = (digest, hash(np.ascontiguousarray(cols).tobytes()), int(n_red), _engine.device().index)
+    hit = _EQ_ROWS_CACHE.get(key)
+    if hit is None:
+        if len(_EQ_ROWS_CACHE) > 8:
+            _EQ_ROWS_CACHE.clear()
+        a_mat = _equality_rows(coord_map, cols, n_red)
+        hit = _EQ_ROWS_CACHE[key] = [a_mat, None]
+    if want_device and hit[1] is None:
+        hit[1] = torch.as_tensor(hit[0], device=_engine.device())
+    return hit[0], hit[1]
+
+
 class _SmallFitPlan:
     """Everything about a small device-side fit that depends only on (coordinate map, constraints, l2):
     column order, CSR of the groups, equality rows, index maps of the QP kernel's outputs and the
@@ -267,11 +292,11 @@ def qp_linear_map(
             qp_mat.diagonal().add_(torch.as_tensor(l2_regularization * group_size, device=qp_mat.device))
         else:
             qp_mat[np.diag_indices(n_red)] += l2_regularization * group_size
-    a_mat = _equality_rows(coord_map, cols, n_red)
+    a_mat, a_dev = _equality_rows_cached(coord_map, cols, n_red, on_device)
     if backend == "exact":
         sol = None
         if on_device:
-            sol = solve_equality_qp_device(qp_mat, a_mat, np.eye(coord_map.n_cg_sites), keep_on_device=True)
+            sol = solve_equality_qp_device(qp_mat, a_dev, np.eye(coord_map.n_cg_sites), keep_on_device=True)
             if sol is not None:
                 # the solution is the coefficient operand of kernel (d) up to a row permutation: the fitted map
                 # is applied from the device, its 20 MB host form (500 x 5 000) only exists if somebody asks

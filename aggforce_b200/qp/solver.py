@@ -77,7 +77,7 @@ def solve_equality_qp_device(P, A, b, keep_on_device: bool = False):
     downloading it -- the fitted map of a large problem is applied from where it is."""
     import torch
 
-    a = torch.as_tensor(np.asarray(A, dtype=np.float64), device=P.device)
+    a = A if isinstance(A, torch.Tensor) else torch.as_tensor(np.asarray(A, dtype=np.float64), device=P.device)
     rhs = torch.as_tensor(np.asarray(b, dtype=np.float64), device=P.device)
     vec = rhs.ndim == 1
     if vec:

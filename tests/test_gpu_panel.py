@@ -438,6 +438,9 @@ def test_gram_i8_matches_the_float64_oracle():
     assert "agf_gram_linear_i8" in names and _lib.LAUNCHES["count"] > n0
     assert rel_fro(got, ref) < 1e-9
     assert rel_fro(got, ref) < 1e-10  # what the scheme delivers on this data
+    # exact integer accumulation across CTAs and launches: bit-identical from run to run
+    for _ in range(3):
+        assert np.array_equal(_gram_caller_order(forces, cols, n_red, True), got)
     assert rel_fro(_gram_caller_order(forces, cols, n_red, False), ref) < 1e-13  # the FP64 DMMA kernel
     # an unaligned device view (frames 3..) and a smaller system (n_red < 96: no ride-along column)
     dev = torch.as_tensor(forces, device="cuda")
