@@ -10,6 +10,8 @@
 // drawn in-kernel from Philox keyed by (seed, global frame, bead, draw id), so slabs of frames and
 // ranks reproduce the same noise without communicating.  Arithmetic in f64, stored in the array
 // dtype.  HBM bound: 24 n_fg bytes read, 24 (n_fg + n_cg) written per frame (f32).
+#include <stdlib.h>
+
 #include "philox.cuh"
 
 namespace agf {
@@ -111,6 +113,90 @@ __global__ void __launch_bounds__(256) augment_kernel(const __grid_constant__ Au
   }
 }
 
+// Row-wise variant (one CTA per frame, grid-stride): the site part of both arrays is a 16-byte vector copy into
+// the wider output rows, the noise of a frame is drawn once into shared memory, and only the sites that carry a
+// bead (the rows of A^T with an entry) are revisited for the force correction -- same float64 arithmetic and the
+// same rounding as augment_kernel, at copy bandwidth instead of three 4-byte accesses per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) augment_rows_kernel(const __grid_constant__ AugmentParams p) {
+  extern __shared__ __align__(16) unsigned char ar_smem[];
+  double* s_eps = reinterpret_cast<double*>(ar_smem);                        // [n_cg][3]
+  int32_t* s_touched = reinterpret_cast<int32_t*>(s_eps + (size_t)p.n_cg * 3);  // sites with a row in A^T
+  __shared__ int n_touched;
+  if (threadIdx.x == 0) n_touched = 0;
+  __syncthreads();
+  for (int s = threadIdx.x; s < p.n_sites; s += blockDim.x)
+    if (__ldg(p.site_ptr + s + 1) > __ldg(p.site_ptr + s)) s_touched[atomicAdd(&n_touched, 1)] = s;
+  const int n_all = p.n_sites + p.n_cg;
+  const T* coords = reinterpret_cast<const T*>(p.coords);
+  const T* forces = reinterpret_cast<const T*>(p.forces);
+  T* oc = reinterpret_cast<T*>(p.out_coords);
+  T* of = reinterpret_cast<T*>(p.out_forces);
+  const int n_vec = (int)((size_t)p.n_sites * 3 * sizeof(T) / 16);
+  for (int64_t t = blockIdx.x; t < p.n_frames; t += gridDim.x) {
+    __syncthreads();  // previous frame's readers of s_eps are done (and the touched list is complete)
+    for (int c = threadIdx.x; c < p.n_cg; c += blockDim.x) {
+      double eps[3];
+      bead_noise<T>(p, t, c, eps);
+      s_eps[3 * c] = eps[0];
+      s_eps[3 * c + 1] = eps[1];
+      s_eps[3 * c + 2] = eps[2];
+    }
+    const int64_t in_frame = t * (int64_t)p.n_sites * 3, out_frame = t * (int64_t)n_all * 3;
+    if (oc) {
+      const uint4* src = reinterpret_cast<const uint4*>(coords + in_frame);
+      uint4* dst = reinterpret_cast<uint4*>(oc + out_frame);
+      for (int i = threadIdx.x; i < n_vec; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (of) {
+      const uint4* src = reinterpret_cast<const uint4*>(forces + in_frame);
+      uint4* dst = reinterpret_cast<uint4*>(of + out_frame);
+      for (int i = threadIdx.x; i < n_vec; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    if (of) {
+      for (int i = threadIdx.x; i < n_touched; i += blockDim.x) {
+        const int s = s_touched[i];
+        const T* f = forces + in_frame + 3 * s;
+        double v[3] = {to_f64(__ldg(f)), to_f64(__ldg(f + 1)), to_f64(__ldg(f + 2))};
+        for (int k = __ldg(p.site_ptr + s); k < __ldg(p.site_ptr + s + 1); ++k) {
+          const double* eps = s_eps + 3 * __ldg(p.site_beads + k);
+          const double w = p.kbt_over_var * __ldg(p.site_w + k);
+          v[0] = fma(w, eps[0], v[0]);
+          v[1] = fma(w, eps[1], v[1]);
+          v[2] = fma(w, eps[2], v[2]);
+        }
+        T* o = of + out_frame + 3 * s;
+        o[0] = static_cast<T>(v[0]);
+        o[1] = static_cast<T>(v[1]);
+        o[2] = static_cast<T>(v[2]);
+      }
+    }
+    for (int c = threadIdx.x; c < p.n_cg; c += blockDim.x) {
+      const double* eps = s_eps + 3 * c;
+      const int64_t o = out_frame + 3 * (int64_t)(p.n_sites + c);
+      if (oc) {
+        double m[3] = {0.0, 0.0, 0.0};
+        for (int k = __ldg(p.bead_ptr + c); k < __ldg(p.bead_ptr + c + 1); ++k) {
+          const T* x = coords + in_frame + 3 * __ldg(p.bead_sites + k);
+          const double w = __ldg(p.bead_w + k);
+          m[0] = fma(w, to_f64(__ldg(x)), m[0]);
+          m[1] = fma(w, to_f64(__ldg(x + 1)), m[1]);
+          m[2] = fma(w, to_f64(__ldg(x + 2)), m[2]);
+        }
+        oc[o] = static_cast<T>(m[0] + eps[0]);
+        oc[o + 1] = static_cast<T>(m[1] + eps[1]);
+        oc[o + 2] = static_cast<T>(m[2] + eps[2]);
+      }
+      if (of) {
+        of[o] = static_cast<T>(-p.kbt_over_var * eps[0]);
+        of[o + 1] = static_cast<T>(-p.kbt_over_var * eps[1]);
+        of[o + 2] = static_cast<T>(-p.kbt_over_var * eps[2]);
+      }
+    }
+  }
+}
+
 }  // namespace agf
 
 extern "C" int agf_gauss_augment(const void* coords, const void* forces, int dtype, int64_t n_frames, int32_t n_sites,
@@ -149,6 +235,24 @@ extern "C" int agf_gauss_augment(const void* coords, const void* forces, int dty
   const int64_t want = (total + 255) / 256;
   const int blocks = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  // rows of both the input and the output are whole 16-byte vectors: the row-wise kernel applies
+  const size_t elem = dtype == AGF_F32 ? 4 : 8;
+  const size_t rows_smem = (size_t)n_cg * 3 * sizeof(double) + (size_t)n_sites * sizeof(int32_t);
+  auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0; };
+  if (((size_t)n_sites * 3 * elem) % 16 == 0 && ((size_t)(n_sites + n_cg) * 3 * elem) % 16 == 0 && aligned(coords) &&
+      aligned(forces) && aligned(out_coords) && aligned(out_forces) && rows_smem <= (size_t)200 * 1024 &&
+      getenv("AGF_AUGMENT_ROWS_OFF") == nullptr) {
+    const int rblocks = (int)(n_frames < (int64_t)sm_count() * 8 ? n_frames : (int64_t)sm_count() * 8);
+    if (dtype == AGF_F32) {
+      AGF_CUDA_TRY(cudaFuncSetAttribute(augment_rows_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+      augment_rows_kernel<float><<<rblocks, 256, rows_smem, s>>>(p);
+    } else {
+      AGF_CUDA_TRY(cudaFuncSetAttribute(augment_rows_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+      augment_rows_kernel<double><<<rblocks, 256, rows_smem, s>>>(p);
+    }
+    AGF_CUDA_TRY(cudaGetLastError());
+    return AGF_OK;
+  }
   if (dtype == AGF_F32) augment_kernel<float><<<blocks, 256, 0, s>>>(p);
   else augment_kernel<double><<<blocks, 256, 0, s>>>(p);
   AGF_CUDA_TRY(cudaGetLastError());

@@ -420,3 +420,39 @@ def test_condnormal_full_covariance(topo, data):
     assert np.abs(emp - sigma).max() < 0.05 * np.abs(sigma).max()
     with pytest.raises(ValueError):
         CondNormal(cov=np.eye(7), premap=cmap)
+
+
+def test_gauss_augment_row_kernel_equals_the_per_site_kernel(monkeypatch):
+    """Systems whose frame rows are whole 16-byte vectors (config 5: 2 000 + 200 sites) take the row-wise
+    augmentation kernel: bit-identical to the per-site kernel (same Philox draw, same float64 arithmetic), for both
+    dtypes, with a site that belongs to two beads, and equal to the numpy closed form for an injected draw."""
+    from aggforce_b200 import LinearMap
+    from aggforce_b200.trajectory import CondNormal
+    from aggforce_b200.trajectory.gausstraj import NoiseDraw
+
+    rng = np.random.default_rng(12)
+    n_sites, n_cg, n_frames = 176, 12, 301
+    groups = [[int(i) for i in rng.choice(n_sites, size=rng.integers(1, 4), replace=False)] for _ in range(n_cg)]
+    groups[3].append(groups[2][0])  # one site in two beads: two corrections on one force
+    mat = np.zeros((n_cg, n_sites))
+    for c, g in enumerate(groups):
+        mat[c, g] = rng.uniform(0.2, 1.0, size=len(g))
+    cmap = LinearMap(mat)
+    for dtype in (np.float32, np.float64):
+        coords = rng.normal(0, 5, size=(n_frames, n_sites, 3)).astype(dtype)
+        forces = rng.normal(0, 40, size=(n_frames, n_sites, 3)).astype(dtype)
+        dc, df = torch.as_tensor(coords, device="cuda"), torch.as_tensor(forces, device="cuda")
+        aug = CondNormal(cov=0.3, premap=cmap, seed=5, dtype=dtype)
+        oc, of = aug.augment_device(dc, df, 0.7, NoiseDraw(1, None), frame0=40)
+        monkeypatch.setenv("AGF_AUGMENT_ROWS_OFF", "1")
+        oc0, of0 = aug.augment_device(dc, df, 0.7, NoiseDraw(1, None), frame0=40)
+        monkeypatch.delenv("AGF_AUGMENT_ROWS_OFF")
+        assert torch.equal(oc, oc0) and torch.equal(of, of0)
+        only_f = aug.augment_device(None, df, 0.7, NoiseDraw(1, None), frame0=40)[1]
+        assert torch.equal(only_f, of)
+        noise = rng.standard_normal((n_frames, n_cg, 3)).astype(dtype)
+        inj = CondNormal(cov=0.3, premap=cmap, noise=noise, dtype=dtype)
+        ic, jf = inj.augment_device(dc, df, 0.7, inj.new_draw())
+        rc, rf = oracle.gauss_augment(coords, forces, mat, 0.3, 0.7, noise)
+        tol = 1e-6 if dtype == np.float32 else 1e-12
+        assert rel_fro(ic.cpu().numpy(), rc) < tol and rel_fro(jf.cpu().numpy(), rf) < tol
