@@ -443,12 +443,24 @@ def _fit_fused(traj, coord_map, featurizer, plan, kbt, n_constraint_frames, cons
     if on_device:
         # all beads at once: equality rows stay on the device (single GPU), one batched Cholesky / Schur solve,
         # one read for the checks -- the per-bead loop below is the fallback when any bead's solve declines
-        dev_rows = not _engine.sharded()
-        a_all = [chosen.rows(b, lambda idx, b=b: ctx.constraint_rows(coords, b, idx, on_device=dev_rows), n_cg)
-                 for b in range(n_cg)]
+        if _engine.sharded():
+            # every rank evaluates the rows of the chosen frames it owns, for all beads, into one zero-filled
+            # device array: ONE sum over the ranks instead of two host collectives per bead
+            n_sel_all = int(chosen.picks.shape[1])
+            a_dev = torch.zeros((n_cg, n_sel_all, n_cg, n_feat), dtype=torch.float64, device=grams.device)
+            for b in range(n_cg):
+                glob = chosen.picks[b]
+                mine = np.nonzero((glob >= chosen.offset) & (glob < chosen.offset + chosen.n_local))[0]
+                if mine.size:
+                    local = ctx.constraint_rows(coords, b, glob[mine] - chosen.offset, on_device=True)
+                    a_dev[b, torch.as_tensor(mine, device=grams.device)] = local.reshape(mine.size, n_cg, n_feat)
+            a_dev = _engine.allreduce_sum_(a_dev).reshape(n_cg, n_sel_all * n_cg, n_feat)
+            a_all = list(a_dev)
+        else:
+            a_all = [chosen.rows(b, lambda idx, b=b: ctx.constraint_rows(coords, b, idx, on_device=True), n_cg)
+                     for b in range(n_cg)]
         if len({tuple(a.shape) for a in a_all}) == 1:
-            a_dev = torch.stack([a if isinstance(a, torch.Tensor) else torch.as_tensor(a, device=grams.device)
-                                 for a in a_all])
+            a_dev = torch.stack(list(a_all))
             n_sel = a_dev.shape[1] // n_cg
             rhs = torch.zeros((n_cg, n_sel, n_cg), dtype=torch.float64, device=grams.device)
             rhs[torch.arange(n_cg), :, torch.arange(n_cg)] = 1.0
