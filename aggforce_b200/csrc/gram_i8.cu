@@ -374,23 +374,32 @@ __global__ void __launch_bounds__(kI8Threads, 1) gram_i8_kernel(const __grid_con
   if (warp == kI8MmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
 }
 
-// Integer partial sums -> float64, once per call (thread = element of the upper triangle); the (96, 96) element
-// sums the per-warp side slots in a fixed order.
+// Integer partial sums -> float64, once per call (thread = element of the upper triangle).  The LAST block sums the
+// per-warp side slots of the (96, 96) element in a fixed order (strided partial sums per thread, then thread 0 over
+// the 256 partials): deterministic like the rest.
 __global__ void __launch_bounds__(256) gram_i8_finalize_kernel(const long long* __restrict__ sums,
                                                                const double* __restrict__ side_slots, int n_slots,
                                                                const unsigned long long* __restrict__ colmax_bits,
                                                                int n_red, double* __restrict__ gram) {
+  if (blockIdx.x == gridDim.x - 1) {
+    if (n_red <= kI8N) return;
+    __shared__ double part[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_slots; i += 256) acc += side_slots[i];
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double side = 0.0;
+      for (int i = 0; i < 256; ++i) side += part[i];
+      gram[(int64_t)kI8N * n_red + kI8N] += ldexp(side, 2 * column_exponent(colmax_bits[kI8N]) - 78);
+    }
+    return;
+  }
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_red * n_red) return;
   const int x = e / n_red, y = e - x * n_red;
-  if (y < x) return;
+  if (y < x || (x == kI8N && y == kI8N)) return;
   const int ex = column_exponent(colmax_bits[x]), ey = column_exponent(colmax_bits[y]);
-  if (x == kI8N && y == kI8N) {
-    double side = 0.0;
-    for (int i = 0; i < n_slots; ++i) side += side_slots[i];
-    gram[e] += ldexp(side, 2 * ex - 78);
-    return;
-  }
   const double g = (double)sums[e] * (1.0 / 256.0) + (double)sums[(int64_t)n_red * n_red + e] * (1.0 / 4294967296.0);
   gram[e] += ldexp(g, ex + ey - 14);
 }
@@ -529,7 +538,7 @@ extern "C" int agf_gram_linear_i8(const void* forces, int dtype, int64_t n_frame
     kern<<<ctas, kI8Threads, smem, s>>>(p);
     AGF_CUDA_TRY(cudaGetLastError());
   }
-  gram_i8_finalize_kernel<<<(n_red * n_red + 255) / 256, 256, 0, s>>>(sums, side_slots, sms * kI8FrameWarps, colmax, n_red, gram);
+  gram_i8_finalize_kernel<<<(n_red * n_red + 255) / 256 + 1, 256, 0, s>>>(sums, side_slots, sms * kI8FrameWarps, colmax, n_red, gram);
   AGF_CUDA_TRY(cudaGetLastError());
   gram_leftover_kernel<<<sms, 256, 0, s>>>(f, 0, n_sites, col_ptr, col_sites, n_red, count, leftover, gram);
   AGF_CUDA_TRY(cudaGetLastError());
