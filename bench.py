@@ -506,7 +506,8 @@ def main() -> None:
 def config_probes(agf, _engine, _lib, torch, dist, rank, world, peaks, hbm_peak, kernel_times, topo, cmap,
                   protein_like_topology, synth_trajectory_device) -> dict:
     """Short runs of BASELINE configs 3, 4 and 5: wall time of the public call (CUDA events, max over
-    ranks) and the roofline fraction of every kernel with a defined algorithmic cost."""
+    ranks, median of three calls after one warm-up call) and the roofline fraction of every kernel with a
+    defined algorithmic cost."""
     from aggforce_b200.qp import Multifeaturize, gb_feat, id_feat, qp_feat_linear_map
     from aggforce_b200.qp.qplinear import reduced_columns
     from aggforce_b200.util import Curry
@@ -516,15 +517,18 @@ def config_probes(agf, _engine, _lib, torch, dist, rank, world, peaks, hbm_peak,
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), out
+        times, out = [], None
+        for _ in range(3):  # median of three timed calls (max over ranks each): one hiccup does not make the number
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            times.append(float(ms.item()))
+        return float(np.median(times)), out
 
     out = {}
     # ---- config 3: featurised fit, cln025, id_feat + gb_feat(0, 8, 1, n_basis=7), l2 = 1e3
