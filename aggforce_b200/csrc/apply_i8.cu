@@ -231,22 +231,28 @@ __global__ void __launch_bounds__(kA_Threads, 1) i8a_gemm_kernel(const __grid_co
       acc_phase ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       for (int c0 = 0; c0 < kA_N; c0 += 16) {  // 16 frames of one xyz component
-        double g[16];
+        // the five levels of 16 columns: loads issued back to back, ONE wait; the levels are combined in integers
+        // first (hi = 2^8 acc_0 + acc_1, lo = 2^16 acc_2 + 2^8 acc_3 + acc_4: exact in int64), so that two
+        // int64 -> float64 conversions per element replace five -- the accumulators are free again sooner
+        uint32_t r[kT_Slices][16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) g[i] = 0.0;
-#pragma unroll
-        for (int l = kT_Slices - 1; l >= 0; --l) {
-          uint32_t r[16];
+        for (int l = 0; l < kT_Slices; ++l) {
           const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(l * kA_N + c0);
           asm volatile(
               "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              : "=r"(r[l][0]), "=r"(r[l][1]), "=r"(r[l][2]), "=r"(r[l][3]), "=r"(r[l][4]), "=r"(r[l][5]), "=r"(r[l][6]),
+                "=r"(r[l][7]), "=r"(r[l][8]), "=r"(r[l][9]), "=r"(r[l][10]), "=r"(r[l][11]), "=r"(r[l][12]), "=r"(r[l][13]),
+                "=r"(r[l][14]), "=r"(r[l][15])
               : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        double g[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) g[i] = g[i] * (1.0 / 256.0) + (double)(int32_t)r[i];  // Horner over the levels
+        for (int i = 0; i < 16; ++i) {
+          const long long hi = (long long)(int32_t)r[0][i] * 256 + (long long)(int32_t)r[1][i];
+          const long long lo = ((long long)(int32_t)r[2][i] * 256 + (long long)(int32_t)r[3][i]) * 256 + (long long)(int32_t)r[4][i];
+          g[i] = (double)hi * (1.0 / 256.0) + (double)lo * (1.0 / 4294967296.0);
         }
         if (c0 + 16 >= kA_N) {  // last column group read: the accumulators may be overwritten
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

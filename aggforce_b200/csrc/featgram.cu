@@ -942,7 +942,7 @@ extern "C" int agf_gram_feat_i8(const void* coords, const void* forces, int dtyp
     l.digits = digits;
     l.n_chunks = 3 * n_fb;
     l.n_red = p.n_feat;
-    l.slice_chunks = 64;  // 10 beads x 37 tiles share a slice: keep the slice of all beads inside L2
+    l.slice_chunks = 0;  // default (256): measured 17.1 / 15.5 / 14.8 / 14.4 ms per 50 k frames at 32 / 64 / 128 / 256
     l.n_batch = n_cg;
     l.digits_batch_stride = L.bead_stride;
     l.pow2 = pow2;
