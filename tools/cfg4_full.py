@@ -2,7 +2,7 @@
 the trajectory (75 GB per array) is never materialised -- SynthFrames regenerate slabs of frames
 from the counter-based generator for every pass (constraint detection, Gram, two applications)."""
 import sys, time
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import numpy as np, torch
 import aggforce_b200 as agf
 from aggforce_b200 import _lib
@@ -47,8 +47,9 @@ print("  entry points [ms]:", ", ".join(f"{n} {ms:.0f}" for n, ms in sorted(agg.
 print("  constraints", len(res["constraints"]), "== topology:", res["constraints"] == topo.xh_constraints,
       " residual", res["residual"], " mapped forces", tuple(res["mapped_forces"].shape), res["mapped_forces"].dtype)
 flop = (3 * 2600 * 2601 + 3 * 5000) * T
-g = agg.get("agf_gram_linear_ws", 0.0)
-if g: print(f"  Gram: {g:.0f} ms = {flop / g / 1e9:.1f} TFLOP/s ({flop / g / 1e9 / 37.15 * 100:.1f}% of DMMA peak)")
+for name in ("agf_gram_linear_ws", "agf_gram_linear_i8t"):
+    g = agg.get(name, 0.0)
+    if g: print(f"  Gram ({name}): {g:.0f} ms = {flop / g / 1e9:.1f} float64-equivalent TFLOP/s ({flop / g / 1e9 / 37.15 * 100:.0f}% of the DMMA peak)")
 print("  peak memory allocated: %.1f GB" % (torch.cuda.max_memory_allocated() / 1e9))
 if world > 1:
     w = torch.as_tensor(np.ascontiguousarray(res["tmap"].force_map.standard_matrix), device="cuda")
