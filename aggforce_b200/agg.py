@@ -146,6 +146,7 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
         status = np.array([st[0], st[1], st[3], st[4]])
         if pend is not None:
             fm._matrix = pend.resolve(got[1])  # raises ValueError("Map optimization failed.") like the host path
+            fm._adopt_device_fit()
         if pend is not None and pend.fell_back:
             # the device solve declined (P or the Schur complement not positive definite): the host
             # solution replaces the map and the force application is redone with it

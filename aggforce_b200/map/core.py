@@ -123,7 +123,16 @@ class LinearMap:
     def _standard_matrix(self) -> np.ndarray:
         if self._matrix is None:  # first host access to a device fit: one synchronising read
             self._matrix = self._pending.matrix()
+            self._adopt_device_fit()
         return self._matrix
+
+    def _adopt_device_fit(self) -> None:
+        """The host copy of a device fit has just been materialised: fingerprint it NOW, while it still equals
+        the coefficients on the device, so that an in-place edit made before the next application is seen."""
+        if self._matrix is not None and self._compiled is not None and self._compiled[0] == b"device-fit":
+            m = self._matrix
+            digest = _fingerprint(m) + repr((m.shape, str(m.dtype), bool(self.handle_nans))).encode()
+            self._compiled = (digest, self._compiled[1])
 
     @_standard_matrix.setter
     def _standard_matrix(self, value: np.ndarray) -> None:
@@ -170,9 +179,6 @@ class LinearMap:
         else:
             digest = self._frozen_digest
         digest += repr((m.shape, str(m.dtype), bool(self.handle_nans))).encode()
-        if self._compiled is not None and self._compiled[0] == b"device-fit":
-            # the downloaded matrix of a device fit: adopt its digest, keep the device copy
-            self._compiled = (digest, self._compiled[1])
         if self._compiled is not None and self._compiled[0] != digest:
             self._column_labels = None  # matrix was edited in place: the fit's column structure is stale
         if self._compiled is None or self._compiled[0] != digest:

@@ -252,3 +252,20 @@ def test_i8_apply_is_what_a_large_linear_map_uses():
     assert rel_fro(out, oracle.apply_map(forces, w)) < 1e-9
     mapped, sumsq = lm.apply_with_sumsq(torch.as_tensor(forces, device="cuda"))
     assert abs(sumsq / float((mapped.double() ** 2).sum().item()) - 1) < 1e-12
+
+
+def test_tiled_gram_with_a_reordered_column_table():
+    """98 <= n_red <= 128: the plan orders the columns by group size (the DMMA kernel's layout), the tiled kernel
+    takes them as they come and gram_linear maps the result back to the caller's order."""
+    from aggforce_b200 import _engine, _lib
+
+    n_sites, n_frames = 131, 3000
+    forces, cons, _, _, n_red = _case(n_sites, 9, n_frames, 21)
+    assert 98 <= n_red <= 128
+    cols = oracle.group_columns(n_sites, cons)
+    _lib.timing(True)
+    gram = _engine.gram_linear(_engine.Frames(forces), cols, n_red)
+    names = {n for n, _ in _lib.timing_records()}
+    _lib.timing(False)
+    assert "agf_gram_linear_i8t" in names
+    assert rel_fro(gram.cpu().numpy(), oracle.gram_linear(forces, cons)) < 1e-9

@@ -397,6 +397,23 @@ def test_device_fit_is_lazy_and_editable():
     fm.standard_matrix[1, 3] += 2.0
     assert rel_fro(fm(forces), oracle.apply_map(forces, fm.standard_matrix)) < 1e-9
     assert rel_fro((2.0 * fm).standard_matrix, 2.0 * fm.standard_matrix) < 1e-15
+    # an edit made BEFORE the fitted map is applied for the first time must be seen too
+    res = project_forces(coords=coords, forces=forces, coord_map=cmap, constrained_inds=cons, l2_regularization=10.0)
+    fm = res["tmap"].force_map
+    fm.standard_matrix[2, 7] -= 1.5
+    assert rel_fro(fm(forces), oracle.apply_map(forces, fm.standard_matrix)) < 1e-9
+    # ... also for a large fit, whose coefficients stay on the device until somebody asks
+    from aggforce_b200.synth import protein_like_topology, synth_trajectory_host
+
+    topo = protein_like_topology(130)
+    c2, f2 = synth_trajectory_host(topo, 64, seed=5)
+    cm2 = LinearMap([[i] for i in topo.bead_atoms], n_fg_sites=topo.n_sites)
+    big = project_forces(coords=c2, forces=f2, coord_map=cm2, constrained_inds=topo.xh_constraints,
+                         l2_regularization=10.0)["tmap"].force_map
+    assert big._matrix is None  # n_red >= 512: device solve, nothing downloaded yet
+    m = big.standard_matrix
+    m[0, 0] += 3.0
+    assert rel_fro(big(f2), oracle.apply_map(f2, m)) < 1e-9
 
 
 # --------------------------------------------------------------------------------------
