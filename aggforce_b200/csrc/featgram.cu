@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256) feat_digits_kernel(const __grid_constant_
   const bool live = warp < nf;  // warp = frame of the group
   const int fb = (int)(fg >> 2), kg = (int)(fg & 3);
   int buf = 0;
-  for (int pass = 0; pass < n_pad / kT_PanelCols; ++pass, buf ^= 1) {
+  for (int pass = 0; pass < (n_pad + kT_PanelCols - 1) / kT_PanelCols; ++pass, buf ^= 1) {
     if (SAMPLE) {
       if (threadIdx.x < kT_PanelCols) s_max[threadIdx.x] = 0ull;
       __syncthreads();
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(256) feat_digits_kernel(const __grid_constant_
     }
     if (SAMPLE) {
       __syncthreads();
-      if (threadIdx.x < kT_PanelCols) {
+      if (threadIdx.x < kT_PanelCols && pass * kT_PanelCols + (int)threadIdx.x < n_pad) {
         const size_t x = (size_t)bead * n_pad + pass * kT_PanelCols + threadIdx.x;
         if (q.gmax != nullptr)
           q.gmax[(size_t)blockIdx.x * p.n_cg * n_pad + x] = __longlong_as_double((long long)s_max[threadIdx.x]);
@@ -558,6 +558,7 @@ __global__ void __launch_bounds__(256) feat_digits_kernel(const __grid_constant_
       const int qq = idx & (kT_ItemFrames - 1);
       const int xb = (idx >> 3) & (kT_PanelCols / 16 - 1), ds = idx >> 6;
       const int gxb = pass * (kT_PanelCols / 16) + xb;
+      if (gxb >= q.n_xb) continue;  // n_pad need not be a multiple of 128 (e.g. 288 for 200 columns)
       const uint4 v = *reinterpret_cast<const uint4*>(tile + (size_t)(ds * (kT_PanelCols / 16) + xb) * kT_TileXb + qq * 16);
       const int d = ds / kT_Slices, s = ds - d * kT_Slices;
       *reinterpret_cast<uint4*>(out + i8t_row_offset<kGramLayout>(q.n_xb, fb, d, s, gxb, kg) + qq * 16) = v;

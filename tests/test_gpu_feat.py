@@ -317,11 +317,11 @@ def test_project_forces_with_gaussian_methods(topo, data):
 # --------------------------------------------------------------------------------------
 # featurised Gram on the tensor cores (agf_gram_feat_i8: int8 digit planes, batched tcgen05 SYRK)
 # --------------------------------------------------------------------------------------
-def _feat_grams(coords, forces, topo, use_i8, min_frames=None):
+def _feat_grams(coords, forces, topo, use_i8, min_frames=None, featurizer=None):
     from aggforce_b200 import _engine, _lib
     from aggforce_b200.qp.featlinearmap import _FusedContext, _fusable
 
-    ctx = _FusedContext(_cmap(topo), topo.xh_constraints, _fusable(_featurizer()))
+    ctx = _FusedContext(_cmap(topo), topo.xh_constraints, _fusable(featurizer or _featurizer()))
     old = (_engine._GRAM_I8[0], _engine._GRAM_I8T_MIN_FRAMES)
     _engine._GRAM_I8[0] = use_i8
     if min_frames is not None:
@@ -456,3 +456,19 @@ def test_gauss_augment_row_kernel_equals_the_per_site_kernel(monkeypatch):
         rc, rf = oracle.gauss_augment(coords, forces, mat, 0.3, 0.7, noise)
         tol = 1e-6 if dtype == np.float32 else 1e-12
         assert rel_fro(ic.cpu().numpy(), rc) < tol and rel_fro(jf.cpu().numpy(), rf) < tol
+
+
+def test_feat_gram_i8_with_a_padded_width_that_is_no_multiple_of_128(topo):
+    """n_basis = 4: 481 features per bead -> 576 padded columns (six 96-column blocks, 4.5 row blocks): the
+    last 128-column pass of the digits kernel is partial."""
+    from aggforce_b200.qp import Multifeaturize, gb_feat, id_feat
+    from aggforce_b200.synth import synth_trajectory_host
+    from aggforce_b200.util import Curry
+
+    feat = Multifeaturize([id_feat, Curry(gb_feat, inner=0.0, outer=8.0, width=1.0, n_basis=4)])
+    coords, forces = synth_trajectory_host(topo, 2100, seed=79)
+    want, _ = _feat_grams(coords, forces, topo, False, featurizer=feat)
+    got, _ = _feat_grams(coords, forces, topo, True, featurizer=feat)
+    assert got.shape == (10, 481, 481)
+    for bead in range(10):
+        assert rel_fro(got[bead], want[bead]) < 1e-9
