@@ -139,33 +139,45 @@ __global__ void __launch_bounds__(256) pair_screen_kernel(const T* __restrict__ 
                                                           double* __restrict__ m2) {
   __shared__ double red[2][8][32];
   const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
-  const int j = blockIdx.x * 32 + lane;
   const int i = blockIdx.y;
-  const bool live = j < n_sites && !(self && i >= j);
-  double s1 = 0.0, s2 = 0.0;
-  if (live) {
-    const double c = pair_dist<T>(other + (int64_t)i * 3, xyz + (int64_t)j * 3);  // frame 0
-    for (int64_t t = slice; t < n_frames; t += 8) {
-      const double e = pair_dist<T>(other + (t * n_other + i) * 3, xyz + (t * n_sites + j) * 3) - c;
-      s1 += e;
-      s2 = fma(e, e, s2);
-    }
+  const int n_jb = (n_sites + 31) / 32;
+  // self pairs: only j > i is visited.  The blocks of row i walk the column blocks from the one holding i + 1
+  // (a block per (i, column block) meant 785 000 blocks at 5 000 sites, half of them empty: the launch rate of
+  // the blocks, not the arithmetic, set the time); block 0 of the row marks what lies to the left.
+  const int first_jb = self ? (i + 1) / 32 : 0;
+  if (blockIdx.x == 0) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    for (int j = threadIdx.x; j < min(first_jb * 32, n_sites); j += blockDim.x) m2[(int64_t)i * n_sites + j] = inf;
   }
-  red[0][slice][lane] = s1;
-  red[1][slice][lane] = s2;
-  __syncthreads();
-  if (slice == 0 && j < n_sites) {
-    double* dst = m2 + (int64_t)i * n_sites + j;
-    if (!live) {
-      *dst = __longlong_as_double(0x7ff0000000000000LL);
-      return;
+  for (int jb = first_jb + blockIdx.x; jb < n_jb; jb += gridDim.x) {
+    const int j = jb * 32 + lane;
+    const bool live = j < n_sites && !(self && i >= j);
+    double s1 = 0.0, s2 = 0.0;
+    if (live) {
+      const double c = pair_dist<T>(other + (int64_t)i * 3, xyz + (int64_t)j * 3);  // frame 0
+      for (int64_t t = slice; t < n_frames; t += 8) {
+        const double e = pair_dist<T>(other + (t * n_other + i) * 3, xyz + (t * n_sites + j) * 3) - c;
+        s1 += e;
+        s2 = fma(e, e, s2);
+      }
     }
+    __syncthreads();  // the previous column block's sums have been read
+    red[0][slice][lane] = s1;
+    red[1][slice][lane] = s2;
+    __syncthreads();
+    if (slice == 0 && j < n_sites) {
+      double* dst = m2 + (int64_t)i * n_sites + j;
+      if (!live) {
+        *dst = __longlong_as_double(0x7ff0000000000000LL);
+      } else {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) {
-      s1 += red[0][k][lane];
-      s2 += red[1][k][lane];
+        for (int k = 1; k < 8; ++k) {
+          s1 += red[0][k][lane];
+          s2 += red[1][k][lane];
+        }
+        *dst = s2 - s1 * s1 / (double)n_frames;
+      }
     }
-    *dst = s2 - s1 * s1 / (double)n_frames;
   }
 }
 
@@ -330,7 +342,8 @@ extern "C" int agf_pair_screen(const void* xyz, const void* other, int dtype, in
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool self = (other == nullptr || other == xyz);
   const int n_o = self ? n_sites : n_other;
-  dim3 grid((n_sites + 31) / 32, n_o);
+  const int n_jb = (n_sites + 31) / 32;
+  dim3 grid(n_jb < 8 ? n_jb : 8, n_o);  // up to eight blocks per row share its column blocks
   AGF_REQUIRE(grid.y <= 65535, "agf_pair_screen: too many sites in `other` (%d)", n_o);
   if (dtype == AGF_F32)
     pair_screen_kernel<float><<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(xyz),
