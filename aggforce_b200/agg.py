@@ -95,11 +95,13 @@ def _project_forces(t, coords, forces, coord_map, constrained_inds, auto, method
     dl_c: list = []  # pinned copies of the mapped arrays whose download has been started (host input only)
     dl_f: list = []
     if isinstance(coord_map, LinearMap) and coords is not None:
-        if method is qp_linear_map and not coords_in.on_host:  # [Gram][coordinate map] | QP
+        if method is qp_linear_map and not coords_in.on_host and coord_map.n_fg_sites > 1024:
+            # large fits go through cuSOLVER with host-side checks: [Gram][coordinate map] | solve
             _engine.defer(lambda: early.update(launch=coord_map._launch(coords_in, slots=slots_c)))
         elif method is qp_linear_map or method is constraint_aware_uni_map:
-            # runs while the host builds the uniform map; for host arrays its download (started inside)
-            # leaves over PCIe while the forces arrive and the fit runs
+            # runs while the host builds the uniform map or prepares the fit's launches (small fits are solved on
+            # the device: nothing later in the call would hide it better); for host arrays its download (started
+            # inside) leaves over PCIe while the forces arrive and the fit runs
             early["launch"] = coord_map._launch(coords_in, slots=slots_c, download=dl_c)
         # other methods return maps that are applied as a whole (featurised / augmented): nothing to hoist
     try:
